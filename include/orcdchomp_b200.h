@@ -1,0 +1,215 @@
+/* orcdchomp_b200.h -- C ABI of the B200-native CHOMP engine.
+ *
+ * This is the drop-in boundary for the hot path of personalrobotics/or_cdchomp:
+ *   - the batched CHOMP iteration that replaces the cd_chomp_iterate + callback
+ *     ping-pong of  src/orcdchomp_mod.cpp:2752-2830  (mod::iterate loop),
+ *     src/libcd/chomp.c:430-683 (cd_chomp_iterate) and the two OpenRAVE-bound
+ *     callbacks sphere_cost_pre / sphere_cost (src/orcdchomp_mod.cpp:968-1327);
+ *   - the signed-distance-field build  cd_grid_double_bin_sdf
+ *     (src/libcd/grid.c:637-687), the flood fill + relabel of
+ *     src/orcdchomp_mod.cpp:543-548 / src/libcd/grid_flood.c:30-111 and the
+ *     occupancy loop of src/orcdchomp_mod.cpp:498-525.
+ *
+ * Plain C types only: pointers, sizes, integer error codes.  No exceptions cross
+ * this boundary, no torch / CUDA types appear in a signature (streams and device
+ * pointers travel as void*).  All host buffers are caller-owned.  One host thread
+ * per engine handle.  Every entry point FAILS (negative code) when no CUDA device
+ * is usable -- there is no CPU fallback behind this header.
+ *
+ * (All file:line citations are relative to the reference repository root.)
+ */
+#ifndef ORCDCHOMP_B200_H
+#define ORCDCHOMP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* error codes (libcd uses -1 alloc / -2 bad type, chomp.c:47,399; grid.c:648) */
+#define OCB_OK              0
+#define OCB_ERR_ALLOC      (-1)   /* host or device allocation failed                 */
+#define OCB_ERR_ARG        (-2)   /* bad argument / unsupported configuration         */
+#define OCB_ERR_CUDA       (-3)   /* CUDA runtime error (see ocb_last_error)          */
+#define OCB_ERR_NODEVICE   (-4)   /* no usable sm_100 device: the engine refuses to run */
+#define OCB_ERR_JLIMIT     (-5)   /* a run left joint limits (chomp.c:651-655)        */
+
+const char *ocb_last_error(void);          /* thread-local, never NULL */
+const char *ocb_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* Robot description: what mod::create pulls out of OpenRAVE once per run
+ * (src/orcdchomp_mod.cpp:2104-2134 dof bookkeeping, 2148-2300 spheres,
+ * 2639-2660 limits) plus the kinematic tree that OpenRAVE's SetActiveDOFValues /
+ * Link::GetTransform / CalculateJacobian evaluate inside sphere_cost_pre
+ * (src/orcdchomp_mod.cpp:1022-1049).  Poses are libcd poses [x y z qx qy qz qw]
+ * (src/libcd/kin.c:42-52).
+ *
+ *   T_world_link[i] = T_world_link[parent[i]] o pose_parent[i] o motion_i(value_i)
+ *   value_i         = dof_coeff[i][0] * q[dof_index[i]] + dof_coeff[i][1]
+ *                     (dof_index[i] < 0: frozen joint, value_i = dof_coeff[i][1])
+ *   motion_i        = rotation by value_i about axis[i]   (OCB_JOINT_REVOLUTE)
+ *                     translation by value_i along axis[i] (OCB_JOINT_PRISMATIC)
+ *                     identity                             (OCB_JOINT_FIXED)
+ * axis[i] is a unit vector in link i's frame through that frame's origin.
+ */
+#define OCB_JOINT_FIXED     0
+#define OCB_JOINT_REVOLUTE  1
+#define OCB_JOINT_PRISMATIC 2
+
+typedef struct ocb_robot
+{
+   int n_links;                 /* link 0 is the root; parent[i] < i                  */
+   const int *parent;           /* [n_links], parent[0] = -1                          */
+   const double *pose_parent;   /* [n_links][7]                                       */
+   const int *joint_type;       /* [n_links]                                          */
+   const double *axis;          /* [n_links][3]                                       */
+   const int *dof_index;        /* [n_links] index into the active-dof vector or -1   */
+   const double *dof_coeff;     /* [n_links][2]                                       */
+   double base_pose[7];         /* world pose of link 0 (robot->GetTransform())       */
+   int n_dof;                   /* n: number of active dofs (GetActiveDOF)            */
+   const double *limit_lower;   /* [n_dof] (GetDOFLimits, mod.cpp:2639-2660)          */
+   const double *limit_upper;   /* [n_dof]                                            */
+   int n_spheres;               /* sphere table in <orcdchomp><spheres> XML order     */
+   const int *sphere_link;      /* [n_spheres] link index (run_sphere.robot_linkindex) */
+   const double *sphere_pos;    /* [n_spheres][3] pos_wrt_link                        */
+   const double *sphere_radius; /* [n_spheres]                                        */
+} ocb_robot;
+
+/* One rooted signed distance field (struct run_rsdf, mod.cpp:850-855): the grid
+ * (struct cd_grid, src/libcd/grid.h:29-41; C order grid[x*NY*NZ+y*NZ+z]) and
+ * the world pose of its frame snapshotted at create (mod.cpp:2347-2369). */
+typedef struct ocb_sdf
+{
+   int sizes[3];
+   double lengths[3];
+   double pose_world_gsdf[7];
+   const double *data;          /* host pointer, sizes[0]*sizes[1]*sizes[2] doubles   */
+} ocb_sdf;
+
+/* Per-batch parameters = the `create` command's numeric arguments and defaults
+ * (src/orcdchomp_mod.cpp:1818-1848, 1875, 1888-2079). */
+typedef struct ocb_params
+{
+   int n_points;                /* default 101; m = n_points-2 moving waypoints       */
+   int derivative;              /* D of cd_chomp_create, default 1                    */
+   double lambda;               /* default 10, must be >= 0.01                        */
+   int use_momentum;
+   int use_hmc;
+   double hmc_resample_lambda;  /* default 0.02                                       */
+   double epsilon;              /* default 0.1                                        */
+   double epsilon_self;         /* default 0.04                                       */
+   double obs_factor;           /* default 200                                        */
+   double obs_factor_self;      /* default 10                                         */
+} ocb_params;
+
+void ocb_params_default(ocb_params *p);
+
+/* ------------------------------------------------------------------------- */
+/* Engine: one per GPU (owns a stream, the resident SDFs and scratch).        */
+typedef struct ocb_engine ocb_engine;
+typedef struct ocb_batch ocb_batch;
+
+int ocb_engine_create(int device, ocb_engine **out);
+int ocb_engine_destroy(ocb_engine *e);
+/* Make the engine launch on a caller stream (cudaStream_t as void*; NULL = own). */
+int ocb_engine_set_stream(ocb_engine *e, void *cuda_stream);
+int ocb_engine_sync(ocb_engine *e);
+
+/* --- SDF residency (replaces mod::sdfs[], mod.cpp:584-586 / 716-718 / 836) --- */
+/* copies the grid to HBM; *id indexes it in later calls */
+int ocb_sdf_upload(ocb_engine *e, const ocb_sdf *sdf, int *id);
+/* adopt an SDF that already lives in HBM (e.g. the output of ocb_sdf_build_device) */
+int ocb_sdf_adopt_device(ocb_engine *e, const int sizes[3], const double lengths[3],
+                         const double pose_world_gsdf[7], const double *d_data, int *id);
+int ocb_sdf_remove(ocb_engine *e, int id);
+
+/* --- SDF build: cd_grid_double_bin_sdf (grid.c:637-687) --------------------- *
+ * obs: 0.0 = free, HUGE_VAL = obstacle (any non-zero finite value is treated as
+ * the parabola height grid.c:274-304 gives it).  sdf: > 0 in free space, < 0
+ * inside obstacles.  _host copies in/out; _device works on HBM pointers.      */
+int ocb_sdf_build_host(ocb_engine *e, const double *obs, const int sizes[3],
+                       const double lengths[3], double *sdf);
+int ocb_sdf_build_device(ocb_engine *e, const double *d_obs, const int sizes[3],
+                         const double lengths[3], double *d_sdf);
+/* squared Euclidean distance transform alone: cd_grid_double_dt_sqeuc (grid.c:462-569) */
+int ocb_dt_sqeuc_device(ocb_engine *e, const double *d_func, const int sizes[3],
+                        const double lengths[3], double *d_out);
+
+/* --- occupancy pipeline of computedistancefield (mod.cpp:386-410, 498-548) --- */
+/* Analytic stand-in for the per-voxel OpenRAVE CheckCollision(cube): a voxel is
+ * an obstacle iff the axis-aligned cube of half-extent cube_extent centred at
+ * the voxel centre (grid frame) overlaps any primitive.  Primitives are given
+ * in the GRID frame.  OCB_PRIM_BOX: pose[7] + half extents (oriented box, SAT
+ * test); OCB_PRIM_SPHERE: centre + radius.  d_grid receives 1.0 (free) or
+ * HUGE_VAL (obstacle) exactly as mod.cpp:398,522 leave it.                     */
+#define OCB_PRIM_BOX    0
+#define OCB_PRIM_SPHERE 1
+typedef struct ocb_prim
+{
+   int type;
+   double pose[7];              /* box: pose in grid frame; sphere: pose[0..2] = centre */
+   double extents[3];           /* box: half extents; sphere: extents[0] = radius       */
+} ocb_prim;
+int ocb_occupancy_device(ocb_engine *e, const ocb_prim *prims, int n_prims,
+                         const int sizes[3], const double lengths[3], double cube_extent,
+                         double *d_grid);
+/* cd_grid_flood_fill(g, 0, no wrap, replace_1_to_0) followed by the 1.0 -> HUGE_VAL
+ * relabel (grid_flood.c:30-111, mod.cpp:143-151, 543-548): 6-connected fill of
+ * the value 1.0 with 0.0 starting at index_start, then every remaining 1.0
+ * becomes HUGE_VAL.  Works in place on an HBM grid.                            */
+int ocb_flood_relabel_device(ocb_engine *e, double *d_grid, const int sizes[3],
+                             size_t index_start);
+/* whole pipeline with host buffers (what `computedistancefield` does after the
+ * AABB sizing): occupancy -> flood/relabel -> SDF.  obs_out may be NULL.       */
+int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prims, int n_prims,
+                                  const int sizes[3], const double lengths[3],
+                                  double cube_extent, double *obs_out, double *sdf_out);
+
+/* --- batched CHOMP runs (replaces struct run + cd_chomp, mod.cpp:887-966) ---- */
+/* R independent runs sharing robot, parameters and SDF set.  q_start/q_goal are
+ * [R][n_dof]; seeds [R] (gsl_rng_set seed, mod.cpp:2303-2304; may be NULL = 0).
+ * The straight-line initial trajectory is mod.cpp:2456-2458.                  */
+int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb_params *params,
+                     int n_sdfs, const int *sdf_ids, int n_runs,
+                     const double *q_start, const double *q_goal,
+                     const unsigned int *seeds, ocb_batch **out);
+/* starttraj variant (mod.cpp:2373-2415): traj is [R][n_points][n_dof] */
+int ocb_batch_set_traj(ocb_batch *b, const double *traj);
+/* n_iter CHOMP iterations per run (mod.cpp:2752-2828) followed by the cost-only
+ * pass (mod.cpp:2830).  Outputs are [R], each may be NULL.  cost_* are
+ * chomp.c:679-681 of the FINAL cost-only pass; status[r] is 0 or OCB_ERR_JLIMIT.
+ * Returns OCB_OK even if individual runs hit OCB_ERR_JLIMIT.                  */
+int ocb_batch_iterate(ocb_batch *b, int n_iter, double *cost_total, double *cost_obs,
+                      double *cost_smooth, int *status);
+/* asynchronous form: enqueue only (results stay on the device) */
+int ocb_batch_iterate_async(ocb_batch *b, int n_iter);
+int ocb_batch_get_costs(ocb_batch *b, double *cost_total, double *cost_obs,
+                        double *cost_smooth, int *status);
+/* per-iteration cost log of the last iterate call: [R][n_iter][3] (total, obs,
+ * smooth) as RAVELOG_INFO prints them (mod.cpp:2798).  Enable before iterate. */
+int ocb_batch_enable_trace(ocb_batch *b, int enable);
+int ocb_batch_get_trace(ocb_batch *b, double *trace, int n_iter);
+/* gettraj (numeric part of mod.cpp:2897-2903): [R][n_points][n_dof] */
+int ocb_batch_get_traj(ocb_batch *b, double *traj);
+/* G of the most recent iteration (chomp.c:474-522: obstacle gradient / m + A T + B),
+ * [R][m][n_dof]; and the raw obstacle gradient before smoothing when
+ * obstacle_only != 0 (sum of c_grad rows, scaled by 1/m).  Parity hooks.      */
+int ocb_batch_get_gradient(ocb_batch *b, double *G, int obstacle_only);
+/* arg-min of cost_total over this batch's runs after iterate (device reduction) */
+int ocb_batch_best(ocb_batch *b, int *best_run, double *best_cost);
+int ocb_batch_destroy(ocb_batch *b);
+/* sizes for callers that allocate outputs */
+int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof);
+/* device pointers (HBM) of the trajectory [R][n_points][n_dof] and costs [R][3],
+ * for callers that keep everything resident (bench, NCCL gather)              */
+int ocb_batch_device_ptrs(ocb_batch *b, void **d_traj, void **d_costs);
+/* kernel launches issued by this engine since creation (bench bookkeeping)    */
+long ocb_engine_launch_count(const ocb_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORCDCHOMP_B200_H */
