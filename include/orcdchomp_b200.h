@@ -194,10 +194,12 @@ int ocb_batch_enable_trace(ocb_batch *b, int enable);
 int ocb_batch_get_trace(ocb_batch *b, double *trace, int n_iter);
 /* gettraj (numeric part of mod.cpp:2897-2903): [R][n_points][n_dof] */
 int ocb_batch_get_traj(ocb_batch *b, double *traj);
-/* G of the most recent iteration (chomp.c:474-522: obstacle gradient / m + A T + B),
- * [R][m][n_dof]; and the raw obstacle gradient before smoothing when
- * obstacle_only != 0 (sum of c_grad rows, scaled by 1/m).  Parity hooks.      */
-int ocb_batch_get_gradient(ocb_batch *b, double *G, int obstacle_only);
+/* Parity hook: capture, during subsequent iterate calls, the gradient of the most
+ * recent iteration, [R][m][n_dof].  mode 1: G after chomp.c:515-522 (obstacle
+ * gradient / m + A T + B); mode 2: the obstacle/self-collision part alone (sum of
+ * the c_grad rows of sphere_cost scaled by 1/m, chomp.c:474-492); mode 0: off. */
+int ocb_batch_capture_gradient(ocb_batch *b, int mode);
+int ocb_batch_get_gradient(ocb_batch *b, double *G);
 /* arg-min of cost_total over this batch's runs after iterate (device reduction) */
 int ocb_batch_best(ocb_batch *b, int *best_run, double *best_cost);
 int ocb_batch_destroy(ocb_batch *b);

@@ -1,0 +1,1157 @@
+/* ocb_engine.cu -- host side of the C ABI (include/orcdchomp_b200.h).
+ *
+ * Owns device memory, compiles the robot description into the joint-frame form
+ * the kernels consume, builds the smoothness metric (band of A, its LDL^T
+ * factor, the B / trC coefficients) and launches the sm_100a kernels.  No numeric
+ * hot-path work happens on the host: everything per-iteration is in
+ * chomp_kernel.cu, everything per-voxel in sdf_kernels.cu.
+ *
+ * Reference counterparts (paths relative to the reference root):
+ *   numeric part of mod::create          src/orcdchomp_mod.cpp:2266-2299, 2315-2369,
+ *                                         2417-2464, 2521, 2567-2580, 2617-2664
+ *   cd_chomp_create / add_KEs / init     src/libcd/chomp.c:40-178, 239-340, 342-428
+ *   mod::iterate / gettraj / destroy     src/orcdchomp_mod.cpp:2690-2852, 2897-2903, 3039-3066
+ *   computedistancefield / addfield      src/orcdchomp_mod.cpp:297-589, 592-722
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/orcdchomp_b200.h"
+#include "ocb_internal.h"
+
+/* ------------------------------------------------------------------ errors */
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+   va_end(ap);
+   return code;
+}
+
+#define CU(call)                                                                              \
+   do                                                                                         \
+   {                                                                                          \
+      cudaError_t e__ = (call);                                                               \
+      if (e__ != cudaSuccess)                                                                 \
+         return fail(OCB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+   } while (0)
+
+extern "C" const char *ocb_last_error(void) { return g_err; }
+extern "C" const char *ocb_version(void) { return "or_cdchomp_b200 0.1 (sm_100a)"; }
+
+extern "C" void ocb_params_default(ocb_params *p)
+{
+   /* src/orcdchomp_mod.cpp:1818-1848, 1875 */
+   p->n_points = 101;
+   p->derivative = 1;
+   p->lambda = 10.0;
+   p->use_momentum = 0;
+   p->use_hmc = 0;
+   p->hmc_resample_lambda = 0.02;
+   p->epsilon = 0.1;
+   p->epsilon_self = 0.04;
+   p->obs_factor = 200.0;
+   p->obs_factor_self = 10.0;
+}
+
+/* ------------------------------------------------------------ small algebra */
+namespace
+{
+struct Xf
+{
+   double R[9]; /* row-major */
+   double t[3];
+};
+
+Xf xf_identity()
+{
+   Xf x;
+   for (int i = 0; i < 9; i++) x.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+   x.t[0] = x.t[1] = x.t[2] = 0.0;
+   return x;
+}
+
+/* rotation matrix of a libcd pose quaternion; entries are the expansion terms of
+ * cd_kin_pose_compos (src/libcd/kin.c:192-210) so R p reproduces its products */
+void quat_to_R(const double *q, double *R)
+{
+   const double qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+   const double qx2 = qx * qx, qy2 = qy * qy, qz2 = qz * qz, qw2 = qw * qw;
+   const double qxqy = qx * qy, qxqz = qx * qz, qxqw = qx * qw;
+   const double qyqz = qy * qz, qyqw = qy * qw, qzqw = qz * qw;
+   R[0] = qx2 - qy2 - qz2 + qw2; R[1] = 2 * (qxqy - qzqw);      R[2] = 2 * (qxqz + qyqw);
+   R[3] = 2 * (qxqy + qzqw);     R[4] = -qx2 + qy2 - qz2 + qw2; R[5] = 2 * (qyqz - qxqw);
+   R[6] = 2 * (qxqz - qyqw);     R[7] = 2 * (qyqz + qxqw);      R[8] = -qx2 - qy2 + qz2 + qw2;
+}
+
+Xf xf_from_pose(const double *pose)
+{
+   Xf x;
+   quat_to_R(pose + 3, x.R);
+   x.t[0] = pose[0]; x.t[1] = pose[1]; x.t[2] = pose[2];
+   return x;
+}
+
+Xf xf_mul(const Xf &a, const Xf &b)
+{
+   Xf c;
+   for (int r = 0; r < 3; r++)
+   {
+      for (int k = 0; k < 3; k++)
+         c.R[3 * r + k] = a.R[3 * r] * b.R[k] + a.R[3 * r + 1] * b.R[3 + k] + a.R[3 * r + 2] * b.R[6 + k];
+      c.t[r] = a.R[3 * r] * b.t[0] + a.R[3 * r + 1] * b.t[1] + a.R[3 * r + 2] * b.t[2] + a.t[r];
+   }
+   return c;
+}
+
+void xf_apply(const Xf &a, const double *p, double *out)
+{
+   for (int r = 0; r < 3; r++) out[r] = a.R[3 * r] * p[0] + a.R[3 * r + 1] * p[1] + a.R[3 * r + 2] * p[2] + a.t[r];
+}
+
+/* rotation Q with Q e_z = axis (unit) */
+Xf xf_align_z(const double *axis)
+{
+   double a[3] = {axis[0], axis[1], axis[2]};
+   const double len = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+   for (int i = 0; i < 3; i++) a[i] /= len;
+   Xf q = xf_identity();
+   if (fabs(a[0]) < 1e-15 && fabs(a[1]) < 1e-15 && a[2] > 0) return q;
+   double h[3] = {0, 0, 0};
+   int smallest = 0;
+   if (fabs(a[1]) < fabs(a[smallest])) smallest = 1;
+   if (fabs(a[2]) < fabs(a[smallest])) smallest = 2;
+   h[smallest] = 1.0;
+   double u[3] = {h[1] * a[2] - h[2] * a[1], h[2] * a[0] - h[0] * a[2], h[0] * a[1] - h[1] * a[0]};
+   const double ul = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+   for (int i = 0; i < 3; i++) u[i] /= ul;
+   double w[3] = {a[1] * u[2] - a[2] * u[1], a[2] * u[0] - a[0] * u[2], a[0] * u[1] - a[1] * u[0]};
+   for (int r = 0; r < 3; r++)
+   {
+      q.R[3 * r] = u[r];
+      q.R[3 * r + 1] = w[r];
+      q.R[3 * r + 2] = a[r];
+   }
+   return q;
+}
+
+Xf xf_transpose_rot(const Xf &a)
+{
+   Xf c = xf_identity();
+   for (int r = 0; r < 3; r++)
+      for (int k = 0; k < 3; k++) c.R[3 * r + k] = a.R[3 * k + r];
+   return c;
+}
+
+Xf xf_motion(int type, const double *axis, double value)
+{
+   Xf x = xf_identity();
+   if (type == OCB_JOINT_REVOLUTE)
+   {
+      const double s = sin(0.5 * value), c = cos(0.5 * value);
+      const double q[4] = {axis[0] * s, axis[1] * s, axis[2] * s, c};
+      quat_to_R(q, x.R);
+   }
+   else if (type == OCB_JOINT_PRISMATIC)
+      for (int i = 0; i < 3; i++) x.t[i] = axis[i] * value;
+   return x;
+}
+
+template <class T>
+int dev_upload(T **dptr, const std::vector<T> &h)
+{
+   *dptr = nullptr;
+   const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+   if (cudaMalloc((void **) dptr, bytes) != cudaSuccess) return -1;
+   if (!h.empty() && cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+      return -1;
+   return 0;
+}
+} /* namespace */
+
+/* ------------------------------------------------------------------ engine */
+struct SdfSlot
+{
+   bool used = false;
+   bool owned = false;
+   double *d_data = nullptr;
+   int sizes[3] = {0, 0, 0};
+   double lengths[3] = {0, 0, 0};
+   double pose[7] = {0, 0, 0, 0, 0, 0, 1};
+};
+
+struct ocb_engine
+{
+   int device = 0;
+   cudaStream_t own_stream = nullptr;
+   cudaStream_t stream = nullptr;
+   std::vector<SdfSlot> sdfs;
+   void *scratch = nullptr;
+   size_t scratch_bytes = 0;
+   long launches = 0;
+   int smem_optin = 0;
+   int sm_count = 0;
+};
+
+static int engine_scratch(ocb_engine *e, size_t bytes)
+{
+   if (bytes <= e->scratch_bytes) return OCB_OK;
+   if (e->scratch) cudaFree(e->scratch);
+   e->scratch = nullptr;
+   e->scratch_bytes = 0;
+   if (cudaMalloc(&e->scratch, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu scratch bytes failed", bytes);
+   }
+   e->scratch_bytes = bytes;
+   return OCB_OK;
+}
+
+extern "C" int ocb_engine_create(int device, ocb_engine **out)
+{
+   if (!out) return fail(OCB_ERR_ARG, "null out pointer");
+   *out = nullptr;
+   int count = 0;
+   cudaError_t err = cudaGetDeviceCount(&count);
+   if (err != cudaSuccess || count == 0)
+   {
+      cudaGetLastError();
+      return fail(OCB_ERR_NODEVICE, "no CUDA device (%s); this engine has no CPU path",
+                  err == cudaSuccess ? "count = 0" : cudaGetErrorString(err));
+   }
+   if (device < 0 || device >= count) return fail(OCB_ERR_ARG, "device %d out of range (%d)", device, count);
+   cudaDeviceProp prop;
+   CU(cudaGetDeviceProperties(&prop, device));
+   if (prop.major < 10)
+      return fail(OCB_ERR_NODEVICE, "device %d is sm_%d%d; this build carries sm_100a code only", device,
+                  prop.major, prop.minor);
+   CU(cudaSetDevice(device));
+   ocb_engine *e = new (std::nothrow) ocb_engine();
+   if (!e) return fail(OCB_ERR_ALLOC, "out of host memory");
+   e->device = device;
+   e->smem_optin = (int) prop.sharedMemPerBlockOptin;
+   e->sm_count = prop.multiProcessorCount;
+   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+   {
+      delete e;
+      return fail(OCB_ERR_CUDA, "cudaStreamCreate failed");
+   }
+   e->stream = e->own_stream;
+   *out = e;
+   return OCB_OK;
+}
+
+extern "C" int ocb_engine_destroy(ocb_engine *e)
+{
+   if (!e) return OCB_OK;
+   cudaSetDevice(e->device);
+   cudaStreamSynchronize(e->stream);
+   for (auto &s : e->sdfs)
+      if (s.used && s.owned) cudaFree(s.d_data);
+   if (e->scratch) cudaFree(e->scratch);
+   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+   delete e;
+   return OCB_OK;
+}
+
+extern "C" int ocb_engine_set_stream(ocb_engine *e, void *cuda_stream)
+{
+   if (!e) return fail(OCB_ERR_ARG, "null engine");
+   cudaStreamSynchronize(e->stream);
+   e->stream = cuda_stream ? (cudaStream_t) cuda_stream : e->own_stream;
+   return OCB_OK;
+}
+
+extern "C" int ocb_engine_sync(ocb_engine *e)
+{
+   if (!e) return fail(OCB_ERR_ARG, "null engine");
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->stream));
+   return OCB_OK;
+}
+
+extern "C" long ocb_engine_launch_count(const ocb_engine *e) { return e ? e->launches : 0; }
+
+/* --------------------------------------------------------------------- SDFs */
+static int sdf_slot_new(ocb_engine *e)
+{
+   for (size_t i = 0; i < e->sdfs.size(); i++)
+      if (!e->sdfs[i].used) return (int) i;
+   e->sdfs.push_back(SdfSlot());
+   return (int) e->sdfs.size() - 1;
+}
+
+static int check_grid(const int sizes[3], const double lengths[3])
+{
+   for (int i = 0; i < 3; i++)
+   {
+      if (sizes[i] < 2) return fail(OCB_ERR_ARG, "grid size %d on axis %d (need >= 2; grid.c:352 indexes a neighbour)", sizes[i], i);
+      if (!(lengths[i] > 0.0)) return fail(OCB_ERR_ARG, "grid length must be positive");
+      if (sizes[i] > 46340) return fail(OCB_ERR_ARG, "grid axis longer than 46340 cells (q*q overflows int, grid.c:298)");
+   }
+   return OCB_OK;
+}
+
+extern "C" int ocb_sdf_upload(ocb_engine *e, const ocb_sdf *sdf, int *id)
+{
+   if (!e || !sdf || !id || !sdf->data) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sdf->sizes, sdf->lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   const size_t cells = (size_t) sdf->sizes[0] * sdf->sizes[1] * sdf->sizes[2];
+   double *d = nullptr;
+   if (cudaMalloc((void **) &d, cells * sizeof(double)) != cudaSuccess)
+   {
+      cudaGetLastError();
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu SDF bytes failed", cells * sizeof(double));
+   }
+   cudaError_t err = cudaMemcpyAsync(d, sdf->data, cells * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+   if (err != cudaSuccess)
+   {
+      cudaFree(d);
+      return fail(OCB_ERR_CUDA, "SDF upload: %s", cudaGetErrorString(err));
+   }
+   const int slot = sdf_slot_new(e);
+   SdfSlot &s = e->sdfs[slot];
+   s.used = true;
+   s.owned = true;
+   s.d_data = d;
+   for (int i = 0; i < 3; i++) { s.sizes[i] = sdf->sizes[i]; s.lengths[i] = sdf->lengths[i]; }
+   memcpy(s.pose, sdf->pose_world_gsdf, sizeof(s.pose));
+   *id = slot;
+   return OCB_OK;
+}
+
+extern "C" int ocb_sdf_adopt_device(ocb_engine *e, const int sizes[3], const double lengths[3],
+                                    const double pose_world_gsdf[7], const double *d_data, int *id)
+{
+   if (!e || !d_data || !id) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   const int slot = sdf_slot_new(e);
+   SdfSlot &s = e->sdfs[slot];
+   s.used = true;
+   s.owned = false;
+   s.d_data = const_cast<double *>(d_data);
+   for (int i = 0; i < 3; i++) { s.sizes[i] = sizes[i]; s.lengths[i] = lengths[i]; }
+   memcpy(s.pose, pose_world_gsdf, sizeof(s.pose));
+   *id = slot;
+   return OCB_OK;
+}
+
+extern "C" int ocb_sdf_remove(ocb_engine *e, int id)
+{
+   if (!e || id < 0 || id >= (int) e->sdfs.size() || !e->sdfs[id].used) return fail(OCB_ERR_ARG, "bad sdf id %d", id);
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->stream));
+   if (e->sdfs[id].owned) cudaFree(e->sdfs[id].d_data);
+   e->sdfs[id] = SdfSlot();
+   return OCB_OK;
+}
+
+extern "C" int ocb_dt_sqeuc_device(ocb_engine *e, const double *d_func, const int sizes[3],
+                                   const double lengths[3], double *d_out)
+{
+   if (!e || !d_func || !d_out) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   rc = engine_scratch(e, ocb_dt_scratch_bytes(sizes));
+   if (rc) return rc;
+   CU(ocb_launch_dt_sqeuc(d_func, d_out, sizes, lengths, e->scratch, e->scratch_bytes, e->stream, &e->launches));
+   return OCB_OK;
+}
+
+extern "C" int ocb_sdf_build_device(ocb_engine *e, const double *d_obs, const int sizes[3],
+                                    const double lengths[3], double *d_sdf)
+{
+   if (!e || !d_obs || !d_sdf) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   rc = engine_scratch(e, ocb_sdf_scratch_bytes(sizes, lengths));
+   if (rc) return rc;
+   CU(ocb_launch_bin_sdf(d_obs, d_sdf, sizes, lengths, e->scratch, e->scratch_bytes, e->stream, &e->launches));
+   return OCB_OK;
+}
+
+extern "C" int ocb_sdf_build_host(ocb_engine *e, const double *obs, const int sizes[3],
+                                  const double lengths[3], double *sdf)
+{
+   if (!e || !obs || !sdf) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
+   double *d_in = nullptr, *d_out = nullptr;
+   if (cudaMalloc((void **) &d_in, bytes) != cudaSuccess || cudaMalloc((void **) &d_out, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      cudaFree(d_in);
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of 2 x %zu bytes failed", bytes);
+   }
+   cudaError_t err = cudaMemcpyAsync(d_in, obs, bytes, cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess)
+   {
+      rc = ocb_sdf_build_device(e, d_in, sizes, lengths, d_out);
+      if (rc == OCB_OK)
+      {
+         err = cudaMemcpyAsync(sdf, d_out, bytes, cudaMemcpyDeviceToHost, e->stream);
+         if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+      }
+   }
+   cudaFree(d_in);
+   cudaFree(d_out);
+   if (rc) return rc;
+   if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "sdf_build_host: %s", cudaGetErrorString(err));
+   return OCB_OK;
+}
+
+extern "C" int ocb_occupancy_device(ocb_engine *e, const ocb_prim *prims, int n_prims, const int sizes[3],
+                                    const double lengths[3], double cube_extent, double *d_grid)
+{
+   if (!e || !d_grid || (n_prims > 0 && !prims)) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   rc = engine_scratch(e, std::max<size_t>(1, n_prims) * sizeof(ocb_prim));
+   if (rc) return rc;
+   if (n_prims > 0)
+      CU(cudaMemcpyAsync(e->scratch, prims, n_prims * sizeof(ocb_prim), cudaMemcpyHostToDevice, e->stream));
+   CU(ocb_launch_occupancy(e->scratch, n_prims, sizes, lengths, cube_extent, d_grid, e->stream));
+   e->launches++;
+   /* the primitives live in the shared scratch: finish before anyone reuses it */
+   CU(cudaStreamSynchronize(e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_flood_relabel_device(ocb_engine *e, double *d_grid, const int sizes[3], size_t index_start)
+{
+   if (!e || !d_grid) return fail(OCB_ERR_ARG, "null argument");
+   const size_t cells = (size_t) sizes[0] * sizes[1] * sizes[2];
+   if (index_start >= cells) return fail(OCB_ERR_ARG, "flood start outside the grid");
+   CU(cudaSetDevice(e->device));
+   int rc = engine_scratch(e, ocb_flood_scratch_bytes(sizes));
+   if (rc) return rc;
+   CU(ocb_launch_flood_relabel(d_grid, sizes, index_start, e->scratch, e->scratch_bytes, e->stream, &e->launches));
+   return OCB_OK;
+}
+
+extern "C" int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prims, int n_prims,
+                                             const int sizes[3], const double lengths[3],
+                                             double cube_extent, double *obs_out, double *sdf_out)
+{
+   if (!e) return fail(OCB_ERR_ARG, "null engine");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
+   double *d_obs = nullptr, *d_sdf = nullptr;
+   if (cudaMalloc((void **) &d_obs, bytes) != cudaSuccess || cudaMalloc((void **) &d_sdf, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      cudaFree(d_obs);
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of 2 x %zu bytes failed", bytes);
+   }
+   rc = ocb_occupancy_device(e, prims, n_prims, sizes, lengths, cube_extent, d_obs);
+   if (rc == OCB_OK) rc = ocb_flood_relabel_device(e, d_obs, sizes, 0);
+   cudaError_t err = cudaSuccess;
+   if (rc == OCB_OK && obs_out) err = cudaMemcpyAsync(obs_out, d_obs, bytes, cudaMemcpyDeviceToHost, e->stream);
+   if (rc == OCB_OK && err == cudaSuccess && sdf_out)
+   {
+      rc = ocb_sdf_build_device(e, d_obs, sizes, lengths, d_sdf);
+      if (rc == OCB_OK) err = cudaMemcpyAsync(sdf_out, d_sdf, bytes, cudaMemcpyDeviceToHost, e->stream);
+   }
+   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+   cudaFree(d_obs);
+   cudaFree(d_sdf);
+   if (rc) return rc;
+   if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "computedistancefield_host: %s", cudaGetErrorString(err));
+   return OCB_OK;
+}
+
+/* -------------------------------------------------------------------- batch */
+struct ocb_batch
+{
+   ocb_engine *e = nullptr;
+   OcbChompArgs args;
+   int threads = 128;
+   size_t smem = 0;
+   int trace_cap = 0; /* iterations the trace buffer can hold */
+   int last_n_iter = 0;
+   std::vector<void *> owned; /* device allocations to free */
+   double *d_start = nullptr, *d_goal = nullptr;
+};
+
+namespace
+{
+/* sparse row of a finite-difference operator */
+typedef std::vector<std::pair<int, double>> SRow;
+
+void srow_axpy(SRow &dst, double alpha, const SRow &src)
+{
+   for (const auto &e : src)
+   {
+      bool found = false;
+      for (auto &d : dst)
+         if (d.first == e.first) { d.second += alpha * e.second; found = true; break; }
+      if (!found) dst.push_back(std::make_pair(e.first, alpha * e.second));
+   }
+}
+
+/* Smoothness metric of cd_chomp_add_KEs (chomp.c:239-340) for the module's
+ * set-up (inits[d] / finals[d] all present, only d = 0 non-zero: mod.cpp:2578-2580,
+ * chomp.c:131-141), kept in banded / coefficient form:
+ *   A    = sum_d w_d/N_d K_d^T K_d                    -> band [m][2D+1]
+ *   B    = sum_d w_d/N_d K_d^T E_d = bi (x) q_start + bf (x) q_goal
+ *   trC  = 1/2 (ss |q_s|^2 + 2 sg q_s.q_g + gg |q_g|^2)                       */
+struct Metric
+{
+   int m, bw;
+   std::vector<double> Aband, Lband, dinv, bi, bf;
+   double ss, sg, gg;
+};
+
+int build_metric(int m, int D, double dt, Metric &M)
+{
+   M.m = m;
+   M.bw = D;
+   const int bw = D;
+   M.Aband.assign((size_t) m * (2 * bw + 1), 0.0);
+   M.bi.assign(m, 0.0);
+   M.bf.assign(m, 0.0);
+   M.ss = M.sg = M.gg = 0.0;
+   std::vector<double> wds(D);
+   for (int d = 0; d < D; d++) wds[d] = (d < D - 1) ? 0.0 : 1.0; /* chomp.c:127-128 */
+
+   std::vector<SRow> Kprev; /* identity on the m moving points (N_{-1} = m) */
+   std::vector<double> ciprev, cfprev;
+   int prev = m;
+   for (int d = 0; d < D; d++)
+   {
+      const int cur = prev + 1; /* prev - 1 + init row + final row */
+      std::vector<SRow> K(cur);
+      std::vector<double> ci(cur, 0.0), cf(cur, 0.0);
+      /* rows of the differencing matrix: (col, value) pairs over the previous level */
+      for (int r = 0; r < cur; r++)
+      {
+         SRow diff;
+         if (r == 0) diff.push_back(std::make_pair(0, 1.0 / dt));
+         else if (r == cur - 1) diff.push_back(std::make_pair(prev - 1, -1.0 / dt));
+         else
+         {
+            diff.push_back(std::make_pair(r - 1, -1.0 / dt));
+            diff.push_back(std::make_pair(r, 1.0 / dt));
+         }
+         for (const auto &e : diff)
+         {
+            if (d == 0)
+               K[r].push_back(std::make_pair(e.first, e.second));
+            else
+            {
+               srow_axpy(K[r], e.second, Kprev[e.first]);
+               ci[r] += e.second * ciprev[e.first];
+               cf[r] += e.second * cfprev[e.first];
+            }
+         }
+      }
+      if (d == 0)
+      {
+         ci[0] += -1.0 / dt;      /* E row 0   = -inits[0]/dt  (chomp.c:281) */
+         cf[cur - 1] += 1.0 / dt; /* E row N-1 = +finals[0]/dt (chomp.c:295) */
+      }
+      const double w = wds[d] / cur;
+      /* S = K^T K accumulated over rows, then A += w S (dgemm alpha, chomp.c:318-320) */
+      std::vector<double> S((size_t) m * (2 * bw + 1), 0.0), sbi(m, 0.0), sbf(m, 0.0);
+      double sss = 0, ssg = 0, sgg = 0;
+      for (int r = 0; r < cur; r++)
+      {
+         for (const auto &e1 : K[r])
+         {
+            for (const auto &e2 : K[r])
+            {
+               const int off = e2.first - e1.first;
+               if (off < -bw || off > bw) return -1;
+               S[(size_t) e1.first * (2 * bw + 1) + off + bw] += e1.second * e2.second;
+            }
+            sbi[e1.first] += e1.second * ci[r];
+            sbf[e1.first] += e1.second * cf[r];
+         }
+         sss += ci[r] * ci[r];
+         ssg += ci[r] * cf[r];
+         sgg += cf[r] * cf[r];
+      }
+      for (size_t k = 0; k < S.size(); k++) M.Aband[k] += w * S[k];
+      for (int i = 0; i < m; i++) { M.bi[i] += w * sbi[i]; M.bf[i] += w * sbf[i]; }
+      M.ss += w * sss;
+      M.sg += w * ssg;
+      M.gg += w * sgg;
+      Kprev.swap(K);
+      ciprev.swap(ci);
+      cfprev.swap(cf);
+      prev = cur;
+   }
+   /* banded LDL^T of A (stands in for dgetrf/dgetri, chomp.c:393-403) */
+   M.Lband.assign((size_t) m * bw, 0.0);
+   M.dinv.assign(m, 0.0);
+   std::vector<double> dd(m, 0.0);
+   auto A = [&](int i, int k) { return M.Aband[(size_t) i * (2 * bw + 1) + (k - i) + bw]; };
+   auto L = [&](int i, int k) -> double & { return M.Lband[(size_t) i * bw + (i - k - 1)]; };
+   for (int i = 0; i < m; i++)
+   {
+      for (int j = std::max(0, i - bw); j < i; j++)
+      {
+         double acc = A(i, j);
+         for (int p = std::max(0, i - bw); p < j; p++)
+            if (j - p <= bw) acc -= L(i, p) * dd[p] * L(j, p);
+         L(i, j) = acc / dd[j];
+      }
+      double acc = A(i, i);
+      for (int p = std::max(0, i - bw); p < i; p++) acc -= L(i, p) * L(i, p) * dd[p];
+      if (!(acc > 0.0)) return -2;
+      dd[i] = acc;
+      M.dinv[i] = 1.0 / acc;
+   }
+   return 0;
+}
+
+struct CompiledRobot
+{
+   std::vector<OcbJointDev> joints;
+   std::vector<OcbSphereDev> spheres;
+   std::vector<OcbPairDev> pairs;
+   std::vector<OcbAncDev> ancs;
+   std::vector<double> inactive_pos;
+   std::vector<double> inactive_radius;
+   std::vector<int> inactive_link;
+   int n_slots = 0;
+};
+
+/* Fold fixed / frozen links into joint frames with the moving axis on local z.
+ * Replaces the OpenRAVE-side bookkeeping of mod::create (mod.cpp:2148-2300) and
+ * prepares what sphere_cost_pre asks OpenRAVE for on every waypoint. */
+int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
+{
+   const int nl = rb->n_links;
+   if (nl < 1 || rb->n_dof < 1) return fail(OCB_ERR_ARG, "robot needs links and active dofs");
+   std::vector<int> anchor(nl, -1);  /* nearest moving ancestor-or-self (index in `raw` joints) */
+   std::vector<Xf> rel(nl);          /* link frame expressed in its anchor's joint frame (or world) */
+   struct RawJoint { int parent; Xf X; int type, dof; double c0, c1; int link; };
+   std::vector<RawJoint> raw;
+   rel[0] = xf_from_pose(rb->base_pose);
+   for (int i = 1; i < nl; i++)
+   {
+      const int p = rb->parent[i];
+      if (p < 0 || p >= i) return fail(OCB_ERR_ARG, "link %d: parent must precede it", i);
+      const Xf Xp = xf_mul(rel[p], xf_from_pose(rb->pose_parent + 7 * i));
+      const int type = rb->joint_type[i];
+      const bool moving = (type != OCB_JOINT_FIXED) && rb->dof_index[i] >= 0;
+      if (moving)
+      {
+         if (rb->dof_index[i] >= rb->n_dof) return fail(OCB_ERR_ARG, "link %d: dof index out of range", i);
+         const Xf Q = xf_align_z(rb->axis + 3 * i);
+         RawJoint J;
+         J.parent = anchor[p];
+         J.X = xf_mul(Xp, Q);
+         J.type = type;
+         J.dof = rb->dof_index[i];
+         J.c0 = rb->dof_coeff[2 * i];
+         J.c1 = rb->dof_coeff[2 * i + 1];
+         J.link = i;
+         raw.push_back(J);
+         anchor[i] = (int) raw.size() - 1;
+         rel[i] = xf_transpose_rot(Q);
+      }
+      else
+      {
+         anchor[i] = anchor[p];
+         rel[i] = xf_mul(Xp, xf_motion(type, rb->axis + 3 * i, rb->dof_coeff[2 * i + 1]));
+      }
+   }
+   const int nj = (int) raw.size();
+   if (nj == 0) return fail(OCB_ERR_ARG, "no moving joints");
+   if (nj > OCB_MAX_JOINTS) return fail(OCB_ERR_ARG, "%d moving joints (max %d)", nj, OCB_MAX_JOINTS);
+
+   /* depth-first order so a child usually follows its parent directly */
+   std::vector<int> order, newidx(nj, -1);
+   {
+      std::vector<std::vector<int>> kids(nj);
+      std::vector<int> roots;
+      for (int j = 0; j < nj; j++)
+         if (raw[j].parent < 0) roots.push_back(j);
+         else kids[raw[j].parent].push_back(j);
+      std::vector<int> stack(roots.rbegin(), roots.rend());
+      while (!stack.empty())
+      {
+         const int j = stack.back();
+         stack.pop_back();
+         newidx[j] = (int) order.size();
+         order.push_back(j);
+         for (auto it = kids[j].rbegin(); it != kids[j].rend(); ++it) stack.push_back(*it);
+      }
+   }
+   C.joints.assign(nj, OcbJointDev());
+   std::vector<int> slot_of(nj, -1);
+   C.n_slots = 0;
+   for (int k = 0; k < nj; k++)
+   {
+      const RawJoint &J = raw[order[k]];
+      OcbJointDev &D = C.joints[k];
+      memcpy(D.XR, J.X.R, sizeof(D.XR));
+      memcpy(D.Xt, J.X.t, sizeof(D.Xt));
+      D.c0 = J.c0;
+      D.c1 = J.c1;
+      D.type = J.type;
+      D.dof = J.dof;
+      D.save = -1;
+      const int par = (J.parent < 0) ? -1 : newidx[J.parent];
+      if (par < 0) D.load = OCB_LOAD_BASE;
+      else if (par == k - 1) D.load = OCB_LOAD_PREV;
+      else
+      {
+         if (slot_of[par] < 0) { slot_of[par] = C.n_slots++; C.joints[par].save = slot_of[par]; }
+         D.load = slot_of[par];
+      }
+   }
+   /* ancestors (self first, then up the tree) */
+   for (int k = 0; k < nj; k++)
+   {
+      C.joints[k].anc_begin = (int) C.ancs.size();
+      for (int j = order[k]; j >= 0; j = raw[j].parent)
+      {
+         OcbAncDev A;
+         A.c0 = raw[j].c0;
+         A.joint = newidx[j];
+         A.dof = raw[j].dof;
+         A.type = raw[j].type;
+         A.pad = 0;
+         C.ancs.push_back(A);
+      }
+      C.joints[k].anc_end = (int) C.ancs.size();
+   }
+   /* spheres: active ones grouped by joint (stable), inactive ones frozen in the world */
+   struct Tmp { int joint; OcbSphereDev s; };
+   std::vector<Tmp> act;
+   for (int s = 0; s < rb->n_spheres; s++)
+   {
+      const int link = rb->sphere_link[s];
+      if (link < 0 || link >= nl) return fail(OCB_ERR_ARG, "sphere %d: bad link", s);
+      double p[3];
+      xf_apply(rel[link], rb->sphere_pos + 3 * s, p);
+      if (anchor[link] >= 0)
+      {
+         Tmp t;
+         t.joint = newidx[anchor[link]];
+         t.s.pos[0] = p[0]; t.s.pos[1] = p[1]; t.s.pos[2] = p[2];
+         t.s.radius = rb->sphere_radius[s];
+         t.s.link = link;
+         t.s.pair_begin = t.s.pair_end = 0;
+         act.push_back(t);
+      }
+      else
+      {
+         C.inactive_pos.push_back(p[0]);
+         C.inactive_pos.push_back(p[1]);
+         C.inactive_pos.push_back(p[2]);
+         C.inactive_radius.push_back(rb->sphere_radius[s]);
+         C.inactive_link.push_back(link);
+      }
+   }
+   if (act.empty()) return fail(OCB_ERR_ARG, "robot active dofs must have at least one sphere!");
+   std::stable_sort(act.begin(), act.end(), [](const Tmp &a, const Tmp &b) { return a.joint < b.joint; });
+   for (int k = 0; k < nj; k++) C.joints[k].sph_begin = C.joints[k].sph_end = 0;
+   for (size_t i = 0; i < act.size(); i++) C.spheres.push_back(act[i].s);
+   for (int k = 0, i = 0; k < nj; k++)
+   {
+      C.joints[k].sph_begin = i;
+      while (i < (int) act.size() && act[i].joint == k) i++;
+      C.joints[k].sph_end = i;
+   }
+   const int nsa = (int) C.spheres.size(), nsi = (int) C.inactive_radius.size();
+   for (int s = 0; s < nsa; s++)
+   {
+      C.spheres[s].pair_begin = (int) C.pairs.size();
+      for (int o = 0; o < nsa + nsi; o++)
+      {
+         const int link2 = (o < nsa) ? C.spheres[o].link : C.inactive_link[o - nsa];
+         const double r2 = (o < nsa) ? C.spheres[o].radius : C.inactive_radius[o - nsa];
+         if (link2 == C.spheres[s].link) continue; /* mod.cpp:1256 */
+         OcbPairDev P;
+         P.rsum = C.spheres[s].radius + r2;
+         const double cut = C.spheres[s].radius + r2 + eps_self;
+         P.cut2 = cut * cut;
+         P.other = o;
+         P.pad = 0;
+         C.pairs.push_back(P);
+      }
+      C.spheres[s].pair_end = (int) C.pairs.size();
+   }
+   return OCB_OK;
+}
+
+void seed_mt(uint32_t *mt, unsigned int seed)
+{
+   /* gsl_rng_set on mt19937: seed 0 -> 4357, 2002 initialisation */
+   if (seed == 0) seed = 4357;
+   mt[0] = seed;
+   for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t) i;
+   mt[624] = 624;
+}
+} /* namespace */
+
+template <class T>
+static int batch_alloc(ocb_batch *b, T **ptr, size_t count)
+{
+   *ptr = nullptr;
+   if (cudaMalloc((void **) ptr, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess)
+   {
+      cudaGetLastError();
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+   }
+   b->owned.push_back(*ptr);
+   return OCB_OK;
+}
+
+template <class T>
+static int batch_upload(ocb_batch *b, const T **ptr, const std::vector<T> &h)
+{
+   T *d = nullptr;
+   int rc = batch_alloc(b, &d, h.size());
+   if (rc) return rc;
+   if (!h.empty())
+      CU(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, b->e->stream));
+   *ptr = d;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_destroy(ocb_batch *b)
+{
+   if (!b) return OCB_OK;
+   cudaSetDevice(b->e->device);
+   cudaStreamSynchronize(b->e->stream);
+   for (void *p : b->owned) cudaFree(p);
+   delete b;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb_params *params,
+                                int n_sdfs, const int *sdf_ids, int n_runs, const double *q_start,
+                                const double *q_goal, const unsigned int *seeds, ocb_batch **out)
+{
+   if (!e || !robot || !params || !out || !q_start || !q_goal) return fail(OCB_ERR_ARG, "null argument");
+   *out = nullptr;
+   /* argument checks of mod::create (mod.cpp:2091-2101) */
+   if (n_sdfs < 1 || !sdf_ids) return fail(OCB_ERR_ARG, "No signed distance fields have yet been computed!");
+   if (n_sdfs > OCB_MAX_SDFS) return fail(OCB_ERR_ARG, "more than %d signed distance fields", OCB_MAX_SDFS);
+   if (params->lambda < 0.01) return fail(OCB_ERR_ARG, "lambda must be >=0.01!");
+   if (params->n_points < 3) return fail(OCB_ERR_ARG, "n_points must be >=3!");
+   if (params->derivative < 1 || params->derivative > OCB_MAX_BW)
+      return fail(OCB_ERR_ARG, "derivative must be in 1..%d", OCB_MAX_BW);
+   if (n_runs < 1) return fail(OCB_ERR_ARG, "need at least one run");
+   /* use_hmc without use_momentum: the reference resamples AG and then overwrites it with
+    * Ainv G (beta = 0, chomp.c:529-530), so nothing observable changes -> same as no hmc */
+   const int use_hmc = (params->use_hmc && params->use_momentum) ? 1 : 0;
+   for (int i = 0; i < n_sdfs; i++)
+      if (sdf_ids[i] < 0 || sdf_ids[i] >= (int) e->sdfs.size() || !e->sdfs[sdf_ids[i]].used)
+         return fail(OCB_ERR_ARG, "bad sdf id %d", sdf_ids[i]);
+   CU(cudaSetDevice(e->device));
+
+   CompiledRobot C;
+   int rc = compile_robot(robot, params->epsilon_self, C);
+   if (rc) return rc;
+   const int P = params->n_points, m = P - 2, n = robot->n_dof;
+   if (m <= params->derivative) return fail(OCB_ERR_ARG, "n_points too small for derivative %d", params->derivative);
+   Metric M;
+   const double dt = 1.0 / (P - 1); /* mod.cpp:2567 */
+   rc = build_metric(m, params->derivative, dt, M);
+   if (rc) return fail(OCB_ERR_ARG, "smoothness metric is not positive definite (code %d)", rc);
+
+   ocb_batch *b = new (std::nothrow) ocb_batch();
+   if (!b) return fail(OCB_ERR_ALLOC, "out of host memory");
+   b->e = e;
+   OcbChompArgs &a = b->args;
+   memset(&a, 0, sizeof(a));
+   a.R = n_runs; a.P = P; a.m = m; a.n = n;
+   a.nj = (int) C.joints.size();
+   a.nsa = (int) C.spheres.size();
+   a.nsi = (int) C.inactive_radius.size();
+   a.nsdf = n_sdfs;
+   a.bw = params->derivative;
+   a.n_slots = C.n_slots;
+   a.Ppad = P | 1;
+   a.use_momentum = params->use_momentum ? 1 : 0;
+   a.use_hmc = use_hmc;
+   for (int j = 0; j < a.nj; j++) a.joints[j] = C.joints[j];
+   a.trc_ss = M.ss; a.trc_sg = M.sg; a.trc_gg = M.gg;
+   a.lambda = params->lambda;
+   a.dt = dt;
+   a.eps = params->epsilon;
+   a.eps_self = params->epsilon_self;
+   a.obs_factor = params->obs_factor;
+   a.obs_factor_self = params->obs_factor_self;
+   a.hmc_lambda = params->hmc_resample_lambda;
+
+   std::vector<OcbSdfDev> sd(n_sdfs);
+   for (int i = 0; i < n_sdfs; i++)
+   {
+      const SdfSlot &s = e->sdfs[sdf_ids[i]];
+      OcbSdfDev &d = sd[i];
+      memset(&d, 0, sizeof(d));
+      d.data = s.d_data;
+      for (int k = 0; k < 3; k++)
+      {
+         d.size[k] = s.sizes[k];
+         d.length[k] = s.lengths[k];
+         d.scale[k] = s.sizes[k] / s.lengths[k];
+         d.cell[k] = s.lengths[k] / s.sizes[k];
+      }
+      /* pose_gsdf_world = inverse of the snapshot pose (cd_kin_pose_invert, mod.cpp:2368) */
+      double inv[7];
+      const double *p = s.pose;
+      const double qi[4] = {-p[3], -p[4], -p[5], p[6]};
+      double Ri[9];
+      quat_to_R(qi, Ri);
+      for (int r = 0; r < 3; r++) inv[r] = -(Ri[3 * r] * p[0] + Ri[3 * r + 1] * p[1] + Ri[3 * r + 2] * p[2]);
+      memcpy(d.Rgw, Ri, sizeof(Ri));
+      d.tgw[0] = inv[0]; d.tgw[1] = inv[1]; d.tgw[2] = inv[2];
+      quat_to_R(p + 3, d.Rwg);
+   }
+
+#define TRY(x) do { rc = (x); if (rc) { ocb_batch_destroy(b); return rc; } } while (0)
+   TRY(batch_upload(b, &a.spheres, C.spheres));
+   TRY(batch_upload(b, &a.pairs, C.pairs));
+   TRY(batch_upload(b, &a.ancs, C.ancs));
+   TRY(batch_upload(b, &a.inactive_pos, C.inactive_pos));
+   TRY(batch_upload(b, &a.sdfs, sd));
+   TRY(batch_upload(b, &a.Aband, M.Aband));
+   TRY(batch_upload(b, &a.Lband, M.Lband));
+   TRY(batch_upload(b, &a.dinv, M.dinv));
+   TRY(batch_upload(b, &a.bcoef_i, M.bi));
+   TRY(batch_upload(b, &a.bcoef_f, M.bf));
+   {
+      std::vector<double> lo(robot->limit_lower, robot->limit_lower + n), hi(robot->limit_upper, robot->limit_upper + n);
+      TRY(batch_upload(b, &a.lim_lo, lo));
+      TRY(batch_upload(b, &a.lim_hi, hi));
+   }
+   const size_t R = (size_t) n_runs;
+   TRY(batch_alloc(b, &a.traj, R * P * n));
+   TRY(batch_alloc(b, &a.costs, R * 3));
+   TRY(batch_alloc(b, &a.status, R));
+   TRY(batch_alloc(b, &b->d_start, R * n));
+   TRY(batch_alloc(b, &b->d_goal, R * n));
+   cudaError_t err = cudaMemsetAsync(a.costs, 0, R * 3 * sizeof(double), e->stream);
+   if (err == cudaSuccess) err = cudaMemsetAsync(a.status, 0, R * sizeof(int), e->stream);
+   if (err == cudaSuccess) err = cudaMemcpyAsync(b->d_start, q_start, R * n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess) err = cudaMemcpyAsync(b->d_goal, q_goal, R * n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess) err = ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, n_runs, P, n, e->stream);
+   e->launches++;
+   if (a.use_momentum && err == cudaSuccess)
+   {
+      TRY(batch_alloc(b, &a.AG, R * m * n));
+      TRY(batch_alloc(b, &a.leapfrog_first, R));
+      err = cudaMemsetAsync(a.AG, 0, R * m * n * sizeof(double), e->stream); /* chomp.c:114-115 */
+      std::vector<int> ones(R, 1);                                            /* chomp.c:88 */
+      if (err == cudaSuccess) err = cudaMemcpyAsync(a.leapfrog_first, ones.data(), R * sizeof(int), cudaMemcpyHostToDevice, e->stream);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+   }
+   if (a.use_hmc && err == cudaSuccess)
+   {
+      TRY(batch_alloc(b, &a.hmc_next, R));
+      TRY(batch_alloc(b, &a.mt_state, R * 625));
+      err = cudaMemsetAsync(a.hmc_next, 0, R * sizeof(int), e->stream); /* mod.cpp:2634 */
+      std::vector<uint32_t> st(R * 625);
+      for (size_t r = 0; r < R; r++) seed_mt(&st[r * 625], seeds ? seeds[r] : 0u);
+      if (err == cudaSuccess) err = cudaMemcpyAsync(a.mt_state, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+   }
+   if (err != cudaSuccess)
+   {
+      ocb_batch_destroy(b);
+      return fail(OCB_ERR_CUDA, "batch_create: %s", cudaGetErrorString(err));
+   }
+
+   /* workspace: per waypoint 3*nsa sphere coordinates + 6*nj axis/origin + 12 per saved frame */
+   a.ws_stride = (size_t) (3 * a.nsa + 6 * a.nj + 12 * a.n_slots) * a.Ppad;
+   a.ws_in_smem = 1;
+   b->smem = ocb_chomp_smem_bytes(&a, 1);
+   if (b->smem > (size_t) e->smem_optin)
+   {
+      a.ws_in_smem = 0;
+      b->smem = ocb_chomp_smem_bytes(&a, 0);
+      if (b->smem > (size_t) e->smem_optin)
+      {
+         ocb_batch_destroy(b);
+         return fail(OCB_ERR_ARG, "trajectory too long for shared memory (%zu bytes)", b->smem);
+      }
+      TRY(batch_alloc(b, &a.ws_global, R * a.ws_stride));
+   }
+   b->threads = std::min(256, ((P + 31) / 32) * 32);
+   err = cudaStreamSynchronize(e->stream);
+   if (err != cudaSuccess)
+   {
+      ocb_batch_destroy(b);
+      return fail(OCB_ERR_CUDA, "batch_create: %s", cudaGetErrorString(err));
+   }
+#undef TRY
+   *out = b;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   if (n_runs) *n_runs = b->args.R;
+   if (n_points) *n_points = b->args.P;
+   if (n_dof) *n_dof = b->args.n;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_set_traj(ocb_batch *b, const double *traj)
+{
+   if (!b || !traj) return fail(OCB_ERR_ARG, "null argument");
+   CU(cudaSetDevice(b->e->device));
+   const size_t bytes = (size_t) b->args.R * b->args.P * b->args.n * sizeof(double);
+   CU(cudaMemcpyAsync(b->args.traj, traj, bytes, cudaMemcpyHostToDevice, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_enable_trace(ocb_batch *b, int enable)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   b->args.trace_on = enable ? 1 : 0;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_capture_gradient(ocb_batch *b, int mode)
+{
+   if (!b || mode < 0 || mode > 2) return fail(OCB_ERR_ARG, "bad argument");
+   CU(cudaSetDevice(b->e->device));
+   if (mode && !b->args.grad_out)
+   {
+      int rc = batch_alloc(b, &b->args.grad_out, (size_t) b->args.R * b->args.m * b->args.n);
+      if (rc) return rc;
+   }
+   b->args.grad_mode = mode;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_iterate_async(ocb_batch *b, int n_iter)
+{
+   if (!b) return fail(OCB_ERR_ARG, "you must pass a created run!");
+   if (n_iter < 0) return fail(OCB_ERR_ARG, "n_iter must be >=0!");
+   CU(cudaSetDevice(b->e->device));
+   OcbChompArgs &a = b->args;
+   if (a.trace_on && n_iter > b->trace_cap)
+   {
+      int rc = batch_alloc(b, &a.trace, (size_t) a.R * n_iter * 3);
+      if (rc) return rc;
+      b->trace_cap = n_iter;
+   }
+   a.n_iter = n_iter;
+   b->last_n_iter = n_iter;
+   CU(ocb_launch_chomp(&a, b->smem, b->threads, b->e->stream));
+   b->e->launches++;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_get_costs(ocb_batch *b, double *cost_total, double *cost_obs, double *cost_smooth, int *status)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   CU(cudaSetDevice(b->e->device));
+   const int R = b->args.R;
+   std::vector<double> c((size_t) R * 3);
+   CU(cudaMemcpyAsync(c.data(), b->args.costs, c.size() * sizeof(double), cudaMemcpyDeviceToHost, b->e->stream));
+   if (status) CU(cudaMemcpyAsync(status, b->args.status, R * sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   for (int r = 0; r < R; r++)
+   {
+      if (cost_total) cost_total[r] = c[(size_t) r * 3];
+      if (cost_obs) cost_obs[r] = c[(size_t) r * 3 + 1];
+      if (cost_smooth) cost_smooth[r] = c[(size_t) r * 3 + 2];
+   }
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_iterate(ocb_batch *b, int n_iter, double *cost_total, double *cost_obs,
+                                 double *cost_smooth, int *status)
+{
+   int rc = ocb_batch_iterate_async(b, n_iter);
+   if (rc) return rc;
+   return ocb_batch_get_costs(b, cost_total, cost_obs, cost_smooth, status);
+}
+
+extern "C" int ocb_batch_get_trace(ocb_batch *b, double *trace, int n_iter)
+{
+   if (!b || !trace) return fail(OCB_ERR_ARG, "null argument");
+   if (!b->args.trace_on || n_iter != b->last_n_iter || !b->args.trace)
+      return fail(OCB_ERR_ARG, "no trace recorded for %d iterations", n_iter);
+   CU(cudaSetDevice(b->e->device));
+   CU(cudaMemcpyAsync(trace, b->args.trace, (size_t) b->args.R * n_iter * 3 * sizeof(double),
+                      cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_get_traj(ocb_batch *b, double *traj)
+{
+   if (!b || !traj) return fail(OCB_ERR_ARG, "null argument");
+   CU(cudaSetDevice(b->e->device));
+   const size_t bytes = (size_t) b->args.R * b->args.P * b->args.n * sizeof(double);
+   CU(cudaMemcpyAsync(traj, b->args.traj, bytes, cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_get_gradient(ocb_batch *b, double *G)
+{
+   if (!b || !G) return fail(OCB_ERR_ARG, "null argument");
+   if (!b->args.grad_mode || !b->args.grad_out) return fail(OCB_ERR_ARG, "gradient capture is off");
+   CU(cudaSetDevice(b->e->device));
+   const size_t bytes = (size_t) b->args.R * b->args.m * b->args.n * sizeof(double);
+   CU(cudaMemcpyAsync(G, b->args.grad_out, bytes, cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_best(ocb_batch *b, int *best_run, double *best_cost)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   CU(cudaSetDevice(b->e->device));
+   int rc = engine_scratch(b->e, 64);
+   if (rc) return rc;
+   int *d_idx = (int *) b->e->scratch;
+   double *d_cost = (double *) ((char *) b->e->scratch + 8);
+   CU(ocb_launch_best(b->args.costs, b->args.status, b->args.R, d_idx, d_cost, b->e->stream));
+   b->e->launches++;
+   int idx = -1;
+   double c = 0;
+   CU(cudaMemcpyAsync(&idx, d_idx, sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaMemcpyAsync(&c, d_cost, sizeof(double), cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   if (best_run) *best_run = idx;
+   if (best_cost) *best_cost = c;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_device_ptrs(ocb_batch *b, void **d_traj, void **d_costs)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   if (d_traj) *d_traj = b->args.traj;
+   if (d_costs) *d_costs = b->args.costs;
+   return OCB_OK;
+}

@@ -1,0 +1,144 @@
+/* ocb_internal.h -- types shared by the host engine and the sm_100a kernels.
+ * Not part of the public ABI (that is include/orcdchomp_b200.h). */
+#ifndef OCB_INTERNAL_H
+#define OCB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#define OCB_MAX_JOINTS 16   /* moving joints carried in kernel-parameter (constant) space */
+#define OCB_MAX_SDFS 16  /* descriptors are staged in shared memory */
+#define OCB_MAX_BW 4        /* half bandwidth of the smoothness metric (= derivative D) */
+
+/* parent-transform source of a joint in the forward sweep */
+#define OCB_LOAD_PREV (-1)
+#define OCB_LOAD_BASE (-2)
+
+/* One moving joint of the compiled kinematic tree.  The joint frame has its axis
+ * on local z; X = fixed transform from the parent joint frame (or world, for
+ * root-level joints; base pose folded in) to this joint's frame at value 0. */
+struct OcbJointDev
+{
+   double XR[9];
+   double Xt[3];
+   double c0, c1;      /* joint value = c0 * q[dof] + c1 */
+   int type;           /* OCB_JOINT_REVOLUTE / OCB_JOINT_PRISMATIC */
+   int dof;
+   int load;           /* OCB_LOAD_PREV / OCB_LOAD_BASE / slot index */
+   int save;           /* slot index to save this joint's transform into, or -1 */
+   int sph_begin, sph_end;   /* active spheres rigidly attached to this joint frame */
+   int anc_begin, anc_end;   /* ancestors (incl. self) in the ancestor table */
+};
+
+struct OcbSphereDev
+{
+   double pos[3];      /* in the joint frame */
+   double radius;
+   int link;           /* original robot link index (same-link pairs are skipped) */
+   int pair_begin, pair_end;
+};
+
+/* candidate self-collision partner of a sphere (different link) */
+struct OcbPairDev
+{
+   double rsum;        /* radius + radius2 */
+   double cut2;        /* (radius + radius2 + epsilon_self)^2 */
+   int other;          /* < n_active: active sphere index; else n_active + inactive index */
+   int pad;
+};
+
+struct OcbAncDev
+{
+   double c0;          /* d(value)/d(dof) */
+   int joint;
+   int dof;
+   int type;
+   int pad;
+};
+
+struct OcbSdfDev
+{
+   const double *data;
+   int size[3];
+   int pad;
+   double length[3];
+   double scale[3];    /* size / length */
+   double cell[3];     /* length / size */
+   double Rgw[9];      /* rotation of pose_gsdf_world (world -> grid), row-major */
+   double tgw[3];
+   double Rwg[9];      /* rotation of pose_world_gsdf (grid -> world) */
+};
+
+struct OcbChompArgs
+{
+   /* sizes */
+   int R, P, m, n;
+   int nj, nsa, nsi, nsdf;
+   int bw, n_slots, Ppad, n_iter;
+   int use_momentum, use_hmc, trace_on, grad_mode; /* grad_mode 0 none, 1 full G, 2 obstacle only */
+   int ws_in_smem, pad0;
+   /* robot */
+   OcbJointDev joints[OCB_MAX_JOINTS];
+   const OcbSphereDev *spheres;
+   const OcbPairDev *pairs;
+   const OcbAncDev *ancs;
+   const double *inactive_pos;
+   const OcbSdfDev *sdfs; /* [nsdf] in HBM, staged to shared memory by the kernel */
+   /* metric: A band [m][2bw+1], LDL^T factors, B coefficient vectors */
+   const double *Aband;
+   const double *Lband;   /* [m][bw] */
+   const double *dinv;    /* [m]     */
+   const double *bcoef_i; /* [m]     */
+   const double *bcoef_f; /* [m]     */
+   double trc_ss, trc_sg, trc_gg;
+   /* parameters */
+   double lambda, dt, eps, eps_self, obs_factor, obs_factor_self, hmc_lambda;
+   const double *lim_lo;
+   const double *lim_hi;
+   /* per-run state in HBM */
+   double *traj;          /* [R][P][n] */
+   double *AG;            /* [R][m][n] */
+   int *leapfrog_first;   /* [R] */
+   int *hmc_next;         /* [R] */
+   uint32_t *mt_state;    /* [R][625] */
+   double *costs;         /* [R][3] */
+   int *status;           /* [R] */
+   double *trace;         /* [R][n_iter][3] */
+   double *grad_out;      /* [R][m][n] */
+   double *ws_global;     /* per-block workspace when it does not fit in shared memory */
+   size_t ws_stride;      /* doubles per block */
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* kernels' host launchers (defined in the .cu files) */
+cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st);
+size_t ocb_chomp_smem_bytes(const OcbChompArgs *args, int ws_in_smem);
+cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const double *q_goal,
+                                 int R, int P, int n, cudaStream_t st);
+cudaError_t ocb_launch_best(const double *costs, const int *status, int R, int *best_run,
+                            double *best_cost, cudaStream_t st);
+
+/* sdf_kernels.cu */
+cudaError_t ocb_launch_dt_sqeuc(const double *d_func, double *d_out, const int sizes[3],
+                                const double lengths[3], void *scratch, size_t scratch_bytes,
+                                cudaStream_t st, long *launches);
+size_t ocb_dt_scratch_bytes(const int sizes[3]);
+cudaError_t ocb_launch_bin_sdf(const double *d_obs, double *d_sdf, const int sizes[3],
+                               const double lengths[3], void *scratch, size_t scratch_bytes,
+                               cudaStream_t st, long *launches);
+size_t ocb_sdf_scratch_bytes(const int sizes[3], const double lengths[3]);
+cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, const int sizes[3],
+                                 const double lengths[3], double cube_extent, double *d_grid,
+                                 cudaStream_t st);
+cudaError_t ocb_launch_flood_relabel(double *d_grid, const int sizes[3], size_t index_start,
+                                     void *scratch, size_t scratch_bytes, cudaStream_t st,
+                                     long *launches);
+size_t ocb_flood_scratch_bytes(const int sizes[3]);
+#ifdef __cplusplus
+}
+#endif
+
+#endif

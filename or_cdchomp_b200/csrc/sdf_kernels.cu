@@ -1,0 +1,447 @@
+/* sdf_kernels.cu -- environment signed-distance-field build on sm_100a.
+ *
+ * Replaces, for 3-d grids of doubles (paths relative to the reference root):
+ *   cd_grid_double_dt_sqeuc + sedt_onedim   src/libcd/grid.c:462-569, 269-329
+ *   cd_grid_double_bin_sdf                  src/libcd/grid.c:637-687
+ *   cd_grid_flood_fill + 1.0->HUGE_VAL      src/libcd/grid_flood.c:30-111,
+ *                                           src/orcdchomp_mod.cpp:143-151, 543-548
+ *   the occupancy loop                      src/orcdchomp_mod.cpp:498-525
+ *                                           (+ cd_grid_center_index, grid.c:172-189)
+ *
+ * This file is compiled with -fmad=false: every product and sum rounds on its
+ * own, so the general distance transform reproduces the reference's arithmetic
+ * operation for operation and the occupancy predicate agrees bit for bit with
+ * the CPU oracle (oracle/orcdchomp_port.c, built with -ffp-contract=off).
+ *
+ * General path (any finite sample heights, any cell pitch): one thread per grid
+ * line runs the lower-envelope scan; the envelope stack lives in HBM scratch laid
+ * out [entry][line] so a warp's accesses coalesce while depths stay similar.
+ */
+#include <math.h>
+#include "ocb_internal.h"
+#include "../../include/orcdchomp_b200.h"
+
+namespace
+{
+
+/* ------------------------------------------------------------------ EDT pass */
+struct EdtPass
+{
+   const double *src; /* read from here ... */
+   double *dst;       /* ... write here (may alias src) */
+   int len;           /* cells along the transformed dimension */
+   size_t stride;     /* element stride along it = product of faster dimensions */
+   size_t inner;      /* == stride */
+   size_t nlines;
+   double pitch2;     /* (length/size)^2, grid.c:518 */
+   int flip;          /* 1: treat the input as (x == 0 ? HUGE_VAL : 0), grid.c:657-663 */
+   int *stk_v;        /* [len][nlines]   */
+   double *stk_z;     /* [len+1][nlines] */
+   double *stk_f;     /* [len][nlines]   */
+};
+
+__global__ void __launch_bounds__(128) edt_pass_kernel(const EdtPass p)
+{
+   const size_t line = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+   if (line >= p.nlines) return;
+   const size_t o = line / p.inner, i = line % p.inner;
+   const size_t base = o * p.inner * (size_t) p.len + i;
+   const double inf = HUGE_VAL;
+   const size_t L = p.nlines;
+
+   /* build the lower envelope (grid.c:280-312); the top entry is kept in registers */
+   int np = 0;
+   int v_top = 0;
+   double z_top = 0.0, f_top = 0.0;
+   for (int q = 0; q < p.len; q++)
+   {
+      double x = p.src[base + (size_t) q * p.stride];
+      if (p.flip) x = (x == 0.0) ? inf : 0.0;
+      const double fq = x / p.pitch2;
+      if (fq == inf) continue;
+      if (np == 0)
+      {
+         np = 1;
+         v_top = q; z_top = -inf; f_top = fq;
+         continue;
+      }
+      double s;
+      for (;;)
+      {
+         s = fq + (double) (q * q);
+         s -= f_top + (double) (v_top * v_top);
+         s /= 2.0 * (double) (q - v_top);
+         if (s <= z_top)
+         {
+            np--; /* z_top == -inf for the last entry, so np never reaches 0 here */
+            v_top = p.stk_v[(size_t) (np - 1) * L + line];
+            z_top = p.stk_z[(size_t) (np - 1) * L + line];
+            f_top = p.stk_f[(size_t) (np - 1) * L + line];
+         }
+         else
+            break;
+      }
+      p.stk_v[(size_t) (np - 1) * L + line] = v_top;
+      p.stk_z[(size_t) (np - 1) * L + line] = z_top;
+      p.stk_f[(size_t) (np - 1) * L + line] = f_top;
+      np++;
+      v_top = q; z_top = s; f_top = fq;
+   }
+   if (np == 0)
+   {
+      for (int q = 0; q < p.len; q++) p.dst[base + (size_t) q * p.stride] = inf; /* inf * pitch2 = inf */
+      return;
+   }
+   p.stk_v[(size_t) (np - 1) * L + line] = v_top;
+   p.stk_z[(size_t) (np - 1) * L + line] = z_top;
+   p.stk_f[(size_t) (np - 1) * L + line] = f_top;
+
+   /* read the envelope back (grid.c:321-326) */
+   int k = 0;
+   int v = p.stk_v[line];
+   double f = p.stk_f[line];
+   double z_next = (np > 1) ? p.stk_z[L + line] : inf;
+   for (int q = 0; q < p.len; q++)
+   {
+      while (z_next < (double) q)
+      {
+         k++;
+         v = p.stk_v[(size_t) k * L + line];
+         f = p.stk_f[(size_t) k * L + line];
+         z_next = (k + 1 < np) ? p.stk_z[(size_t) (k + 1) * L + line] : inf;
+      }
+      const double d = (double) (q - v);
+      double out = d * d + f;
+      out *= p.pitch2;
+      p.dst[base + (size_t) q * p.stride] = out;
+   }
+}
+
+/* sqrt(sedt_obs) - sqrt(sedt_emp), grid.c:674-679 */
+__global__ void sdf_combine_kernel(const double *__restrict__ d_obs, const double *__restrict__ d_emp,
+                                   double *__restrict__ out, size_t n)
+{
+   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+      out[i] = sqrt(d_obs[i]) - sqrt(d_emp[i]);
+}
+
+/* ---------------------------------------------------------------- occupancy */
+struct PrimDev
+{
+   int type;
+   double c[3];   /* centre in the grid frame */
+   double e[3];   /* half extents (box) / e[0] = radius (sphere) */
+   double R[9];   /* box axes = columns */
+   double A[9];   /* |R| + 1e-12 */
+};
+
+__global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const ocb_prim &p = prims[i];
+   PrimDev d;
+   d.type = p.type;
+   for (int k = 0; k < 3; k++) { d.c[k] = p.pose[k]; d.e[k] = p.extents[k]; }
+   const double qx = p.pose[3], qy = p.pose[4], qz = p.pose[5], qw = p.pose[6];
+   const double qx2 = qx * qx, qy2 = qy * qy, qz2 = qz * qz, qw2 = qw * qw;
+   const double qxqy = qx * qy, qxqz = qx * qz, qxqw = qx * qw;
+   const double qyqz = qy * qz, qyqw = qy * qw, qzqw = qz * qw;
+   d.R[0] = qx2 - qy2 - qz2 + qw2; d.R[1] = 2 * (qxqy - qzqw);      d.R[2] = 2 * (qxqz + qyqw);
+   d.R[3] = 2 * (qxqy + qzqw);     d.R[4] = -qx2 + qy2 - qz2 + qw2; d.R[5] = 2 * (qyqz - qxqw);
+   d.R[6] = 2 * (qxqz - qyqw);     d.R[7] = 2 * (qyqz + qxqw);      d.R[8] = -qx2 - qy2 + qz2 + qw2;
+   for (int k = 0; k < 9; k++) d.A[k] = fabs(d.R[k]) + 1e-12;
+   out[i] = d;
+}
+
+/* cube (centre c, half extent h, axes = grid axes) against one primitive; the
+ * operation order is the contract shared with oracle/orcdchomp_port.c */
+__device__ __forceinline__ bool cube_hits(const double c[3], double h, const PrimDev &p)
+{
+   if (p.type == OCB_PRIM_SPHERE)
+   {
+      double d2 = 0.0;
+      const double r = p.e[0];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+      {
+         double d = fabs(p.c[k] - c[k]) - h;
+         if (d < 0.0) d = 0.0;
+         d2 = d2 + d * d;
+      }
+      return d2 <= r * r;
+   }
+   const double *R = p.R, *A = p.A, *e = p.e;
+   double t[3];
+#pragma unroll
+   for (int i = 0; i < 3; i++) t[i] = p.c[i] - c[i];
+#pragma unroll
+   for (int i = 0; i < 3; i++)
+   {
+      const double ra = h;
+      const double rb = e[0] * A[3 * i + 0] + e[1] * A[3 * i + 1] + e[2] * A[3 * i + 2];
+      if (fabs(t[i]) > ra + rb) return false;
+   }
+#pragma unroll
+   for (int j = 0; j < 3; j++)
+   {
+      const double ra = h * A[0 + j] + h * A[3 + j] + h * A[6 + j];
+      const double rb = e[j];
+      const double tl = t[0] * R[0 + j] + t[1] * R[3 + j] + t[2] * R[6 + j];
+      if (fabs(tl) > ra + rb) return false;
+   }
+#pragma unroll
+   for (int i = 0; i < 3; i++)
+   {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+      {
+         const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+         const double ra = h * A[3 * i1 + j] + h * A[3 * i2 + j];
+         const double rb = e[j1] * A[3 * i + j2] + e[j2] * A[3 * i + j1];
+         const double tl = t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j];
+         if (fabs(tl) > ra + rb) return false;
+      }
+   }
+   return true;
+}
+
+__global__ void __launch_bounds__(256)
+occupancy_kernel(const PrimDev *__restrict__ prims, int n_prims, int sx, int sy, int sz,
+                 double lx, double ly, double lz, double h, double *__restrict__ grid)
+{
+   extern __shared__ __align__(16) unsigned char osm[];
+   PrimDev *sp = reinterpret_cast<PrimDev *>(osm);
+   const size_t total = (size_t) sx * sy * sz;
+   for (size_t base = blockIdx.x * (size_t) blockDim.x; base < total; base += (size_t) gridDim.x * blockDim.x)
+   {
+      const size_t idx = base + threadIdx.x;
+      double c[3] = {0, 0, 0};
+      if (idx < total)
+      {
+         const int z = (int) (idx % sz), y = (int) ((idx / sz) % sy), x = (int) (idx / ((size_t) sz * sy));
+         /* cd_grid_center_index: ((0.5 + sub) / size) * length   (grid.c:184-187) */
+         c[0] = (0.5 + x) / sx * lx;
+         c[1] = (0.5 + y) / sy * ly;
+         c[2] = (0.5 + z) / sz * lz;
+      }
+      bool hit = false;
+      for (int p0 = 0; p0 < n_prims; p0 += 64)
+      {
+         const int cnt = min(64, n_prims - p0);
+         __syncthreads();
+         {
+            const int words = cnt * (int) (sizeof(PrimDev) / 4);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(prims + p0);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sp);
+            for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+         }
+         __syncthreads();
+         if (idx < total && !hit)
+            for (int k = 0; k < cnt; k++)
+               if (cube_hits(c, h, sp[k])) { hit = true; break; }
+      }
+      if (idx < total) grid[idx] = hit ? HUGE_VAL : 1.0; /* mod.cpp:398, 522 */
+   }
+}
+
+/* --------------------------------------------------------------- flood fill */
+/* state: 0 = not fillable, 1 = fillable (cell == 1.0), 2 = filled */
+__global__ void flood_init_kernel(const double *__restrict__ grid, unsigned char *__restrict__ st,
+                                  size_t n, size_t start)
+{
+   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+   {
+      unsigned char s = (grid[i] == 1.0) ? 1 : 0;
+      if (i == start && s == 1) s = 2;
+      st[i] = s;
+   }
+}
+
+/* propagate "filled" along whole lines of one axis, both directions */
+__global__ void __launch_bounds__(128)
+flood_sweep_kernel(unsigned char *st, int len, size_t stride, size_t inner, size_t nlines, int *changed)
+{
+   const size_t line = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+   if (line >= nlines) return;
+   const size_t o = line / inner, i = line % inner;
+   unsigned char *base = st + o * inner * (size_t) len + i;
+   bool any = false;
+   unsigned char prev = 0;
+   for (int q = 0; q < len; q++)
+   {
+      unsigned char s = base[(size_t) q * stride];
+      if (s == 1 && prev == 2) { s = 2; base[(size_t) q * stride] = 2; any = true; }
+      prev = s;
+   }
+   prev = 0;
+   for (int q = len - 1; q >= 0; q--)
+   {
+      unsigned char s = base[(size_t) q * stride];
+      if (s == 1 && prev == 2) { s = 2; base[(size_t) q * stride] = 2; any = true; }
+      prev = s;
+   }
+   if (any) *changed = 1;
+}
+
+/* filled -> 0.0 (replace_1_to_0, mod.cpp:143-151); still 1.0 -> HUGE_VAL (mod.cpp:546-548) */
+__global__ void flood_finish_kernel(double *__restrict__ grid, const unsigned char *__restrict__ st, size_t n)
+{
+   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+   {
+      const unsigned char s = st[i];
+      if (s == 2) grid[i] = 0.0;
+      else if (s == 1) grid[i] = HUGE_VAL;
+   }
+}
+
+int grid_blocks(size_t n, int threads)
+{
+   size_t b = (n + threads - 1) / threads;
+   const size_t cap = 148 * 16;
+   if (b > cap) b = cap;
+   if (b < 1) b = 1;
+   return (int) b;
+}
+
+} /* namespace */
+
+/* ------------------------------------------------------------ host launchers */
+extern "C" size_t ocb_dt_scratch_bytes(const int sizes[3])
+{
+   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   int maxlen = sizes[0];
+   if (sizes[1] > maxlen) maxlen = sizes[1];
+   if (sizes[2] > maxlen) maxlen = sizes[2];
+   /* per cell: int apex + double bound + double height, plus one extra bound row per line */
+   return n * (sizeof(int) + 2 * sizeof(double)) + (n / 2 + 1024) * sizeof(double) + 4096;
+}
+
+static cudaError_t run_edt(const double *src, double *dst, const int sizes[3], const double lengths[3],
+                           int flip, void *scratch, cudaStream_t st, long *launches)
+{
+   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   char *sp = (char *) scratch;
+   double *stk_z = (double *) sp;
+   size_t maxlines = 0;
+   for (int d = 0; d < 3; d++) maxlines = (n / sizes[d] > maxlines) ? n / sizes[d] : maxlines;
+   double *stk_f = stk_z + n + maxlines;
+   int *stk_v = (int *) (stk_f + n);
+   for (int d = 0; d < 3; d++)
+   {
+      EdtPass p;
+      p.src = (d == 0) ? src : dst;
+      p.dst = dst;
+      p.len = sizes[d];
+      p.stride = 1;
+      for (int d2 = d + 1; d2 < 3; d2++) p.stride *= (size_t) sizes[d2];
+      p.inner = p.stride;
+      p.nlines = n / (size_t) sizes[d];
+      const double pitch = lengths[d] / sizes[d];
+      p.pitch2 = pitch * pitch; /* pow(x, 2.0) */
+      p.flip = (d == 0) ? flip : 0;
+      p.stk_v = stk_v;
+      p.stk_z = stk_z;
+      p.stk_f = stk_f;
+      const int threads = 128;
+      const unsigned blocks = (unsigned) ((p.nlines + threads - 1) / threads);
+      edt_pass_kernel<<<blocks, threads, 0, st>>>(p);
+      if (launches) (*launches)++;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+   }
+   return cudaSuccess;
+}
+
+extern "C" cudaError_t ocb_launch_dt_sqeuc(const double *d_func, double *d_out, const int sizes[3],
+                                           const double lengths[3], void *scratch, size_t scratch_bytes,
+                                           cudaStream_t st, long *launches)
+{
+   if (scratch_bytes < ocb_dt_scratch_bytes(sizes)) return cudaErrorInvalidValue;
+   return run_edt(d_func, d_out, sizes, lengths, 0, scratch, st, launches);
+}
+
+extern "C" size_t ocb_sdf_scratch_bytes(const int sizes[3], const double lengths[3])
+{
+   (void) lengths;
+   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   return ocb_dt_scratch_bytes(sizes) + 2 * n * sizeof(double) + 512;
+}
+
+extern "C" cudaError_t ocb_launch_bin_sdf(const double *d_obs, double *d_sdf, const int sizes[3],
+                                          const double lengths[3], void *scratch, size_t scratch_bytes,
+                                          cudaStream_t st, long *launches)
+{
+   if (scratch_bytes < ocb_sdf_scratch_bytes(sizes, lengths)) return cudaErrorInvalidValue;
+   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   double *g_emp = (double *) scratch;
+   double *g_obs = g_emp + n;
+   void *stk = (void *) (g_obs + n + 32);
+   cudaError_t e = run_edt(d_obs, g_emp, sizes, lengths, 0, stk, st, launches);
+   if (e != cudaSuccess) return e;
+   e = run_edt(d_obs, g_obs, sizes, lengths, 1, stk, st, launches);
+   if (e != cudaSuccess) return e;
+   sdf_combine_kernel<<<grid_blocks(n, 256), 256, 0, st>>>(g_obs, g_emp, d_sdf, n);
+   if (launches) (*launches)++;
+   return cudaGetLastError();
+}
+
+extern "C" cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, const int sizes[3],
+                                            const double lengths[3], double cube_extent, double *d_grid,
+                                            cudaStream_t st)
+{
+   /* the raw ocb_prim array sits at the start of the scratch; the prepared form follows it */
+   const size_t raw = ((size_t) (n_prims > 0 ? n_prims : 1) * sizeof(ocb_prim) + 255) & ~(size_t) 255;
+   PrimDev *prep = nullptr;
+   cudaError_t e = cudaMallocAsync((void **) &prep, (size_t) (n_prims > 0 ? n_prims : 1) * sizeof(PrimDev), st);
+   if (e != cudaSuccess) return e;
+   (void) raw;
+   if (n_prims > 0)
+      prep_prims_kernel<<<(n_prims + 127) / 128, 128, 0, st>>>((const ocb_prim *) d_prims, prep, n_prims);
+   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   occupancy_kernel<<<grid_blocks(n, 256), 256, 64 * sizeof(PrimDev), st>>>(
+      prep, n_prims, sizes[0], sizes[1], sizes[2], lengths[0], lengths[1], lengths[2], cube_extent, d_grid);
+   e = cudaGetLastError();
+   cudaFreeAsync(prep, st);
+   return e;
+}
+
+extern "C" size_t ocb_flood_scratch_bytes(const int sizes[3])
+{
+   return (size_t) sizes[0] * sizes[1] * sizes[2] + 256;
+}
+
+extern "C" cudaError_t ocb_launch_flood_relabel(double *d_grid, const int sizes[3], size_t index_start,
+                                                void *scratch, size_t scratch_bytes, cudaStream_t st,
+                                                long *launches)
+{
+   if (scratch_bytes < ocb_flood_scratch_bytes(sizes)) return cudaErrorInvalidValue;
+   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   int *changed = (int *) scratch;
+   unsigned char *state = (unsigned char *) scratch + 256;
+   flood_init_kernel<<<grid_blocks(n, 256), 256, 0, st>>>(d_grid, state, n, index_start);
+   if (launches) (*launches)++;
+   for (int round = 0; round < 100000; round++)
+   {
+      cudaError_t e = cudaMemsetAsync(changed, 0, sizeof(int), st);
+      if (e != cudaSuccess) return e;
+      for (int d = 2; d >= 0; d--)
+      {
+         size_t stride = 1;
+         for (int d2 = d + 1; d2 < 3; d2++) stride *= (size_t) sizes[d2];
+         const size_t nlines = n / (size_t) sizes[d];
+         flood_sweep_kernel<<<(unsigned) ((nlines + 127) / 128), 128, 0, st>>>(state, sizes[d], stride, stride, nlines, changed);
+         if (launches) (*launches)++;
+      }
+      int h = 0;
+      e = cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+      if (!h) break;
+   }
+   flood_finish_kernel<<<grid_blocks(n, 256), 256, 0, st>>>(d_grid, state, n);
+   if (launches) (*launches)++;
+   return cudaGetLastError();
+}

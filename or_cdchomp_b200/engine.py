@@ -1,0 +1,205 @@
+"""Thin Python host layer over the C ABI (include/orcdchomp_b200.h).
+
+Every numeric operation happens inside liborcdchomp_b200.so on the GPU; this file
+only marshals numpy arrays.  It mirrors the life cycle of the reference module's
+run handle: create -> iterate -> gettraj -> destroy
+(src/orcdchomp_mod.cpp:1800, 2690, 2854, 3013 in the reference).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import as_f64, c_double_p, c_int_p, c_uint_p, check, dptr
+
+
+def _i3(a):
+    return (C.c_int * 3)(*[int(x) for x in a])
+
+
+def _d3(a):
+    return (C.c_double * 3)(*[float(x) for x in a])
+
+
+class Engine:
+    """One engine per GPU: owns the resident SDFs, a stream and scratch."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or capi.load_library()
+        h = C.c_void_p()
+        check(self.lib, self.lib.ocb_engine_create(int(device), C.byref(h)), "ocb_engine_create")
+        self.h = h
+        self.device = device
+
+    # -- SDF residency -----------------------------------------------------
+    def upload_sdf(self, sdf_desc):
+        sid = C.c_int()
+        check(self.lib, self.lib.ocb_sdf_upload(self.h, C.byref(sdf_desc.struct), C.byref(sid)), "ocb_sdf_upload")
+        return sid.value
+
+    def adopt_sdf(self, sizes, lengths, pose_world_gsdf, device_ptr):
+        sid = C.c_int()
+        pose = as_f64(pose_world_gsdf)
+        check(self.lib, self.lib.ocb_sdf_adopt_device(self.h, _i3(sizes), _d3(lengths), dptr(pose),
+                                                     C.c_void_p(int(device_ptr)), C.byref(sid)),
+              "ocb_sdf_adopt_device")
+        return sid.value
+
+    def remove_sdf(self, sid):
+        check(self.lib, self.lib.ocb_sdf_remove(self.h, int(sid)), "ocb_sdf_remove")
+
+    # -- SDF build ---------------------------------------------------------
+    def sdf_build(self, obs, lengths):
+        """cd_grid_double_bin_sdf on host arrays (copies in and out)."""
+        obs = as_f64(obs)
+        out = np.empty_like(obs)
+        check(self.lib, self.lib.ocb_sdf_build_host(self.h, dptr(obs), _i3(obs.shape), _d3(lengths), dptr(out)),
+              "ocb_sdf_build_host")
+        return out
+
+    def sdf_build_device(self, d_obs, sizes, lengths, d_sdf):
+        check(self.lib, self.lib.ocb_sdf_build_device(self.h, C.c_void_p(int(d_obs)), _i3(sizes), _d3(lengths),
+                                                     C.c_void_p(int(d_sdf))), "ocb_sdf_build_device")
+
+    def dt_sqeuc_device(self, d_func, sizes, lengths, d_out):
+        check(self.lib, self.lib.ocb_dt_sqeuc_device(self.h, C.c_void_p(int(d_func)), _i3(sizes), _d3(lengths),
+                                                    C.c_void_p(int(d_out))), "ocb_dt_sqeuc_device")
+
+    def occupancy_device(self, prims, sizes, lengths, cube_extent, d_grid):
+        arr = capi.make_prims(prims)
+        check(self.lib, self.lib.ocb_occupancy_device(self.h, arr, len(prims), _i3(sizes), _d3(lengths),
+                                                     float(cube_extent), C.c_void_p(int(d_grid))),
+              "ocb_occupancy_device")
+
+    def flood_relabel_device(self, d_grid, sizes, index_start=0):
+        check(self.lib, self.lib.ocb_flood_relabel_device(self.h, C.c_void_p(int(d_grid)), _i3(sizes),
+                                                         int(index_start)), "ocb_flood_relabel_device")
+
+    def computedistancefield(self, prims, sizes, lengths, cube_extent, want_sdf=True):
+        """occupancy -> flood fill + relabel -> SDF with host outputs
+        (src/orcdchomp_mod.cpp:498-560 in the reference)."""
+        arr = capi.make_prims(prims)
+        shape = tuple(int(s) for s in sizes)
+        obs = np.empty(shape)
+        sdf = np.empty(shape) if want_sdf else None
+        check(self.lib, self.lib.ocb_computedistancefield_host(
+            self.h, arr, len(prims), _i3(sizes), _d3(lengths), float(cube_extent), dptr(obs),
+            dptr(sdf) if want_sdf else None), "ocb_computedistancefield_host")
+        return obs, sdf
+
+    # -- batches -----------------------------------------------------------
+    def create_batch(self, robot, params, sdf_ids, q_start, q_goal, seeds=None):
+        return Batch(self, robot, params, sdf_ids, q_start, q_goal, seeds)
+
+    def set_stream(self, cuda_stream):
+        check(self.lib, self.lib.ocb_engine_set_stream(self.h, C.c_void_p(int(cuda_stream or 0))),
+              "ocb_engine_set_stream")
+
+    def sync(self):
+        check(self.lib, self.lib.ocb_engine_sync(self.h), "ocb_engine_sync")
+
+    def launch_count(self):
+        return int(self.lib.ocb_engine_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.ocb_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """R independent CHOMP runs on one GPU (struct run x R)."""
+
+    def __init__(self, engine, robot, params, sdf_ids, q_start, q_goal, seeds=None):
+        self.engine, self.lib = engine, engine.lib
+        self.robot, self.params = robot, params
+        q_start, q_goal = as_f64(q_start), as_f64(q_goal)
+        if q_start.ndim == 1:
+            q_start, q_goal = q_start[None, :], q_goal[None, :]
+        assert q_start.shape == q_goal.shape and q_start.shape[1] == robot.n_dof
+        self.R, self.n = q_start.shape
+        self.P = params.n_points
+        self.m = self.P - 2
+        ids = np.ascontiguousarray(sdf_ids, dtype=np.int32)
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+            assert len(self._seeds) == self.R
+            sp = self._seeds.ctypes.data_as(c_uint_p)
+        h = C.c_void_p()
+        check(self.lib, self.lib.ocb_batch_create(engine.h, C.byref(robot.struct), C.byref(params), len(ids),
+                                                 ids.ctypes.data_as(c_int_p), self.R, dptr(q_start), dptr(q_goal),
+                                                 sp, C.byref(h)), "ocb_batch_create")
+        self.h = h
+
+    def set_traj(self, traj):
+        traj = as_f64(traj)
+        assert traj.shape == (self.R, self.P, self.n)
+        check(self.lib, self.lib.ocb_batch_set_traj(self.h, dptr(traj)), "ocb_batch_set_traj")
+
+    def enable_trace(self, on=True):
+        check(self.lib, self.lib.ocb_batch_enable_trace(self.h, int(bool(on))), "ocb_batch_enable_trace")
+
+    def capture_gradient(self, mode):
+        check(self.lib, self.lib.ocb_batch_capture_gradient(self.h, int(mode)), "ocb_batch_capture_gradient")
+
+    def iterate(self, n_iter):
+        """Returns (costs[R,3] = total/obs/smooth of the final cost-only pass, status[R])."""
+        ct, co, cs = np.empty(self.R), np.empty(self.R), np.empty(self.R)
+        st = np.empty(self.R, dtype=np.int32)
+        check(self.lib, self.lib.ocb_batch_iterate(self.h, int(n_iter), dptr(ct), dptr(co), dptr(cs),
+                                                  st.ctypes.data_as(c_int_p)), "ocb_batch_iterate")
+        return np.stack([ct, co, cs], axis=1), st
+
+    def iterate_async(self, n_iter):
+        check(self.lib, self.lib.ocb_batch_iterate_async(self.h, int(n_iter)), "ocb_batch_iterate_async")
+
+    def get_costs(self):
+        ct, co, cs = np.empty(self.R), np.empty(self.R), np.empty(self.R)
+        st = np.empty(self.R, dtype=np.int32)
+        check(self.lib, self.lib.ocb_batch_get_costs(self.h, dptr(ct), dptr(co), dptr(cs),
+                                                    st.ctypes.data_as(c_int_p)), "ocb_batch_get_costs")
+        return np.stack([ct, co, cs], axis=1), st
+
+    def get_trace(self, n_iter):
+        out = np.empty((self.R, n_iter, 3))
+        check(self.lib, self.lib.ocb_batch_get_trace(self.h, dptr(out), int(n_iter)), "ocb_batch_get_trace")
+        return out
+
+    def get_traj(self, out=None):
+        if out is None:
+            out = np.empty((self.R, self.P, self.n))
+        check(self.lib, self.lib.ocb_batch_get_traj(self.h, dptr(out)), "ocb_batch_get_traj")
+        return out
+
+    def get_gradient(self):
+        out = np.empty((self.R, self.m, self.n))
+        check(self.lib, self.lib.ocb_batch_get_gradient(self.h, dptr(out)), "ocb_batch_get_gradient")
+        return out
+
+    def best(self):
+        idx, cost = C.c_int(), C.c_double()
+        check(self.lib, self.lib.ocb_batch_best(self.h, C.byref(idx), C.byref(cost)), "ocb_batch_best")
+        return idx.value, cost.value
+
+    def device_ptrs(self):
+        t, c = C.c_void_p(), C.c_void_p()
+        check(self.lib, self.lib.ocb_batch_device_ptrs(self.h, C.byref(t), C.byref(c)), "ocb_batch_device_ptrs")
+        return t.value, c.value
+
+    def close(self):
+        if self.h:
+            self.lib.ocb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
