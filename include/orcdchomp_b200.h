@@ -176,6 +176,13 @@ int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb_params *pa
                      int n_sdfs, const int *sdf_ids, int n_runs,
                      const double *q_start, const double *q_goal,
                      const unsigned int *seeds, ocb_batch **out);
+/* Re-arm an existing batch as if it had just been created: new end points (host
+ * pointers, [R][n_dof]; NULL = keep the resident ones), straight-line
+ * trajectories, zero momentum, fresh rng (seeds NULL = keep the previous seeds).
+ * Equivalent to destroy + create with the same robot / parameters / SDFs, without
+ * re-allocating.  Asynchronous on the engine stream. */
+int ocb_batch_reset(ocb_batch *b, const double *q_start, const double *q_goal,
+                    const unsigned int *seeds);
 /* starttraj variant (mod.cpp:2373-2415): traj is [R][n_points][n_dof] */
 int ocb_batch_set_traj(ocb_batch *b, const double *traj);
 /* n_iter CHOMP iterations per run (mod.cpp:2752-2828) followed by the cost-only
@@ -208,6 +215,8 @@ int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof);
 /* device pointers (HBM) of the trajectory [R][n_points][n_dof] and costs [R][3],
  * for callers that keep everything resident (bench, NCCL gather)              */
 int ocb_batch_device_ptrs(ocb_batch *b, void **d_traj, void **d_costs);
+/* copy one run's trajectory [n_points][n_dof] to another HBM buffer (async, D2D) */
+int ocb_batch_copy_run_traj_device(ocb_batch *b, int run, void *d_dst);
 /* kernel launches issued by this engine since creation (bench bookkeeping)    */
 long ocb_engine_launch_count(const ocb_engine *e);
 

@@ -249,6 +249,7 @@ EXPORTS = {
     "ocb_flood_relabel_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, C.c_size_t]),
     "ocb_computedistancefield_host": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p, C.c_double, c_double_p, c_double_p]),
     "ocb_batch_create": (C.c_int, [C.c_void_p, C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_int, c_int_p, C.c_int, c_double_p, c_double_p, c_uint_p, C.POINTER(C.c_void_p)]),
+    "ocb_batch_reset": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_uint_p]),
     "ocb_batch_set_traj": (C.c_int, [C.c_void_p, c_double_p]),
     "ocb_batch_iterate": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
     "ocb_batch_iterate_async": (C.c_int, [C.c_void_p, C.c_int]),
@@ -262,6 +263,7 @@ EXPORTS = {
     "ocb_batch_destroy": (C.c_int, [C.c_void_p]),
     "ocb_batch_dims": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p]),
     "ocb_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "ocb_batch_copy_run_traj_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ocb_engine_launch_count": (C.c_long, [C.c_void_p]),
 }
 

@@ -495,6 +495,7 @@ struct ocb_batch
    int last_n_iter = 0;
    std::vector<void *> owned; /* device allocations to free */
    double *d_start = nullptr, *d_goal = nullptr;
+   std::vector<uint32_t> mt_host; /* seeded generator states, [R][625] (hmc only) */
 };
 
 namespace
@@ -973,7 +974,8 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       TRY(batch_alloc(b, &a.hmc_next, R));
       TRY(batch_alloc(b, &a.mt_state, R * 625));
       err = cudaMemsetAsync(a.hmc_next, 0, R * sizeof(int), e->stream); /* mod.cpp:2634 */
-      std::vector<uint32_t> st(R * 625);
+      b->mt_host.resize(R * 625);
+      std::vector<uint32_t> &st = b->mt_host;
       for (size_t r = 0; r < R; r++) seed_mt(&st[r * 625], seeds ? seeds[r] : 0u);
       if (err == cudaSuccess) err = cudaMemcpyAsync(a.mt_state, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream);
       if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
@@ -1017,6 +1019,41 @@ extern "C" int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, in
    if (n_runs) *n_runs = b->args.R;
    if (n_points) *n_points = b->args.P;
    if (n_dof) *n_dof = b->args.n;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_reset(ocb_batch *b, const double *q_start, const double *q_goal,
+                               const unsigned int *seeds)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   if ((q_start == nullptr) != (q_goal == nullptr)) return fail(OCB_ERR_ARG, "pass both end points or neither");
+   CU(cudaSetDevice(b->e->device));
+   OcbChompArgs &a = b->args;
+   const size_t R = (size_t) a.R;
+   cudaStream_t st = b->e->stream;
+   if (q_start)
+   {
+      CU(cudaMemcpyAsync(b->d_start, q_start, R * a.n * sizeof(double), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(b->d_goal, q_goal, R * a.n * sizeof(double), cudaMemcpyHostToDevice, st));
+   }
+   CU(ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, a.R, a.P, a.n, st));
+   b->e->launches++;
+   CU(cudaMemsetAsync(a.costs, 0, R * 3 * sizeof(double), st));
+   CU(cudaMemsetAsync(a.status, 0, R * sizeof(int), st));
+   if (a.use_momentum)
+   {
+      CU(cudaMemsetAsync(a.AG, 0, R * a.m * a.n * sizeof(double), st));
+      std::vector<int> ones(R, 1);
+      CU(cudaMemcpyAsync(a.leapfrog_first, ones.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st)); /* `ones` is a host temporary */
+   }
+   if (a.use_hmc)
+   {
+      if (seeds)
+         for (size_t r = 0; r < R; r++) seed_mt(&b->mt_host[r * 625], seeds[r]);
+      CU(cudaMemsetAsync(a.hmc_next, 0, R * sizeof(int), st));
+      CU(cudaMemcpyAsync(a.mt_state, b->mt_host.data(), b->mt_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+   }
    return OCB_OK;
 }
 
@@ -1153,5 +1190,15 @@ extern "C" int ocb_batch_device_ptrs(ocb_batch *b, void **d_traj, void **d_costs
    if (!b) return fail(OCB_ERR_ARG, "null batch");
    if (d_traj) *d_traj = b->args.traj;
    if (d_costs) *d_costs = b->args.costs;
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_copy_run_traj_device(ocb_batch *b, int run, void *d_dst)
+{
+   if (!b || !d_dst || run < 0 || run >= b->args.R) return fail(OCB_ERR_ARG, "bad argument");
+   CU(cudaSetDevice(b->e->device));
+   const size_t bytes = (size_t) b->args.P * b->args.n * sizeof(double);
+   CU(cudaMemcpyAsync(d_dst, b->args.traj + (size_t) run * b->args.P * b->args.n, bytes,
+                      cudaMemcpyDeviceToDevice, b->e->stream));
    return OCB_OK;
 }

@@ -138,6 +138,18 @@ class Batch:
                                                  sp, C.byref(h)), "ocb_batch_create")
         self.h = h
 
+    def reset(self, q_start=None, q_goal=None, seeds=None):
+        """Re-arm the batch (straight lines, zero momentum, fresh rng); async."""
+        qs = qg = sp = None
+        if q_start is not None:
+            self._qs, self._qg = as_f64(q_start), as_f64(q_goal)
+            assert self._qs.shape == (self.R, self.n) and self._qg.shape == (self.R, self.n)
+            qs, qg = dptr(self._qs), dptr(self._qg)
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+            sp = self._seeds.ctypes.data_as(c_uint_p)
+        check(self.lib, self.lib.ocb_batch_reset(self.h, qs, qg, sp), "ocb_batch_reset")
+
     def set_traj(self, traj):
         traj = as_f64(traj)
         assert traj.shape == (self.R, self.P, self.n)
@@ -187,6 +199,10 @@ class Batch:
         idx, cost = C.c_int(), C.c_double()
         check(self.lib, self.lib.ocb_batch_best(self.h, C.byref(idx), C.byref(cost)), "ocb_batch_best")
         return idx.value, cost.value
+
+    def copy_run_traj_device(self, run, d_dst):
+        check(self.lib, self.lib.ocb_batch_copy_run_traj_device(self.h, int(run), C.c_void_p(int(d_dst))),
+              "ocb_batch_copy_run_traj_device")
 
     def device_ptrs(self):
         t, c = C.c_void_p(), C.c_void_p()

@@ -790,6 +790,9 @@ int cd_chomp_init(struct cd_chomp *c)
  *   G += A T + B (515-522); AG = Ainv G, or the leapfrog momentum form (525-548)
  *   T -= AG/lambda (604-605); joint-limit projection loop (608-655)
  *   cost_smooth = tr(1/2 T^T A T + B^T T) + trC on the updated T (660-671) */
+/* test hook (port only): largest number of joint-limit rounds any iteration needed */
+int orc_debug_max_limit_rounds = 0;
+
 int cd_chomp_iterate(struct cd_chomp *c, int do_iteration, double *costp_total,
                      double *costp_obs, double *costp_smooth)
 {
@@ -863,6 +866,7 @@ int cd_chomp_iterate(struct cd_chomp *c, int do_iteration, double *costp_total,
           * i.e. it assumes ldt == n */
          for (i = 0; i < m * n; i++) c->T[i] += scale * c->GjlimitAinv[i];
       }
+      if (round > orc_debug_max_limit_rounds) orc_debug_max_limit_rounds = round;
       if (!(round < 1000))
       {
          printf("ran too many joint limit fixes! aborting ...\n");

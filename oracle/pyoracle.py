@@ -98,6 +98,17 @@ def load(flavour="port"):
     return lib
 
 
+def debug_limit_rounds(reset=False):
+    """port flavour only: the largest number of joint-limit rounds (chomp.c:608-655) any
+    iteration has needed since the last reset."""
+    lib = load("port")
+    cnt = C.c_int.in_dll(lib, "orc_debug_max_limit_rounds")
+    v = cnt.value
+    if reset:
+        cnt.value = 0
+    return v
+
+
 def best_flavour():
     """'reference' when the compiled reference is present, else 'port'."""
     return "reference" if available("reference") else "port"

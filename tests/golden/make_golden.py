@@ -1,0 +1,139 @@
+"""Regenerates tests/golden/*.npz from the REFERENCE build of the oracle
+(oracle/_ref/liboracle_ref.so = the unmodified /root/reference/src/libcd sources
++ oracle/orcdchomp_port.c).  Only runs where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+The fixtures let the GPU box (which has no /root/reference) check both the
+self-contained oracle port and the CUDA engine against reference outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from or_cdchomp_b200 import capi, models  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+FL = "reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def sdf_kat():
+    rng = np.random.default_rng(11)
+    grid = rng.normal(size=(6, 7, 5))
+    grid[2, 3, 1] = np.inf
+    grid[5, 6, 4] = np.inf
+    lengths = np.array([1.2, 0.7, 2.0])
+    pts = [rng.uniform(-0.05, 1.05, size=(400, 3)) * lengths]
+    # boundaries, cell faces and cell-centre planes
+    edge = []
+    for ax in range(3):
+        for v in (0.0, lengths[ax], lengths[ax] * 0.5, lengths[ax] / grid.shape[ax] * 1.5,
+                  lengths[ax] / grid.shape[ax] * 2.0, -1e-12, lengths[ax] * (1 + 1e-12)):
+            p = 0.37 * lengths
+            p = p.copy()
+            p[ax] = v
+            edge.append(p)
+    edge.append(np.zeros(3))
+    edge.append(lengths.copy())
+    pts.append(np.array(edge))
+    pts = np.concatenate(pts)
+    vals, grads, errs = po.sdf_sample(grid, lengths, pts, flavour=FL)
+    np.savez_compressed(os.path.join(OUT, "sdf_kat.npz"), grid=grid, lengths=lengths, points=pts,
+                        values=vals, grads=grads, errs=errs)
+
+
+def sdf_build():
+    rng = np.random.default_rng(5)
+    cases = {}
+    o = np.where(rng.uniform(size=(14, 11, 9)) < 0.08, np.inf, 0.0)
+    cases["iso"] = (o, np.array([1.4, 1.1, 0.9]))
+    o = np.where(rng.uniform(size=(9, 13, 10)) < 0.15, np.inf, 0.0)
+    cases["aniso"] = (o, np.array([1.0, 2.6, 0.5]))
+    o = np.where(rng.uniform(size=(8, 8, 12)) < 0.1, np.inf, 0.0)
+    o[rng.uniform(size=o.shape) < 0.05] = 0.3  # finite non-zero heights (treated as obstacles by the flip)
+    cases["heights"] = (o, np.array([0.8, 0.8, 1.2]))
+    cases["allfree"] = (np.zeros((4, 5, 6)), np.array([1.0, 1.0, 1.0]))
+    cases["allobs"] = (np.full((4, 5, 6), np.inf), np.array([1.0, 1.0, 1.0]))
+    out = {}
+    for k, (o, l) in cases.items():
+        out[k + "_obs"] = o
+        out[k + "_len"] = l
+        out[k + "_sdf"] = po.sdf_from_obsarray(o, l, flavour=FL)
+        out[k + "_dt"] = po.dt_sqeuc(o, l, flavour=FL)
+    np.savez_compressed(os.path.join(OUT, "sdf_build.npz"), **out)
+
+
+def occupancy():
+    prims, apos, aext = models.clutter_scene(n_boxes=10, n_balls=6, seed=3, half_span=0.9)
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.04, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    pa = capi.make_prims(gp)
+    occ = po.occupancy(pa, len(gp), sizes, lengths, 0.04, flavour=FL)
+    obs, sdf = po.computedistancefield(pa, len(gp), sizes, lengths, 0.04, flavour=FL)
+    np.savez_compressed(os.path.join(OUT, "occupancy.npz"), sizes=np.array(sizes), lengths=np.array(lengths),
+                        occ_hit=np.packbits(np.isinf(occ)), obs_hit=np.packbits(np.isinf(obs)),
+                        sdf=sdf.astype(np.float64))
+
+
+def chomp():
+    robot = models.wam7_robot()
+    kin_pose, prims, apos, aext = models.table_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.02, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    pa = capi.make_prims(gp)
+    obs, sdf = po.computedistancefield(pa, len(gp), sizes, lengths, 0.02, flavour=FL)
+    pose_world = models.pose_compose(kin_pose, gpose)
+    sd = capi.SdfDesc(sdf, lengths, pose_world)
+    out = dict(table_sdf=sdf, table_obs_hit=np.packbits(np.isinf(obs)), table_lengths=np.array(lengths),
+               table_pose=pose_world)
+    # config 1: demo start, 100 iterations
+    params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
+    starts, goals = models.random_endpoints(robot, 4)
+    starts[0], goals[0] = models.WAM7_DEMO_START, models.WAM7_DEMO_GOAL
+    trajs, traces, costs, g0 = [], [], [], []
+    for r in range(4):
+        run = po.Run(robot, params, [sd], starts[r], goals[r], flavour=FL)
+        ret, c, tr, gr = run.iterate(100, want_trace=True, want_grads=True)
+        assert ret == 0
+        trajs.append(run.traj()); traces.append(tr); costs.append(c); g0.append(gr[0])
+        run.close()
+    out.update(cfg1_starts=starts, cfg1_goals=goals, cfg1_traj=np.array(trajs), cfg1_trace=np.array(traces),
+               cfg1_costs=np.array(costs), cfg1_grad0=np.array(g0))
+    # momentum + hmc, shorter trajectory
+    params = capi.default_params(n_points=40, lambda_=50.0, obs_factor=300.0, use_momentum=1, use_hmc=1,
+                                 hmc_resample_lambda=0.05)
+    trajs, costs, moms, nexts = [], [], [], []
+    for seed in (0, 7, 123456):
+        run = po.Run(robot, params, [sd], starts[1], goals[1], seed=seed, flavour=FL)
+        ret, c, _, _ = run.iterate(60)
+        assert ret == 0
+        trajs.append(run.traj()); costs.append(c); moms.append(run.momentum()); nexts.append(run.hmc_next())
+        run.close()
+    out.update(hmc_traj=np.array(trajs), hmc_costs=np.array(costs), hmc_mom=np.array(moms),
+               hmc_next=np.array(nexts), hmc_seeds=np.array([0, 7, 123456]))
+    # derivative 2
+    params = capi.default_params(n_points=50, lambda_=200.0, derivative=2)
+    run = po.Run(robot, params, [sd], starts[2], goals[2], flavour=FL)
+    ret, c, _, _ = run.iterate(30)
+    assert ret == 0
+    out.update(d2_traj=run.traj(), d2_costs=c)
+    run.close()
+    np.savez_compressed(os.path.join(OUT, "chomp.npz"), **out)
+
+
+def mt():
+    g = po.MT(0, flavour=FL)
+    raw0 = np.array([g.next() for _ in range(1300)], dtype=np.uint64)
+    g = po.MT(20260217, flavour=FL)
+    gs = np.array([g.gaussian(0.1) for _ in range(200)])
+    np.savez_compressed(os.path.join(OUT, "mt.npz"), raw_seed0=raw0, gauss_seed20260217=gs)
+
+
+if __name__ == "__main__":
+    assert po.available("reference"), "build oracle/_ref first (needs /root/reference)"
+    sdf_kat(); sdf_build(); occupancy(); chomp(); mt()
+    print("golden fixtures written to", OUT)

@@ -1,0 +1,71 @@
+"""The C-ABI library loads and exports every symbol include/orcdchomp_b200.h declares;
+without a GPU every entry point refuses loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from or_cdchomp_b200 import capi
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "orcdchomp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_bindings_agree():
+    names = declared_functions()
+    assert len(names) >= 30
+    assert sorted(capi.EXPORTS) == names
+
+
+def test_library_exports_every_symbol():
+    lib = capi.load_library()
+    for name in declared_functions():
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.ocb_version()
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors vs the C compiler's layout (checked by compiling a probe)."""
+    import subprocess
+    import tempfile
+    probe = r'''
+    #include <stdio.h>
+    #include "orcdchomp_b200.h"
+    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(ocb_robot), sizeof(ocb_sdf), sizeof(ocb_params), sizeof(ocb_prim)); return 0; }
+    '''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c")
+        open(c, "w").write(probe)
+        exe = os.path.join(d, "p")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(capi.OcbRobot), C.sizeof(capi.OcbSdf), C.sizeof(capi.OcbParams), C.sizeof(capi.OcbPrim)]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = capi.load_library()
+    h = C.c_void_p()
+    rc = lib.ocb_engine_create(0, C.byref(h))
+    assert rc == capi.OCB_ERR_NODEVICE and not h.value
+    assert b"no CPU path" in lib.ocb_last_error()
+    from or_cdchomp_b200.engine import Engine
+    with pytest.raises(capi.OcbError):
+        Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    """nothing under or_cdchomp_b200/ may reference the oracle."""
+    pkg = os.path.join(ROOT, "or_cdchomp_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "pyoracle" not in text and "liboracle" not in text and "import oracle" not in text, f

@@ -1,0 +1,159 @@
+"""GPU parity tests of the SDF build pipeline through the C ABI: bit-exact occupancy,
+SDF within 1e-12 (BASELINE.json), against the CPU oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_path
+from or_cdchomp_b200 import capi, models
+
+pytestmark = pytest.mark.gpu
+SDF_ATOL = 1e-12
+
+
+def test_sdf_build_golden(engine):
+    gold = np.load(golden_path("sdf_build.npz"))
+    for k in ("iso", "aniso", "heights", "allfree", "allobs"):
+        sdf = engine.sdf_build(gold[k + "_obs"], gold[k + "_len"])
+        ref = gold[k + "_sdf"]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(sdf), fin), k
+        assert np.array_equal(sdf[~fin], ref[~fin]), k
+        assert np.max(np.abs(sdf[fin] - ref[fin]), initial=0.0) <= SDF_ATOL, k
+
+
+def test_sdf_build_random_shapes(engine, oracle, flavour):
+    rng = np.random.default_rng(17)
+    cases = [((2, 2, 2), (1, 1, 1), 0.3), ((33, 17, 40), (3.3, 1.7, 4.0), 0.05), ((40, 40, 40), (0.8, 0.8, 0.8), 0.02),
+             ((5, 64, 7), (1.0, 3.0, 0.2), 0.2), ((64, 3, 31), (0.64, 0.09, 0.5), 0.01)]
+    for shape, lens, frac in cases:
+        obs = np.where(rng.uniform(size=shape) < frac, np.inf, 0.0)
+        sdf = engine.sdf_build(obs, lens)
+        ref = oracle.sdf_from_obsarray(obs, lens, flavour=flavour)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(sdf), fin)
+        assert np.max(np.abs(sdf[fin] - ref[fin]), initial=0.0) <= SDF_ATOL, shape
+
+
+def test_dt_sqeuc_device(engine, oracle, flavour):
+    """cd_grid_double_dt_sqeuc alone, on HBM pointers, arbitrary finite heights."""
+    rng = np.random.default_rng(4)
+    f = rng.uniform(0, 0.5, size=(12, 20, 9))
+    f[rng.uniform(size=f.shape) < 0.6] = np.inf
+    lens = (1.2, 1.0, 1.8)
+    d_in = torch.from_numpy(f).cuda()
+    d_out = torch.empty_like(d_in)
+    engine.dt_sqeuc_device(d_in.data_ptr(), f.shape, lens, d_out.data_ptr())
+    engine.sync()
+    ref = oracle.dt_sqeuc(f, lens, flavour=flavour)
+    assert np.max(np.abs(d_out.cpu().numpy() - ref)) <= SDF_ATOL
+
+
+def test_occupancy_flood_sdf_pipeline(engine, oracle, flavour):
+    """computedistancefield after the sizing: occupancy bit-exact, flood + relabel bit-exact, SDF 1e-12."""
+    gold = np.load(golden_path("occupancy.npz"))
+    prims, apos, aext = models.clutter_scene(n_boxes=10, n_balls=6, seed=3, half_span=0.9)
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.04, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    n = int(np.prod(sizes))
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    engine.occupancy_device(gp, sizes, lengths, 0.04, d.data_ptr())
+    occ = d.cpu().numpy().reshape(sizes)
+    assert set(np.unique(occ[np.isfinite(occ)])) == {1.0}
+    assert np.array_equal(np.packbits(np.isinf(occ)), gold["occ_hit"])
+    engine.flood_relabel_device(d.data_ptr(), sizes, 0)
+    engine.sync()
+    obs = d.cpu().numpy().reshape(sizes)
+    assert np.array_equal(np.packbits(np.isinf(obs)), gold["obs_hit"])
+    obs2, sdf = engine.computedistancefield(gp, sizes, lengths, 0.04)
+    assert np.array_equal(obs2, obs)
+    assert np.max(np.abs(sdf - gold["sdf"])) <= SDF_ATOL
+    # a second, larger random scene directly against the oracle
+    prims, apos, aext = models.clutter_scene(n_boxes=24, n_balls=12, seed=8, half_span=1.2)
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.025, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    obs_g, sdf_g = engine.computedistancefield(gp, sizes, lengths, 0.025)
+    pa = capi.make_prims(gp)
+    obs_r, sdf_r = oracle.computedistancefield(pa, len(gp), sizes, lengths, 0.025, flavour=flavour)
+    assert np.array_equal(obs_g, obs_r)
+    assert np.max(np.abs(sdf_g - sdf_r)) <= SDF_ATOL
+
+
+def test_flood_encloses_pocket(engine):
+    t, h = 0.03, 0.3
+    slabs = []
+    for ax in range(3):
+        for sgn in (-1, 1):
+            c = [0.0, 0.0, 0.0]
+            c[ax] = sgn * h
+            e = [h + t, h + t, h + t]
+            e[ax] = t
+            slabs.append(("box", models.pose_make(c), tuple(e)))
+    sizes, lengths, gpose = models.field_geometry((0, 0, 0), (h + t,) * 3, 0.02, 0.1)
+    gp = models.prims_to_grid_frame(slabs, gpose)
+    obs, sdf = engine.computedistancefield(gp, sizes, lengths, 0.02)
+    mid = tuple(s // 2 for s in sizes)
+    assert np.isinf(obs[mid]) and obs[0, 0, 0] == 0.0 and sdf[mid] < 0 and sdf[0, 0, 0] > 0
+
+
+def test_sdf_sampling_matches_oracle_through_cost(engine, oracle, flavour, wam7, table):
+    """cd_grid_double_interp / grad on the device are exercised through the obstacle-only
+    gradient with self-collision off, against the oracle (covers in-range / out-of-range spheres)."""
+    params = capi.default_params(n_points=60, lambda_=100.0, obs_factor=500.0, obs_factor_self=0.0)
+    starts, goals = models.random_endpoints(wam7, 8, seed0=555)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    b.capture_gradient(2)
+    b.iterate(1)
+    g = b.get_gradient()
+    hit = 0
+    for r in range(8):
+        run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
+        og, oc = run.obstacle_gradient()
+        og = og / (params.n_points - 2)
+        if np.abs(og).max() > 0:
+            hit += 1
+            assert np.max(np.abs(g[r] - og)) <= 1e-9 * np.abs(og).max()
+        run.close()
+    assert hit >= 4
+    b.close()
+    engine.remove_sdf(sid)
+
+
+def test_full_size_sdf_properties(engine):
+    """BASELINE configs[2] scale (400^3, cube_extent 0.005 -> 0.01 m voxels): properties that do
+    not need the CPU oracle at this size."""
+    prims, apos, aext = models.clutter_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.005, 0.2)
+    assert list(sizes) == [400, 400, 400]
+    gp = models.prims_to_grid_frame(prims, gpose)
+    n = int(np.prod(sizes))
+    d_obs = torch.empty(n, dtype=torch.float64, device="cuda")
+    d_sdf = torch.empty(n, dtype=torch.float64, device="cuda")
+    engine.occupancy_device(gp, sizes, lengths, 0.005, d_obs.data_ptr())
+    engine.flood_relabel_device(d_obs.data_ptr(), sizes, 0)
+    engine.sdf_build_device(d_obs.data_ptr(), sizes, lengths, d_sdf.data_ptr())
+    engine.sync()
+    obs = d_obs.view(400, 400, 400)
+    sdf = d_sdf.view(400, 400, 400)
+    occ = torch.isinf(obs)
+    assert bool(torch.isfinite(sdf).all())
+    assert 0.005 < float(occ.double().mean()) < 0.5
+    assert bool((sdf[occ] < 0).all()) and bool((sdf[~occ] > 0).all())          # sign convention
+    pitch = 0.01
+    for ax in range(3):                                                        # 1-Lipschitz along each axis
+        a = sdf.narrow(ax, 0, 399)
+        bb = sdf.narrow(ax, 1, 399)
+        assert float((a - bb).abs().max()) <= pitch * (1 + 1e-9)
+    # free cells next to an obstacle are exactly one voxel away, and vice versa
+    near = occ[1:, :, :] ^ occ[:-1, :, :]
+    assert float((sdf[1:, :, :][near].abs() - pitch).abs().max()) < 1e-12
+    # exactness on a random sample of cells against brute force over the obstacle set
+    oc = occ.nonzero().double()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    pick = torch.randint(0, 400, (64, 3), generator=g).cuda()
+    for p in pick:
+        if bool(occ[p[0], p[1], p[2]]):
+            continue
+        d = ((oc - p.double()) * pitch).pow(2).sum(1).min().sqrt()
+        assert abs(float(d) - float(sdf[p[0], p[1], p[2]])) < 1e-12

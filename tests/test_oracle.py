@@ -1,0 +1,210 @@
+"""CPU tests of the checker itself: the self-contained oracle port
+(oracle/libcd_port.c + oracle/orcdchomp_port.c) against
+  (a) golden vectors generated from the reference's own libcd sources
+      (tests/golden/make_golden.py), always;
+  (b) the compiled reference (oracle/_ref), when it is present in this checkout;
+  (c) independent closed forms / brute force.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_path
+from or_cdchomp_b200 import capi, models
+
+
+def test_mt19937_matches_numpy_and_golden(oracle):
+    """gsl_rng_mt19937 restatement: seed 0 -> 4357 (GSL), raw stream == numpy's MT19937."""
+    g = oracle.MT(0)
+    raw = np.array([g.next() for _ in range(1300)], dtype=np.uint64)
+    gold = np.load(golden_path("mt.npz"))
+    assert np.array_equal(raw, gold["raw_seed0"])
+    rs = np.random.RandomState(4357)  # init_genrand(4357)
+    ref = rs.randint(0, 2 ** 32, size=1300, dtype=np.uint64)
+    assert np.array_equal(raw, ref)
+    g = oracle.MT(5489)
+    assert g.next() == 3499211612  # published first output of mt19937 for seed 5489
+    g = oracle.MT(20260217)
+    gs = np.array([g.gaussian(0.1) for _ in range(200)])
+    assert np.array_equal(gs, gold["gauss_seed20260217"])
+    g = oracle.MT(99)
+    many = np.array([g.gaussian(2.0) for _ in range(20000)])
+    assert abs(many.mean()) < 0.06 and abs(many.std() - 2.0) < 0.05
+
+
+def test_sdf_sampling_kat(oracle):
+    """cd_grid_lookup_index / interp / grad known answers incl. edges (grid.c:191-209, 331-454)."""
+    gold = np.load(golden_path("sdf_kat.npz"))
+    vals, grads, errs = oracle.sdf_sample(gold["grid"], gold["lengths"], gold["points"])
+    assert np.array_equal(errs, gold["errs"])
+    ok = errs == 0
+    assert ok.sum() > 300 and (~ok).sum() > 10
+    assert np.array_equal(vals[ok], gold["values"][ok])
+    fin = ok & np.isfinite(gold["values"])
+    assert np.array_equal(grads[fin], gold["grads"][fin])
+    assert np.isinf(gold["values"][ok]).sum() >= 1  # HUGE_VAL stencil cases are covered
+
+
+def test_sdf_sampling_semantics(oracle):
+    """x == length is inside (last cell); value is continuous across cell-centre planes."""
+    grid = np.arange(4 * 3 * 5, dtype=np.float64).reshape(4, 3, 5) ** 1.1
+    lengths = np.array([2.0, 1.5, 2.5])
+    v, g, e = oracle.sdf_sample(grid, lengths, [[2.0, 1.5, 2.5], [2.0000001, 1.0, 1.0], [-1e-9, 1, 1]])
+    assert list(e) == [0, 1, 1]
+    c = 0.5 * (2.0 / 4) * 3  # centre plane of cell 1 on axis 0
+    v, g, e = oracle.sdf_sample(grid, lengths, [[c - 1e-9, 0.7, 1.2], [c + 1e-9, 0.7, 1.2]])
+    assert abs(v[0] - v[1]) < 1e-6 and g[0, 0] != g[1, 0]
+
+
+def test_sdf_build_golden(oracle):
+    gold = np.load(golden_path("sdf_build.npz"))
+    for k in ("iso", "aniso", "heights", "allfree", "allobs"):
+        obs, ln = gold[k + "_obs"], gold[k + "_len"]
+        sdf = oracle.sdf_from_obsarray(obs, ln)
+        dt = oracle.dt_sqeuc(obs, ln)
+        assert np.array_equal(dt, gold[k + "_dt"]), k
+        if k.startswith("all"):
+            assert np.array_equal(sdf, gold[k + "_sdf"])
+        else:
+            assert np.array_equal(sdf, gold[k + "_sdf"]), k
+
+
+def test_edt_brute_force(oracle):
+    """exact squared EDT vs brute force, anisotropic pitch (SURVEY section 4 iii)."""
+    rng = np.random.default_rng(2)
+    shape, lengths = (9, 7, 11), np.array([0.9, 1.4, 0.55])
+    obs = np.where(rng.uniform(size=shape) < 0.07, 0.0, np.inf)  # seeds are the zeros
+    dt = oracle.dt_sqeuc(obs, lengths)
+    pitch = lengths / np.array(shape)
+    idx = np.argwhere(obs == 0.0)
+    grid = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), -1).reshape(-1, 3)
+    d2 = (((grid[:, None, :] - idx[None, :, :]) * pitch) ** 2).sum(-1).min(1).reshape(shape)
+    assert np.max(np.abs(dt - d2)) < 1e-12
+    # SDF sign convention: positive in free space, negative inside obstacles
+    occ = np.where(rng.uniform(size=shape) < 0.3, np.inf, 0.0)
+    sdf = oracle.sdf_from_obsarray(occ, lengths)
+    assert (sdf[occ == 0.0] > 0).all() and (sdf[np.isinf(occ)] < 0).all()
+
+
+def test_occupancy_and_flood_golden(oracle):
+    gold = np.load(golden_path("occupancy.npz"))
+    prims, apos, aext = models.clutter_scene(n_boxes=10, n_balls=6, seed=3, half_span=0.9)
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.04, 0.2)
+    assert list(sizes) == list(gold["sizes"])
+    gp = models.prims_to_grid_frame(prims, gpose)
+    pa = capi.make_prims(gp)
+    occ = oracle.occupancy(pa, len(gp), sizes, lengths, 0.04)
+    obs, sdf = oracle.computedistancefield(pa, len(gp), sizes, lengths, 0.04)
+    assert np.array_equal(np.packbits(np.isinf(occ)), gold["occ_hit"])
+    assert np.array_equal(np.packbits(np.isinf(obs)), gold["obs_hit"])
+    assert np.array_equal(sdf, gold["sdf"])
+    assert set(np.unique(obs[np.isfinite(obs)])) <= {0.0}
+    assert np.isinf(obs).sum() >= np.isinf(occ).sum()  # enclosed pockets can only add obstacles
+
+
+def test_flood_fill_encloses_pocket(oracle):
+    """a hollow box: the inside is not reachable from voxel 0 and becomes obstacle (mod.cpp:543-548)."""
+    # two nested boxes are not expressible as a hollow primitive; build the shell from 6 slabs
+    t, h = 0.03, 0.3
+    slabs = []
+    for ax in range(3):
+        for sgn in (-1, 1):
+            c = [0.0, 0.0, 0.0]
+            c[ax] = sgn * h
+            e = [h + t, h + t, h + t]
+            e[ax] = t
+            slabs.append(("box", models.pose_make(c), tuple(e)))
+    sizes, lengths, gpose = models.field_geometry((0, 0, 0), (h + t,) * 3, 0.02, 0.1)
+    gp = models.prims_to_grid_frame(slabs, gpose)
+    pa = capi.make_prims(gp)
+    occ = oracle.occupancy(pa, len(gp), sizes, lengths, 0.02)
+    obs, _ = oracle.computedistancefield(pa, len(gp), sizes, lengths, 0.02, want_sdf=False)
+    mid = tuple(s // 2 for s in sizes)
+    assert occ[mid] == 1.0 and np.isinf(obs[mid]) and obs[0, 0, 0] == 0.0
+
+
+def test_metric_closed_form(oracle, wam7, table):
+    """D=1, both ends fixed: straight line has cost_smooth = 1/2 (m+1) sum |dq|^2."""
+    params = capi.default_params(n_points=30, lambda_=100.0, obs_factor=0.0, obs_factor_self=0.0)
+    qs, qg = models.WAM7_DEMO_START, models.WAM7_DEMO_GOAL
+    run = oracle.Run(wam7, params, [table["desc"]], qs, qg)
+    ret, costs, _, _ = run.iterate(0)
+    m = params.n_points - 2
+    dq = (qg - qs) / (m + 1)
+    expect = 0.5 * (m + 1) * (m + 1) * float(dq @ dq)
+    assert ret == 0 and abs(costs[2] - expect) < 1e-9 * expect and costs[1] == 0.0
+    run.close()
+
+
+def test_chomp_golden(oracle, wam7):
+    """full runs (config 1 + random + momentum/HMC + derivative 2) against reference outputs."""
+    gold = np.load(golden_path("chomp.npz"))
+    sd = capi.SdfDesc(gold["table_sdf"], gold["table_lengths"], gold["table_pose"])
+    params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
+    for r in range(2):
+        run = oracle.Run(wam7, params, [sd], gold["cfg1_starts"][r], gold["cfg1_goals"][r])
+        ret, c, tr, gr = run.iterate(100, want_trace=True, want_grads=True)
+        assert ret == 0
+        assert np.max(np.abs(run.traj() - gold["cfg1_traj"][r])) < 1e-9
+        assert np.max(np.abs(tr - gold["cfg1_trace"][r])) < 1e-8
+        assert np.max(np.abs(gr[0] - gold["cfg1_grad0"][r])) < 1e-9 * np.max(np.abs(gold["cfg1_grad0"][r]))
+        run.close()
+    params = capi.default_params(n_points=40, lambda_=50.0, obs_factor=300.0, use_momentum=1, use_hmc=1,
+                                 hmc_resample_lambda=0.05)
+    for k, seed in enumerate(gold["hmc_seeds"]):
+        run = oracle.Run(wam7, params, [sd], gold["cfg1_starts"][1], gold["cfg1_goals"][1], seed=int(seed))
+        ret, c, _, _ = run.iterate(60)
+        assert ret == 0 and run.hmc_next() == gold["hmc_next"][k]
+        assert np.max(np.abs(run.traj() - gold["hmc_traj"][k])) < 1e-8
+        assert np.max(np.abs(run.momentum() - gold["hmc_mom"][k])) < 1e-8
+        run.close()
+    params = capi.default_params(n_points=50, lambda_=200.0, derivative=2)
+    run = oracle.Run(wam7, params, [sd], gold["cfg1_starts"][2], gold["cfg1_goals"][2])
+    ret, c, _, _ = run.iterate(30)
+    assert ret == 0 and np.max(np.abs(run.traj() - gold["d2_traj"])) < 1e-8
+    run.close()
+
+
+def test_port_vs_compiled_reference(oracle, wam7, table):
+    """(b): the port against the reference's own compiled sources, when present here."""
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built in this checkout (needs /root/reference)")
+    rng = np.random.default_rng(3)
+    obs = np.where(rng.uniform(size=(12, 10, 15)) < 0.1, np.inf, 0.0)
+    ln = [1.2, 0.8, 1.7]
+    assert np.array_equal(oracle.sdf_from_obsarray(obs, ln, "port"), oracle.sdf_from_obsarray(obs, ln, "reference"))
+    grid = rng.normal(size=(5, 6, 7))
+    pts = rng.uniform(-0.1, 1.1, size=(500, 3)) * np.array(ln)
+    a, b = oracle.sdf_sample(grid, ln, pts, "port"), oracle.sdf_sample(grid, ln, pts, "reference")
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    fa, fb = oracle.fk(wam7, models.WAM7_DEMO_START, "port"), oracle.fk(wam7, models.WAM7_DEMO_START, "reference")
+    assert np.max(np.abs(fa - fb)) < 1e-15
+    robot = models.prismatic_test_robot()
+    for rb, P, kw in ((wam7, 60, {}), (robot, 25, {}), (wam7, 30, dict(use_momentum=1, use_hmc=1))):
+        params = capi.default_params(n_points=P, lambda_=80.0, obs_factor=400.0, **kw)
+        starts, goals = models.random_endpoints(rb, 1, seed0=77)
+        outs = []
+        for fl in ("port", "reference"):
+            run = oracle.Run(rb, params, [table["desc"]], starts[0], goals[0], seed=5, flavour=fl)
+            ret, c, tr, _ = run.iterate(40, want_trace=True)
+            outs.append((ret, run.traj(), tr))
+            run.close()
+        assert outs[0][0] == outs[1][0] == 0
+        assert np.max(np.abs(outs[0][1] - outs[1][1])) < 1e-10
+        assert np.max(np.abs(outs[0][2] - outs[1][2])) < 1e-8
+
+
+def test_fk_jacobian_finite_difference(oracle):
+    """restated FK / Jacobian are mutually consistent: obstacle gradient == d cost / d q numerically."""
+    robot = models.prismatic_test_robot()
+    rng = np.random.default_rng(1)
+    sdf = rng.uniform(0.05, 0.4, size=(12, 12, 12))
+    # smooth field so the piecewise-constant gradient equals the derivative of the interpolant
+    x = (np.arange(12) + 0.5) / 12
+    sdf = 0.3 + 0.2 * x[:, None, None] - 0.15 * x[None, :, None] + 0.1 * x[None, None, :]
+    sd = capi.SdfDesc(sdf, [1.5, 1.5, 1.5], models.pose_make((-0.7, -0.7, -0.3)))
+    params = capi.default_params(n_points=7, epsilon=1.0, obs_factor=10.0, obs_factor_self=0.0)
+    starts, goals = models.random_endpoints(robot, 1, seed0=5)
+    run = oracle.Run(robot, params, [sd], starts[0], goals[0])
+    g, c = run.obstacle_gradient()
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    run.close()
