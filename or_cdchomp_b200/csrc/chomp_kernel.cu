@@ -63,100 +63,183 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 }
 
 /* ------------------------------------------------------------------------- */
-/* forward kinematics of waypoint t: sphere centres, joint axes and origins.
+/* Shared-memory carve-up, computed identically on host and device. */
+struct SmemLayout
+{
+   int T, G, AG, red, ws, cut2, radius; /* offsets in doubles */
+   int sdf, sph, desc, mt, ired;        /* offsets in bytes   */
+   int bytes;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(const OcbChompArgs &a, int ws_in_smem)
+{
+   SmemLayout l;
+   int d = 0;
+   l.T = d; d += a.n * a.Ppad;
+   l.G = d; d += a.n * a.Ppad;
+   l.AG = d; d += a.use_momentum ? a.n * a.Ppad : 0;
+   l.red = d; d += 36;
+   l.ws = d; d += ws_in_smem ? (int) a.ws_stride : 0;
+   l.cut2 = d; d += ws_in_smem ? a.nsa * (a.NAp + a.nsi) : 0;
+   l.radius = d; d += ws_in_smem ? (a.nsa + a.nsi) : 0;
+   int b = d * 8;
+   l.sdf = b; b += a.nsdf * (int) sizeof(OcbSdfDev);
+   l.sph = b; b += ws_in_smem ? a.nsa * (int) sizeof(OcbSphereDev) : 0;
+   l.desc = b; b += ws_in_smem ? a.n_desc * 4 : 0;
+   l.mt = b; b += a.use_hmc ? 626 * 4 : 0;
+   l.ired = b; b += 40 * 4;
+   l.bytes = b;
+   return l;
+}
+
+/* read-only tables: in shared memory for the common small-robot case, else in HBM */
+struct Tables
+{
+   const OcbSphereDev *sph;
+   const int *desc;
+   const double *cut2;
+   const double *radius;
+   const OcbSdfDev *sdfs;
+};
+
+/* ------------------------------------------------------------------------- */
+/* One step of the forward sweep over the compiled joint tree for waypoint t:
+ * on return (R, tr) is joint j's frame after its motion and (ax, org) its axis
+ * (local z) and a point on it, in the world frame.  Frames needed again at a
+ * branch are saved to / loaded from the `slots` rows of ws. */
+template <bool SAVE>
+__device__ __forceinline__ void fk_step(const OcbJointDev &J, const double *__restrict__ Ts, double *__restrict__ slots,
+                                        int Pp, int t, double R[9], double tr[3], double ax[3], double org[3])
+{
+   double Rn[9], tn[3];
+   if (J.load == OCB_LOAD_BASE)
+   {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rn[k] = J.XR[k];
+      tn[0] = J.Xt[0]; tn[1] = J.Xt[1]; tn[2] = J.Xt[2];
+   }
+   else
+   {
+      if (J.load >= 0)
+      {
+         const double *sl = slots + 12 * J.load * Pp + t;
+#pragma unroll
+         for (int k = 0; k < 9; k++) R[k] = sl[k * Pp];
+#pragma unroll
+         for (int k = 0; k < 3; k++) tr[k] = sl[(9 + k) * Pp];
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+      {
+#pragma unroll
+         for (int c = 0; c < 3; c++)
+            Rn[3 * r + c] = R[3 * r] * J.XR[c] + R[3 * r + 1] * J.XR[3 + c] + R[3 * r + 2] * J.XR[6 + c];
+         tn[r] = R[3 * r] * J.Xt[0] + R[3 * r + 1] * J.Xt[1] + R[3 * r + 2] * J.Xt[2] + tr[r];
+      }
+   }
+   const double q = Ts[J.dof * Pp + t];
+   const double v = fma(J.c0, q, J.c1);
+   ax[0] = Rn[2]; ax[1] = Rn[5]; ax[2] = Rn[8];
+   org[0] = tn[0]; org[1] = tn[1]; org[2] = tn[2];
+   if (J.type == OCB_JOINT_REVOLUTE)
+   {
+      double s, c;
+      sincos(v, &s, &c);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+      {
+         R[3 * r] = c * Rn[3 * r] + s * Rn[3 * r + 1];
+         R[3 * r + 1] = c * Rn[3 * r + 1] - s * Rn[3 * r];
+         R[3 * r + 2] = Rn[3 * r + 2];
+         tr[r] = tn[r];
+      }
+   }
+   else
+   {
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+      {
+         R[3 * r] = Rn[3 * r];
+         R[3 * r + 1] = Rn[3 * r + 1];
+         R[3 * r + 2] = Rn[3 * r + 2];
+         tr[r] = fma(v, Rn[3 * r + 2], tn[r]);
+      }
+   }
+   if (SAVE && J.save >= 0)
+   {
+      double *sl = slots + 12 * J.save * Pp + t;
+#pragma unroll
+      for (int k = 0; k < 9; k++) sl[k * Pp] = R[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sl[(9 + k) * Pp] = tr[k];
+   }
+}
+
+/* forward kinematics of waypoint t: world positions of the active spheres.
  * Replaces SetActiveDOFValues + GetTransform()*pos (mod.cpp:1026-1038). */
-__device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const double *__restrict__ Ts,
-                                            double *__restrict__ ws, int t)
+__device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables &tb,
+                                            const double *__restrict__ Ts, double *__restrict__ ws, int t)
 {
    const int Pp = a.Ppad;
-   double *jax = ws + (size_t) 3 * a.nsa * Pp;
-   double *slots = jax + (size_t) 6 * a.nj * Pp;
-   double R[9], tr[3];
+   double *slots = ws + 3 * a.nsa * Pp;
+   double R[9], tr[3], ax[3], org[3];
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
-
    for (int j = 0; j < a.nj; j++)
    {
       const OcbJointDev &J = a.joints[j];
-      double Rn[9], tn[3];
-      if (J.load == OCB_LOAD_BASE)
-      {
-#pragma unroll
-         for (int k = 0; k < 9; k++) Rn[k] = J.XR[k];
-         tn[0] = J.Xt[0]; tn[1] = J.Xt[1]; tn[2] = J.Xt[2];
-      }
-      else
-      {
-         if (J.load >= 0)
-         {
-            const double *sl = slots + (size_t) 12 * J.load * Pp + t;
-#pragma unroll
-            for (int k = 0; k < 9; k++) R[k] = sl[(size_t) k * Pp];
-#pragma unroll
-            for (int k = 0; k < 3; k++) tr[k] = sl[(size_t) (9 + k) * Pp];
-         }
-#pragma unroll
-         for (int r = 0; r < 3; r++)
-         {
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-               Rn[3 * r + c] = R[3 * r] * J.XR[c] + R[3 * r + 1] * J.XR[3 + c] + R[3 * r + 2] * J.XR[6 + c];
-            tn[r] = R[3 * r] * J.Xt[0] + R[3 * r + 1] * J.Xt[1] + R[3 * r + 2] * J.Xt[2] + tr[r];
-         }
-      }
-      const double q = Ts[J.dof * Pp + t];
-      const double v = fma(J.c0, q, J.c1);
-      /* joint axis (local z) and a point on it, in the world frame */
-      double *jx = jax + (size_t) 6 * j * Pp + t;
-      jx[0] = Rn[2];
-      jx[(size_t) Pp] = Rn[5];
-      jx[(size_t) 2 * Pp] = Rn[8];
-      jx[(size_t) 3 * Pp] = tn[0];
-      jx[(size_t) 4 * Pp] = tn[1];
-      jx[(size_t) 5 * Pp] = tn[2];
-      if (J.type == OCB_JOINT_REVOLUTE)
-      {
-         double s, c;
-         sincos(v, &s, &c);
-#pragma unroll
-         for (int r = 0; r < 3; r++)
-         {
-            R[3 * r] = c * Rn[3 * r] + s * Rn[3 * r + 1];
-            R[3 * r + 1] = c * Rn[3 * r + 1] - s * Rn[3 * r];
-            R[3 * r + 2] = Rn[3 * r + 2];
-            tr[r] = tn[r];
-         }
-      }
-      else
-      {
-#pragma unroll
-         for (int r = 0; r < 3; r++)
-         {
-            R[3 * r] = Rn[3 * r];
-            R[3 * r + 1] = Rn[3 * r + 1];
-            R[3 * r + 2] = Rn[3 * r + 2];
-            tr[r] = fma(v, Rn[3 * r + 2], tn[r]);
-         }
-      }
-      if (J.save >= 0)
-      {
-         double *sl = slots + (size_t) 12 * J.save * Pp + t;
-#pragma unroll
-         for (int k = 0; k < 9; k++) sl[(size_t) k * Pp] = R[k];
-#pragma unroll
-         for (int k = 0; k < 3; k++) sl[(size_t) (9 + k) * Pp] = tr[k];
-      }
+      fk_step<true>(J, Ts, slots, Pp, t, R, tr, ax, org);
       for (int s = J.sph_begin; s < J.sph_end; s++)
       {
-         const double px = __ldg(&a.spheres[s].pos[0]);
-         const double py = __ldg(&a.spheres[s].pos[1]);
-         const double pz = __ldg(&a.spheres[s].pos[2]);
-         double *o = ws + (size_t) 3 * s * Pp + t;
+         const double px = tb.sph[s].pos[0], py = tb.sph[s].pos[1], pz = tb.sph[s].pos[2];
+         double *o = ws + 3 * s * Pp + t;
          o[0] = R[0] * px + R[1] * py + R[2] * pz + tr[0];
-         o[(size_t) Pp] = R[3] * px + R[4] * py + R[5] * pz + tr[1];
-         o[(size_t) 2 * Pp] = R[6] * px + R[7] * py + R[8] * pz + tr[2];
+         o[Pp] = R[3] * px + R[4] * py + R[5] * pz + tr[1];
+         o[2 * Pp] = R[6] * px + R[7] * py + R[8] * pz + tr[2];
       }
+   }
+}
+
+/* J^T f for waypoint t.  The workspace forces of sphere_cost have been gathered as
+ * one wrench (F, M about the world origin) per sphere-carrying joint frame; a second
+ * forward sweep regenerates each joint's axis and origin and contracts them with
+ * the wrench of the joint's subtree:  dC/dq_j = c0 * axis . (M - origin x F)  for a
+ * revolute joint, c0 * axis . F for a prismatic one.  This is the product with the
+ * CalculateJacobian columns (mod.cpp:1048, 1244, 1314) without storing them. */
+__device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tables &tb,
+                                               const double *__restrict__ Ts, double *__restrict__ ws,
+                                               double *__restrict__ Gs, int t)
+{
+   const int Pp = a.Ppad;
+   double *slots = ws + 3 * a.nsa * Pp;
+   const double *Wg = ws + (3 * a.nsa + 12 * a.n_slots) * Pp + t;
+   double R[9], tr[3], ax[3], org[3];
+#pragma unroll
+   for (int k = 0; k < 9; k++) R[k] = 0.0;
+   tr[0] = tr[1] = tr[2] = 0.0;
+   for (int j = 0; j < a.nj; j++)
+   {
+      const OcbJointDev &J = a.joints[j];
+      fk_step<false>(J, Ts, slots, Pp, t, R, tr, ax, org);
+      double F0 = 0.0, F1 = 0.0, F2 = 0.0, M0 = 0.0, M1 = 0.0, M2 = 0.0;
+      for (int di = J.desc_begin; di < J.desc_end; di++)
+      {
+         const double *Wo = Wg + 6 * tb.desc[di] * Pp;
+         F0 += Wo[0]; F1 += Wo[Pp]; F2 += Wo[2 * Pp];
+         M0 += Wo[3 * Pp]; M1 += Wo[4 * Pp]; M2 += Wo[5 * Pp];
+      }
+      double val;
+      if (J.type == OCB_JOINT_REVOLUTE)
+      {
+         const double mx = M0 - (org[1] * F2 - org[2] * F1);
+         const double my = M1 - (org[2] * F0 - org[0] * F2);
+         const double mz = M2 - (org[0] * F1 - org[1] * F0);
+         val = ax[0] * mx + ax[1] * my + ax[2] * mz;
+      }
+      else
+         val = ax[0] * F0 + ax[1] * F1 + ax[2] * F2;
+      Gs[J.dof * Pp + t] = fma(J.c0, val, Gs[J.dof * Pp + t]);
    }
 }
 
@@ -176,34 +259,26 @@ __device__ __forceinline__ bool sdf_sample(const OcbSdfDev &S, const double g[3]
       if (s >= S.size[ax]) s = S.size[ax] - 1;
       sub[ax] = s;
    }
-   const size_t stride[3] = {(size_t) S.size[1] * S.size[2], (size_t) S.size[2], 1};
-   const size_t idx = ((size_t) sub[0] * S.size[1] + sub[1]) * S.size[2] + sub[2];
-   double centre[3];
-   bool next[3];
-   size_t nb[3];
-#pragma unroll
-   for (int ax = 0; ax < 3; ax++)
-   {
-      centre[ax] = (0.5 + sub[ax]) * S.cell[ax];
-      next[ax] = (sub[ax] == 0) || (sub[ax] != S.size[ax] - 1 && !(g[ax] < centre[ax]));
-      nb[ax] = next[ax] ? idx + stride[ax] : idx - stride[ax];
-   }
+   const long long stride0 = (long long) S.size[1] * S.size[2], stride1 = S.size[2];
+   const long long idx = ((long long) sub[0] * S.size[1] + sub[1]) * S.size[2] + sub[2];
+   double c0 = (0.5 + sub[0]) * S.cell[0], c1 = (0.5 + sub[1]) * S.cell[1], c2 = (0.5 + sub[2]) * S.cell[2];
+   const bool nx0 = (sub[0] == 0) || (sub[0] != S.size[0] - 1 && !(g[0] < c0));
+   const bool nx1 = (sub[1] == 0) || (sub[1] != S.size[1] - 1 && !(g[1] < c1));
+   const bool nx2 = (sub[2] == 0) || (sub[2] != S.size[2] - 1 && !(g[2] < c2));
    const double c = __ldg(S.data + idx);
-   const double n0 = __ldg(S.data + nb[0]);
-   const double n1 = __ldg(S.data + nb[1]);
-   const double n2 = __ldg(S.data + nb[2]);
-   const double nbv[3] = {n0, n1, n2};
+   const double n0 = __ldg(S.data + (nx0 ? idx + stride0 : idx - stride0));
+   const double n1 = __ldg(S.data + (nx1 ? idx + stride1 : idx - stride1));
+   const double n2 = __ldg(S.data + (nx2 ? idx + 1 : idx - 1));
    const double inf = HUGE_VAL;
-   bool bad = (c == inf) || (n0 == inf) || (n1 == inf) || (n2 == inf);
+   const bool bad = (c == inf) || (n0 == inf) || (n1 == inf) || (n2 == inf);
+   const double s2 = (nx2 ? (n2 - c) : (c - n2)) * S.scale[2];
+   const double s1 = (nx1 ? (n1 - c) : (c - n1)) * S.scale[1];
+   const double s0 = (nx0 ? (n0 - c) : (c - n0)) * S.scale[0];
    double value = c;
-#pragma unroll
-   for (int ax = 2; ax >= 0; ax--)
-   {
-      const double diff = next[ax] ? (nbv[ax] - c) : (c - nbv[ax]);
-      const double slope = diff * S.scale[ax];
-      gg[ax] = slope;
-      value = fma(slope, g[ax] - centre[ax], value);
-   }
+   value = fma(s2, g[2] - c2, value);
+   value = fma(s1, g[1] - c1, value);
+   value = fma(s0, g[0] - c0, value);
+   gg[0] = s0; gg[1] = s1; gg[2] = s2;
    val = bad ? inf : value;
    return true;
 }
@@ -211,16 +286,30 @@ __device__ __forceinline__ bool sdf_sample(const OcbSdfDev &S, const double g[3]
 /* ------------------------------------------------------------------------- */
 /* cost (and, when want_grad, the configuration-space gradient row) of moving
  * waypoint t (1..P-2).  Restates sphere_cost (mod.cpp:1134-1327) on top of the
- * finite differences of sphere_cost_pre (mod.cpp:1099-1127). */
-__device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const OcbSdfDev *__restrict__ sdfs,
-                                                const double *__restrict__ ws, double *__restrict__ Gs,
+ * finite differences of sphere_cost_pre (mod.cpp:1099-1127).
+ *
+ * Self collision: the reference visits every ordered pair (s, s2) and adds
+ * (J_s - J_s2)^T x(s, s2).  Here each unordered pair is visited once; both
+ * directed terms x(s,o) and x(o,s) are formed, their difference is the net
+ * workspace force on s and its negative the force on o.  Forces are gathered as
+ * wrenches per joint frame in ws and mapped to joint space by flush_wrenches. */
+__device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tables &tb,
+                                                const double *__restrict__ Ts,
+                                                double *__restrict__ ws, double *__restrict__ Gs,
                                                 int t, bool want_grad)
 {
    const int Pp = a.Ppad;
-   const double *jax = ws + (size_t) 3 * a.nsa * Pp;
+   const int nsa = a.nsa;
+   const int row = a.NAp + a.nsi;
+   double *Wg = ws + (3 * nsa + 12 * a.n_slots) * Pp + t;
    const double inv2dt = 1.0 / (2.0 * a.dt);
    const double invdt2 = 1.0 / (a.dt * a.dt);
+   const double es = a.eps_self, inv_es = 1.0 / es, half_inv_es = 0.5 / es;
+   const double eps = a.eps, inv_eps = 1.0 / eps, half_inv_eps = 0.5 / eps;
    double cost = 0.0;
+
+   if (want_grad)
+      for (int k = 0; k < 6 * a.ng; k++) Wg[k * Pp] = 0.0;
 
    for (int j = 0; j < a.nj; j++)
    {
@@ -229,7 +318,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
       double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
       for (int s = J.sph_begin; s < J.sph_end; s++)
       {
-         const double *ps = ws + (size_t) 3 * s * Pp + t;
+         const double *ps = ws + 3 * s * Pp + t;
          double p[3], vel[3], acc[3];
 #pragma unroll
          for (int k = 0; k < 3; k++)
@@ -243,7 +332,9 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
          }
          const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
          const double vn = sqrt(vn2);
-         const double radius = __ldg(&a.spheres[s].radius);
+         const double iv2 = 1.0 / vn2; /* unguarded, as mod.cpp:1239 */
+         const bool moving = vn > 0.000001;
+         const double radius = tb.radius[s];
          double cost_s = 0.0;
          double f[3] = {0.0, 0.0, 0.0};
 
@@ -253,7 +344,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
          double bg[3] = {0.0, 0.0, 0.0};
          for (int k = 0; k < a.nsdf; k++)
          {
-            const OcbSdfDev &S = sdfs[k];
+            const OcbSdfDev &S = tb.sdfs[k];
             double g[3], d, gg[3];
 #pragma unroll
             for (int r = 0; r < 3; r++)
@@ -269,16 +360,15 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
          if (best >= 0)
          {
             const double d = best_d - radius;
-            const double eps = a.eps;
             if (d < 0.0)
                cost_s += vn * a.obs_factor * (0.5 * eps - d);
             else if (d < eps)
-               cost_s += vn * a.obs_factor * (0.5 / eps) * (d - eps) * (d - eps);
+               cost_s += vn * a.obs_factor * half_inv_eps * (d - eps) * (d - eps);
             if (want_grad)
             {
-               const OcbSdfDev &S = sdfs[best];
+               const OcbSdfDev &S = tb.sdfs[best];
                double x[3], cv[3];
-               const double sc = (d < 0.0) ? -1.0 : ((d < eps) ? (d / eps - 1.0) : 0.0);
+               const double sc = (d < 0.0) ? -1.0 : ((d < eps) ? (d * inv_eps - 1.0) : 0.0);
                const double w = vn * a.obs_factor;
 #pragma unroll
                for (int r = 0; r < 3; r++)
@@ -287,10 +377,10 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
                   x[r] = (d < eps) ? gw * sc * w : 0.0;
                   cv[r] = acc[r];
                }
-               if (vn > 0.000001)
+               if (moving)
                {
-                  const double pj = (x[0] * vel[0] + x[1] * vel[1] + x[2] * vel[2]) / vn2;
-                  const double pc = (cv[0] * vel[0] + cv[1] * vel[1] + cv[2] * vel[2]) / vn2;
+                  const double pj = (x[0] * vel[0] + x[1] * vel[1] + x[2] * vel[2]) * iv2;
+                  const double pc = (cv[0] * vel[0] + cv[1] * vel[1] + cv[2] * vel[2]) * iv2;
 #pragma unroll
                   for (int r = 0; r < 3; r++)
                   {
@@ -298,7 +388,6 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
                      cv[r] = fma(-pc, vel[r], cv[r]);
                   }
                }
-               const double iv2 = 1.0 / vn2; /* unguarded, as mod.cpp:1239 */
 #pragma unroll
                for (int r = 0; r < 3; r++)
                {
@@ -308,75 +397,103 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
             }
          }
 
-         /* --- self collision against spheres of other links (1251-1317) --- */
-         const int pb = __ldg(&a.spheres[s].pair_begin);
-         const int pe = __ldg(&a.spheres[s].pair_end);
-         for (int pi = pb; pi < pe; pi++)
+         /* --- self collision, each unordered pair once (1251-1317) --- */
+         const double *crow = tb.cut2 + s * row;
+         const double ws_self = vn * a.obs_factor_self;
+         /* a partner within range: q its centre, po its column in ws (NULL: inactive, frozen) */
+         auto in_range = [&](const double q[3], const double *po, int o)
          {
-            const int o = __ldg(&a.pairs[pi].other);
-            const double cut2 = __ldg(&a.pairs[pi].cut2);
-            double q[3];
-            if (o < a.nsa)
-            {
-               const double *po = ws + (size_t) 3 * o * Pp + t;
-               q[0] = po[0]; q[1] = po[(size_t) Pp]; q[2] = po[(size_t) 2 * Pp];
-            }
-            else
-            {
-               const double *po = a.inactive_pos + 3 * (o - a.nsa);
-               q[0] = __ldg(po); q[1] = __ldg(po + 1); q[2] = __ldg(po + 2);
-            }
             const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
             const double d2 = dx * dx + dy * dy + dz * dz;
-            if (d2 > cut2) continue;
-            const double rsum = __ldg(&a.pairs[pi].rsum);
-            const double dist = sqrt(d2);
-            const double dd = dist - rsum;
-            const double es = a.eps_self;
-            if (dd < 0.0)
-               cost_s += vn * a.obs_factor_self * (0.5 * es - dd);
-            else
-               cost_s += vn * a.obs_factor_self * (0.5 / es) * (dd - es) * (dd - es);
-            if (want_grad)
+            const double inv = rsqrt(d2);
+            const double dist = d2 * inv;
+            const double dd = dist - (radius + tb.radius[o]);
+            /* cost shape shared by both directions (1281-1289) */
+            const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
+            cost_s += ws_self * cshape;
+            double w2 = 0.0, v2[3] = {0.0, 0.0, 0.0}, r2 = 0.0;
+            bool moving2 = false;
+            if (po)
             {
-               const double sc = (dd < 0.0) ? -1.0 : ((dd < es) ? (dd / es - 1.0) : 1.0);
-               const double gh[3] = {dx / dist, dy / dist, dz / dist};
-               double x[3];
-               const double w = vn * a.obs_factor_self;
 #pragma unroll
-               for (int r = 0; r < 3; r++) x[r] = gh[r] * sc * w;
-               if (vn > 0.000001)
-               {
-                  const double pj = (x[0] * vel[0] + x[1] * vel[1] + x[2] * vel[2]) / vn2;
-#pragma unroll
-                  for (int r = 0; r < 3; r++) x[r] = fma(-pj, vel[r], x[r]);
-               }
-#pragma unroll
-               for (int r = 0; r < 3; r++) f[r] += x[r];
-               if (o < a.nsa)
-               {
-                  /* the same pair seen from the other sphere: (J2 - J)^T x2 puts -x2 on us */
-                  const double *po = ws + (size_t) 3 * o * Pp + t;
-                  double v2[3];
-#pragma unroll
-                  for (int r = 0; r < 3; r++)
-                     v2[r] = (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
-                  const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-                  const double v2n = sqrt(v2n2);
-                  const double w2 = v2n * a.obs_factor_self;
-                  double y[3];
-#pragma unroll
-                  for (int r = 0; r < 3; r++) y[r] = -gh[r] * sc * w2;
-                  if (v2n > 0.000001)
-                  {
-                     const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) / v2n2;
-#pragma unroll
-                     for (int r = 0; r < 3; r++) y[r] = fma(-pj, v2[r], y[r]);
-                  }
-#pragma unroll
-                  for (int r = 0; r < 3; r++) f[r] -= y[r];
-               }
+               for (int r = 0; r < 3; r++) v2[r] = (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
+               const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+               r2 = rsqrt(v2n2);
+               const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
+               moving2 = v2n > 0.000001;
+               w2 = v2n * a.obs_factor_self;
+               cost_s += w2 * cshape; /* the other sphere's own cost_sphere term */
             }
+            if (!want_grad) return;
+            const double sc = (dd < 0.0) ? -1.0 : ((dd < es) ? (dd * inv_es - 1.0) : 1.0);
+            const double gh[3] = {dx * inv, dy * inv, dz * inv};
+            double x[3];
+            const double wa = sc * ws_self;
+#pragma unroll
+            for (int r = 0; r < 3; r++) x[r] = gh[r] * wa;
+            if (moving)
+            {
+               const double pj = (x[0] * vel[0] + x[1] * vel[1] + x[2] * vel[2]) * iv2;
+#pragma unroll
+               for (int r = 0; r < 3; r++) x[r] = fma(-pj, vel[r], x[r]);
+            }
+            if (po)
+            {
+               /* the pair seen from o: unit vector -gh, weighted by o's speed */
+               double y[3];
+               const double wb = -sc * w2;
+#pragma unroll
+               for (int r = 0; r < 3; r++) y[r] = gh[r] * wb;
+               if (moving2)
+               {
+                  const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * (r2 * r2);
+#pragma unroll
+                  for (int r = 0; r < 3; r++) y[r] = fma(-pj, v2[r], y[r]);
+               }
+               /* (J_s - J_o)^T x + (J_o - J_s)^T y = J_s^T (x - y) - J_o^T (x - y) */
+#pragma unroll
+               for (int r = 0; r < 3; r++) x[r] -= y[r];
+               double *Wo = Wg + 6 * tb.sph[o].group * Pp;
+               Wo[0] -= x[0];
+               Wo[Pp] -= x[1];
+               Wo[2 * Pp] -= x[2];
+               Wo[3 * Pp] -= q[1] * x[2] - q[2] * x[1];
+               Wo[4 * Pp] -= q[2] * x[0] - q[0] * x[2];
+               Wo[5 * Pp] -= q[0] * x[1] - q[1] * x[0];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) f[r] += x[r];
+         };
+         /* active partners: range tests four at a time (independent chains); the padded
+          * tail of the cut2 row is -1 and never passes */
+         for (int o0 = s + 1; o0 < nsa; o0 += 4)
+         {
+            unsigned mask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+               const double *po = ws + 3 * min(o0 + k, nsa - 1) * Pp + t;
+               const double dx = p[0] - po[0], dy = p[1] - po[Pp], dz = p[2] - po[2 * Pp];
+               const double d2 = dx * dx + dy * dy + dz * dz;
+               if (d2 <= crow[o0 + k]) mask |= 1u << k;
+            }
+            if (mask == 0) continue;
+#pragma unroll 1
+            for (int k = 0; k < 4; k++)
+            {
+               if (!((mask >> k) & 1u)) continue;
+               const double *po = ws + 3 * (o0 + k) * Pp + t;
+               const double q[3] = {po[0], po[Pp], po[2 * Pp]};
+               in_range(q, po, o0 + k);
+            }
+         }
+         /* inactive partners are frozen in the world (mod.cpp:2332-2345) */
+         for (int i = 0; i < a.nsi; i++)
+         {
+            const double q[3] = {__ldg(a.inactive_pos + 3 * i), __ldg(a.inactive_pos + 3 * i + 1),
+                                 __ldg(a.inactive_pos + 3 * i + 2)};
+            const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+            if (dx * dx + dy * dy + dz * dz <= crow[a.NAp + i]) in_range(q, nullptr, nsa + i);
          }
          cost += cost_s;
          if (want_grad)
@@ -389,30 +506,12 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Ocb
       }
       if (want_grad)
       {
-         /* J^T f for the whole joint frame: every ancestor joint sees the wrench */
-         for (int ai = J.anc_begin; ai < J.anc_end; ai++)
-         {
-            const int aj = __ldg(&a.ancs[ai].joint);
-            const int dof = __ldg(&a.ancs[ai].dof);
-            const int type = __ldg(&a.ancs[ai].type);
-            const double c0 = __ldg(&a.ancs[ai].c0);
-            const double *jx = jax + (size_t) 6 * aj * Pp + t;
-            const double ax = jx[0], ay = jx[(size_t) Pp], az = jx[(size_t) 2 * Pp];
-            double val;
-            if (type == OCB_JOINT_REVOLUTE)
-            {
-               const double ox = jx[(size_t) 3 * Pp], oy = jx[(size_t) 4 * Pp], oz = jx[(size_t) 5 * Pp];
-               const double mx = M[0] - (oy * F[2] - oz * F[1]);
-               const double my = M[1] - (oz * F[0] - ox * F[2]);
-               const double mz = M[2] - (ox * F[1] - oy * F[0]);
-               val = ax * mx + ay * my + az * mz;
-            }
-            else
-               val = ax * F[0] + ay * F[1] + az * F[2];
-            Gs[dof * Pp + t] = fma(c0, val, Gs[dof * Pp + t]);
-         }
+         double *Wo = Wg + 6 * tb.sph[J.sph_begin].group * Pp;
+         Wo[0] += F[0]; Wo[Pp] += F[1]; Wo[2 * Pp] += F[2];
+         Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
       }
    }
+   if (want_grad) flush_wrenches(a, tb, Ts, ws, Gs, t);
    return cost;
 }
 
@@ -433,23 +532,24 @@ __device__ __forceinline__ double band_AT(const OcbChompArgs &a, const double *_
 
 /* banded LDL^T solve in place on x[0..m) (one dof column); replaces the product
  * with the explicit inverse (chomp.c:529-530, 540-546, 640-641) */
-__device__ __forceinline__ void band_solve(const OcbChompArgs &a, const double *__restrict__ Ls,
-                                           const double *__restrict__ dinv, double *__restrict__ x)
+__device__ __forceinline__ void band_solve(const OcbChompArgs &a, double *__restrict__ x)
 {
    const int m = a.m, bw = a.bw;
+   const double *__restrict__ Ls = a.Lband;
+   const double *__restrict__ dinv = a.dinv;
    if (bw == 1)
    {
       double prev = x[0];
       for (int i = 1; i < m; i++)
       {
-         prev = fma(-Ls[i], prev, x[i]);
+         prev = fma(-__ldg(Ls + i), prev, x[i]);
          x[i] = prev;
       }
-      prev = x[m - 1] * dinv[m - 1];
+      prev = x[m - 1] * __ldg(dinv + m - 1);
       x[m - 1] = prev;
       for (int i = m - 2; i >= 0; i--)
       {
-         prev = fma(-Ls[i + 1], prev, x[i] * dinv[i]);
+         prev = fma(-__ldg(Ls + i + 1), prev, x[i] * __ldg(dinv + i));
          x[i] = prev;
       }
       return;
@@ -457,13 +557,13 @@ __device__ __forceinline__ void band_solve(const OcbChompArgs &a, const double *
    for (int i = 0; i < m; i++)
    {
       double acc = x[i];
-      for (int k = 1; k <= bw && k <= i; k++) acc = fma(-Ls[i * bw + (k - 1)], x[i - k], acc);
+      for (int k = 1; k <= bw && k <= i; k++) acc = fma(-__ldg(Ls + i * bw + (k - 1)), x[i - k], acc);
       x[i] = acc;
    }
    for (int i = m - 1; i >= 0; i--)
    {
-      double acc = x[i] * dinv[i];
-      for (int k = 1; k <= bw && i + k < m; k++) acc = fma(-Ls[(i + k) * bw + (k - 1)], x[i + k], acc);
+      double acc = x[i] * __ldg(dinv + i);
+      for (int k = 1; k <= bw && i + k < m; k++) acc = fma(-__ldg(Ls + (i + k) * bw + (k - 1)), x[i + k], acc);
       x[i] = acc;
    }
 }
@@ -527,7 +627,8 @@ __device__ __forceinline__ ArgMax argmax_pick(ArgMax a, ArgMax b)
    return a;
 }
 
-__global__ void __launch_bounds__(256)
+template <bool WS_SMEM, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 3 : 1)
 chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -536,18 +637,41 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
    const int run = blockIdx.x;
    const int P = a.P, m = a.m, n = a.n, Pp = a.Ppad, bw = a.bw;
 
-   /* ---- shared memory carve-up (doubles first) ---- */
-   double *Ts = reinterpret_cast<double *>(smem_raw);        /* [n][Pp] */
-   double *Gs = Ts + (size_t) n * Pp;                        /* [n][Pp] */
-   double *AGs = Gs + (size_t) n * Pp;                       /* [n][Pp] (momentum only) */
-   double *Ls = AGs + (a.use_momentum ? (size_t) n * Pp : 0);/* [m][bw] */
-   double *dinv = Ls + (size_t) m * bw;                      /* [m] */
-   double *red = dinv + m;                                   /* [36] */
-   double *wsS = red + 36;
-   OcbSdfDev *sdfs = reinterpret_cast<OcbSdfDev *>(wsS + (a.ws_in_smem ? a.ws_stride : 0));
-   uint32_t *mts = reinterpret_cast<uint32_t *>(sdfs + a.nsdf); /* [625] (hmc only) */
-   int *ired = reinterpret_cast<int *>(mts + (a.use_hmc ? 626 : 0)); /* [40] */
-   double *ws = a.ws_in_smem ? wsS : (a.ws_global + (size_t) run * a.ws_stride);
+   /* ---- shared memory carve-up ---- */
+   const SmemLayout lay = smem_layout(a, WS_SMEM ? 1 : 0);
+   double *sd = reinterpret_cast<double *>(smem_raw);
+   double *Ts = sd + lay.T;     /* [n][Pp] */
+   double *Gs = sd + lay.G;     /* [n][Pp] */
+   double *AGs = sd + lay.AG;   /* [n][Pp] (momentum only) */
+   double *red = sd + lay.red;
+   OcbSdfDev *sdfs = reinterpret_cast<OcbSdfDev *>(smem_raw + lay.sdf);
+   uint32_t *mts = reinterpret_cast<uint32_t *>(smem_raw + lay.mt);
+   int *ired = reinterpret_cast<int *>(smem_raw + lay.ired);
+   double *ws;
+   Tables tb;
+   tb.sdfs = sdfs;
+   if (WS_SMEM)
+   {
+      ws = sd + lay.ws;
+      double *c2 = sd + lay.cut2, *rad = sd + lay.radius;
+      OcbSphereDev *sph = reinterpret_cast<OcbSphereDev *>(smem_raw + lay.sph);
+      int *dsc = reinterpret_cast<int *>(smem_raw + lay.desc);
+      for (int e = tid; e < a.nsa * (a.NAp + a.nsi); e += NT) c2[e] = __ldg(a.cut2 + e);
+      for (int e = tid; e < a.nsa + a.nsi; e += NT) rad[e] = __ldg(a.radius + e);
+      {
+         const int words = a.nsa * (int) (sizeof(OcbSphereDev) / 4);
+         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.spheres);
+         uint32_t *dst = reinterpret_cast<uint32_t *>(sph);
+         for (int e = tid; e < words; e += NT) dst[e] = __ldg(src + e);
+      }
+      for (int e = tid; e < a.n_desc; e += NT) dsc[e] = __ldg(a.desc + e);
+      tb.sph = sph; tb.desc = dsc; tb.cut2 = c2; tb.radius = rad;
+   }
+   else
+   {
+      ws = a.ws_global + (size_t) run * a.ws_stride;
+      tb.sph = a.spheres; tb.desc = a.desc; tb.cut2 = a.cut2; tb.radius = a.radius;
+   }
 
    /* ---- stage per-run state and shared constants ---- */
    double *traj = a.traj + (size_t) run * P * n;
@@ -557,8 +681,6 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       const double *ag = a.AG + (size_t) run * m * n;
       for (int e = tid; e < m * n; e += NT) AGs[(e % n) * Pp + (e / n) + 1] = ag[e];
    }
-   for (int e = tid; e < m * bw; e += NT) Ls[e] = __ldg(a.Lband + e);
-   for (int e = tid; e < m; e += NT) dinv[e] = __ldg(a.dinv + e);
    {
       const int words = (int) (sizeof(OcbSdfDev) / 4) * a.nsdf;
       const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sdfs);
@@ -610,7 +732,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       }
 
       /* ---- forward kinematics of all P waypoints ---- */
-      for (int t = tid; t < P; t += NT) fk_waypoint(a, Ts, ws, t);
+      for (int t = tid; t < P; t += NT) fk_waypoint(a, tb, Ts, ws, t);
       __syncthreads();
 
       /* ---- obstacle + self-collision cost / gradient, then G = G/m + A T + B ---- */
@@ -619,7 +741,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       {
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
-         csum += waypoint_cost(a, sdfs, ws, Gs, t, !final_pass);
+         csum += waypoint_cost(a, tb, Ts, ws, Gs, t, !final_pass);
          if (!final_pass)
          {
             const double bi = __ldg(a.bcoef_i + t - 1), bf = __ldg(a.bcoef_f + t - 1);
@@ -652,7 +774,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       }
 
       /* ---- AG = A^-1 G (banded solve, one thread per dof) ---- */
-      if (tid < n) band_solve(a, Ls, dinv, Gs + tid * Pp + 1);
+      if (tid < n) band_solve(a, Gs + tid * Pp + 1);
       __syncthreads();
 
       /* ---- momentum / plain update, T -= AG/lambda (chomp.c:525-548, 604-605) ---- */
@@ -725,7 +847,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
          const double worst = red[33];
          const int worst_idx = ired[33];
          if (worst == 0.0) break;
-         if (tid < n) band_solve(a, Ls, dinv, Gs + tid * Pp + 1);
+         if (tid < n) band_solve(a, Gs + tid * Pp + 1);
          __syncthreads();
          const double scale = 1.01 * red[34] / Gs[(worst_idx % n) * Pp + (worst_idx / n) + 1];
          for (int t = tid + 1; t <= m; t += NT)
@@ -832,28 +954,32 @@ __global__ void best_kernel(const double *costs, const int *status, int R, int *
 
 extern "C" size_t ocb_chomp_smem_bytes(const OcbChompArgs *a, int ws_in_smem)
 {
-   size_t d = (size_t) 2 * a->n * a->Ppad;
-   if (a->use_momentum) d += (size_t) a->n * a->Ppad;
-   d += (size_t) a->m * a->bw + a->m + 36;
-   if (ws_in_smem) d += a->ws_stride;
-   size_t bytes = d * sizeof(double) + (size_t) a->nsdf * sizeof(OcbSdfDev);
-   if (a->use_hmc) bytes += 626 * sizeof(uint32_t);
-   bytes += 40 * sizeof(int);
-   return bytes;
+   return (size_t) smem_layout(*a, ws_in_smem).bytes;
 }
 
-extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
+template <bool WS_SMEM, int NT_MAX>
+static cudaError_t launch_variant(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    static size_t configured = 0;
    if (smem_bytes > configured)
    {
-      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int) smem_bytes);
+      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel<WS_SMEM, NT_MAX>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
       if (e != cudaSuccess) return e;
       configured = smem_bytes;
    }
-   chomp_iterate_kernel<<<args->R, threads, smem_bytes, st>>>(*args);
+   chomp_iterate_kernel<WS_SMEM, NT_MAX><<<args->R, threads, smem_bytes, st>>>(*args);
    return cudaGetLastError();
+}
+
+extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
+{
+   if (threads > 256 || threads % 32) return cudaErrorInvalidValue;
+   if (args->ws_in_smem)
+      return threads <= 128 ? launch_variant<true, 128>(args, smem_bytes, threads, st)
+                            : launch_variant<true, 256>(args, smem_bytes, threads, st);
+   return threads <= 128 ? launch_variant<false, 128>(args, smem_bytes, threads, st)
+                         : launch_variant<false, 256>(args, smem_bytes, threads, st);
 }
 
 extern "C" cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const double *q_goal,

@@ -634,8 +634,9 @@ struct CompiledRobot
 {
    std::vector<OcbJointDev> joints;
    std::vector<OcbSphereDev> spheres;
-   std::vector<OcbPairDev> pairs;
-   std::vector<OcbAncDev> ancs;
+   std::vector<double> cut2, radius; /* [nsa][NS], [NS] */
+   int n_groups = 0;
+   std::vector<int> desc;
    std::vector<double> inactive_pos;
    std::vector<double> inactive_radius;
    std::vector<int> inactive_link;
@@ -728,22 +729,6 @@ int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
          D.load = slot_of[par];
       }
    }
-   /* ancestors (self first, then up the tree) */
-   for (int k = 0; k < nj; k++)
-   {
-      C.joints[k].anc_begin = (int) C.ancs.size();
-      for (int j = order[k]; j >= 0; j = raw[j].parent)
-      {
-         OcbAncDev A;
-         A.c0 = raw[j].c0;
-         A.joint = newidx[j];
-         A.dof = raw[j].dof;
-         A.type = raw[j].type;
-         A.pad = 0;
-         C.ancs.push_back(A);
-      }
-      C.joints[k].anc_end = (int) C.ancs.size();
-   }
    /* spheres: active ones grouped by joint (stable), inactive ones frozen in the world */
    struct Tmp { int joint; OcbSphereDev s; };
    std::vector<Tmp> act;
@@ -760,7 +745,7 @@ int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
          t.s.pos[0] = p[0]; t.s.pos[1] = p[1]; t.s.pos[2] = p[2];
          t.s.radius = rb->sphere_radius[s];
          t.s.link = link;
-         t.s.pair_begin = t.s.pair_end = 0;
+         t.s.group = 0;
          act.push_back(t);
       }
       else
@@ -782,24 +767,40 @@ int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
       while (i < (int) act.size() && act[i].joint == k) i++;
       C.joints[k].sph_end = i;
    }
-   const int nsa = (int) C.spheres.size(), nsi = (int) C.inactive_radius.size();
+   const int nsa = (int) C.spheres.size(), nsi = (int) C.inactive_radius.size(), NS = nsa + nsi;
+   /* compact group index per sphere-carrying joint frame */
+   C.n_groups = 0;
+   for (int k = 0; k < nj; k++)
+      if (C.joints[k].sph_end > C.joints[k].sph_begin)
+      {
+         for (int s = C.joints[k].sph_begin; s < C.joints[k].sph_end; s++) C.spheres[s].group = C.n_groups;
+         C.n_groups++;
+      }
+   C.radius.resize(NS);
+   for (int o = 0; o < NS; o++) C.radius[o] = (o < nsa) ? C.spheres[o].radius : C.inactive_radius[o - nsa];
+   const int NAp = nsa + 3; /* the 4-wide range test starts at s+1: up to 3 entries past nsa */
+   C.cut2.assign((size_t) nsa * (NAp + nsi), -1.0);
    for (int s = 0; s < nsa; s++)
-   {
-      C.spheres[s].pair_begin = (int) C.pairs.size();
-      for (int o = 0; o < nsa + nsi; o++)
+      for (int o = 0; o < NS; o++)
       {
          const int link2 = (o < nsa) ? C.spheres[o].link : C.inactive_link[o - nsa];
-         const double r2 = (o < nsa) ? C.spheres[o].radius : C.inactive_radius[o - nsa];
-         if (link2 == C.spheres[s].link) continue; /* mod.cpp:1256 */
-         OcbPairDev P;
-         P.rsum = C.spheres[s].radius + r2;
-         const double cut = C.spheres[s].radius + r2 + eps_self;
-         P.cut2 = cut * cut;
-         P.other = o;
-         P.pad = 0;
-         C.pairs.push_back(P);
+         if (o == s || link2 == C.spheres[s].link) continue; /* mod.cpp:1256 */
+         const double cut = C.spheres[s].radius + C.radius[o] + eps_self; /* mod.cpp:1268 */
+         C.cut2[(size_t) s * (NAp + nsi) + (o < nsa ? o : NAp + (o - nsa))] = cut * cut;
       }
-      C.spheres[s].pair_end = (int) C.pairs.size();
+   /* for every joint: the sphere groups carried by its subtree (its J^T sees their wrenches) */
+   for (int k = 0; k < nj; k++)
+   {
+      C.joints[k].desc_begin = (int) C.desc.size();
+      for (int k2 = 0; k2 < nj; k2++)
+      {
+         if (C.joints[k2].sph_end == C.joints[k2].sph_begin) continue;
+         bool below = false;
+         for (int j = order[k2]; j >= 0; j = raw[j].parent)
+            if (j == order[k]) { below = true; break; }
+         if (below) C.desc.push_back(C.spheres[C.joints[k2].sph_begin].group);
+      }
+      C.joints[k].desc_end = (int) C.desc.size();
    }
    return OCB_OK;
 }
@@ -893,7 +894,10 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    a.nsdf = n_sdfs;
    a.bw = params->derivative;
    a.n_slots = C.n_slots;
-   a.Ppad = P | 1;
+   a.ng = C.n_groups;
+   a.n_desc = (int) C.desc.size();
+   a.NAp = a.nsa + 3;
+   a.Ppad = P;
    a.use_momentum = params->use_momentum ? 1 : 0;
    a.use_hmc = use_hmc;
    for (int j = 0; j < a.nj; j++) a.joints[j] = C.joints[j];
@@ -934,8 +938,9 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
 
 #define TRY(x) do { rc = (x); if (rc) { ocb_batch_destroy(b); return rc; } } while (0)
    TRY(batch_upload(b, &a.spheres, C.spheres));
-   TRY(batch_upload(b, &a.pairs, C.pairs));
-   TRY(batch_upload(b, &a.ancs, C.ancs));
+   TRY(batch_upload(b, &a.cut2, C.cut2));
+   TRY(batch_upload(b, &a.radius, C.radius));
+   TRY(batch_upload(b, &a.desc, C.desc));
    TRY(batch_upload(b, &a.inactive_pos, C.inactive_pos));
    TRY(batch_upload(b, &a.sdfs, sd));
    TRY(batch_upload(b, &a.Aband, M.Aband));
@@ -986,8 +991,9 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       return fail(OCB_ERR_CUDA, "batch_create: %s", cudaGetErrorString(err));
    }
 
-   /* workspace: per waypoint 3*nsa sphere coordinates + 6*nj axis/origin + 12 per saved frame */
-   a.ws_stride = (size_t) (3 * a.nsa + 6 * a.nj + 12 * a.n_slots) * a.Ppad;
+   /* workspace: per waypoint 3*nsa sphere coordinates + 12 per saved branch frame
+    * + 6 per sphere-carrying joint frame (wrench accumulators) */
+   a.ws_stride = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
    a.ws_in_smem = 1;
    b->smem = ocb_chomp_smem_bytes(&a, 1);
    if (b->smem > (size_t) e->smem_optin)

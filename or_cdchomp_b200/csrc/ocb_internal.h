@@ -28,7 +28,7 @@ struct OcbJointDev
    int load;           /* OCB_LOAD_PREV / OCB_LOAD_BASE / slot index */
    int save;           /* slot index to save this joint's transform into, or -1 */
    int sph_begin, sph_end;   /* active spheres rigidly attached to this joint frame */
-   int anc_begin, anc_end;   /* ancestors (incl. self) in the ancestor table */
+   int desc_begin, desc_end; /* sphere groups in this joint's subtree (incl. its own), in the desc table */
 };
 
 struct OcbSphereDev
@@ -36,25 +36,7 @@ struct OcbSphereDev
    double pos[3];      /* in the joint frame */
    double radius;
    int link;           /* original robot link index (same-link pairs are skipped) */
-   int pair_begin, pair_end;
-};
-
-/* candidate self-collision partner of a sphere (different link) */
-struct OcbPairDev
-{
-   double rsum;        /* radius + radius2 */
-   double cut2;        /* (radius + radius2 + epsilon_self)^2 */
-   int other;          /* < n_active: active sphere index; else n_active + inactive index */
-   int pad;
-};
-
-struct OcbAncDev
-{
-   double c0;          /* d(value)/d(dof) */
-   int joint;
-   int dof;
-   int type;
-   int pad;
+   int group;          /* compact index of the joint frame among those that carry spheres */
 };
 
 struct OcbSdfDev
@@ -77,13 +59,19 @@ struct OcbChompArgs
    int nj, nsa, nsi, nsdf;
    int bw, n_slots, Ppad, n_iter;
    int use_momentum, use_hmc, trace_on, grad_mode; /* grad_mode 0 none, 1 full G, 2 obstacle only */
-   int ws_in_smem, pad0;
+   int ws_in_smem, ng;     /* ng: joint frames that carry spheres (wrench accumulators) */
+   int n_desc, NAp;        /* NAp: padded active part of a cut2 row (>= nsa + 3); row = NAp + nsi */
    /* robot */
    OcbJointDev joints[OCB_MAX_JOINTS];
    const OcbSphereDev *spheres;
-   const OcbPairDev *pairs;
-   const OcbAncDev *ancs;
+   const int *desc;        /* [n_desc] group indices, see OcbJointDev::desc_begin */
    const double *inactive_pos;
+   /* self-collision tables over NS = nsa + nsi spheres (active first):
+    * cut2[s][o] = (r_s + r_o + epsilon_self)^2, or -1 when s and o sit on the same link
+    * (mod.cpp:1256) so the pair never passes the range test.  Row layout: NAp entries for
+    * active partners (padded with -1), then nsi entries for inactive ones.  radius[o]. */
+   const double *cut2;
+   const double *radius;
    const OcbSdfDev *sdfs; /* [nsdf] in HBM, staged to shared memory by the kernel */
    /* metric: A band [m][2bw+1], LDL^T factors, B coefficient vectors */
    const double *Aband;

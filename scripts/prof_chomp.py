@@ -11,7 +11,7 @@ obs, sdf = eng.computedistancefield(gprims, sizes, lengths, 0.02)
 sid = eng.upload_sdf(capi.SdfDesc(sdf, lengths, pose_world))
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 its = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-starts, goals = models.random_endpoints(robot, R)
+starts, goals = models.random_endpoints(robot, R, shrink=float(os.environ.get('SHRINK', '0.3')))
 b = eng.create_batch(robot, params, [sid], starts, goals)
 b.iterate(its)
 b.reset()
