@@ -134,6 +134,10 @@ int ocb_sdf_build_host(ocb_engine *e, const double *obs, const int sizes[3],
                        const double lengths[3], double *sdf);
 int ocb_sdf_build_device(ocb_engine *e, const double *d_obs, const int sizes[3],
                          const double lengths[3], double *d_sdf);
+/* ocb_sdf_build_* picks an exact integer path when the grid holds only 0 / HUGE_VAL and
+ * its cells are cubes (what computedistancefield produces), else the general fp64 path
+ * that follows grid.c:462-569 operation for operation.  Test hook: force the latter. */
+int ocb_engine_force_general_sdf(ocb_engine *e, int on);
 /* squared Euclidean distance transform alone: cd_grid_double_dt_sqeuc (grid.c:462-569) */
 int ocb_dt_sqeuc_device(ocb_engine *e, const double *d_func, const int sizes[3],
                         const double lengths[3], double *d_out);

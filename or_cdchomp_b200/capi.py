@@ -244,6 +244,7 @@ EXPORTS = {
     "ocb_sdf_remove": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_sdf_build_host": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, c_double_p]),
     "ocb_sdf_build_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, c_double_p, C.c_void_p]),
+    "ocb_engine_force_general_sdf": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_dt_sqeuc_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, c_double_p, C.c_void_p]),
     "ocb_occupancy_device": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p, C.c_double, C.c_void_p]),
     "ocb_flood_relabel_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, C.c_size_t]),

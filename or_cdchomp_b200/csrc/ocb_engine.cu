@@ -203,6 +203,7 @@ struct ocb_engine
    long launches = 0;
    int smem_optin = 0;
    int sm_count = 0;
+   int force_general_sdf = 0; /* test hook: always take the general fp64 distance transform */
 };
 
 static int engine_scratch(ocb_engine *e, size_t bytes)
@@ -284,6 +285,13 @@ extern "C" int ocb_engine_sync(ocb_engine *e)
 }
 
 extern "C" long ocb_engine_launch_count(const ocb_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int ocb_engine_force_general_sdf(ocb_engine *e, int on)
+{
+   if (!e) return fail(OCB_ERR_ARG, "null engine");
+   e->force_general_sdf = on ? 1 : 0;
+   return OCB_OK;
+}
 
 /* --------------------------------------------------------------------- SDFs */
 static int sdf_slot_new(ocb_engine *e)
@@ -383,6 +391,15 @@ extern "C" int ocb_sdf_build_device(ocb_engine *e, const double *d_obs, const in
    int rc = check_grid(sizes, lengths);
    if (rc) return rc;
    CU(cudaSetDevice(e->device));
+   if (ocb_sdf_fast_eligible(sizes, lengths) && !e->force_general_sdf)
+   {
+      rc = engine_scratch(e, ocb_sdf_fast_scratch_bytes(sizes));
+      if (rc) return rc;
+      int used_fast = 0;
+      CU(ocb_launch_bin_sdf_fast(d_obs, d_sdf, sizes, lengths, e->scratch, e->scratch_bytes, e->stream,
+                                 &e->launches, &used_fast));
+      if (used_fast) return OCB_OK;
+   }
    rc = engine_scratch(e, ocb_sdf_scratch_bytes(sizes, lengths));
    if (rc) return rc;
    CU(ocb_launch_bin_sdf(d_obs, d_sdf, sizes, lengths, e->scratch, e->scratch_bytes, e->stream, &e->launches));

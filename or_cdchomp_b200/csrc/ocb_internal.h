@@ -118,6 +118,12 @@ cudaError_t ocb_launch_bin_sdf(const double *d_obs, double *d_sdf, const int siz
                                const double lengths[3], void *scratch, size_t scratch_bytes,
                                cudaStream_t st, long *launches);
 size_t ocb_sdf_scratch_bytes(const int sizes[3], const double lengths[3]);
+/* sdf_fast.cu: exact integer path for 0 / HUGE_VAL grids with cubic cells, axes <= 1024 */
+int ocb_sdf_fast_eligible(const int sizes[3], const double lengths[3]);
+size_t ocb_sdf_fast_scratch_bytes(const int sizes[3]);
+cudaError_t ocb_launch_bin_sdf_fast(const double *d_obs, double *d_sdf, const int sizes[3],
+                                    const double lengths[3], void *scratch, size_t scratch_bytes,
+                                    cudaStream_t st, long *launches, int *used_fast);
 cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, const int sizes[3],
                                  const double lengths[3], double cube_extent, double *d_grid,
                                  cudaStream_t st);

@@ -57,6 +57,9 @@ class Engine:
               "ocb_sdf_build_host")
         return out
 
+    def force_general_sdf(self, on=True):
+        check(self.lib, self.lib.ocb_engine_force_general_sdf(self.h, int(bool(on))), "ocb_engine_force_general_sdf")
+
     def sdf_build_device(self, d_obs, sizes, lengths, d_sdf):
         check(self.lib, self.lib.ocb_sdf_build_device(self.h, C.c_void_p(int(d_obs)), _i3(sizes), _d3(lengths),
                                                      C.c_void_p(int(d_sdf))), "ocb_sdf_build_device")

@@ -35,6 +35,41 @@ def test_sdf_build_random_shapes(engine, oracle, flavour):
         assert np.max(np.abs(sdf[fin] - ref[fin]), initial=0.0) <= SDF_ATOL, shape
 
 
+def test_fast_integer_path_equals_general_and_oracle(engine, oracle, flavour):
+    """binary grids with cubic cells take the exact integer path (sdf_fast.cu); it must agree
+    with the general fp64 path and with the oracle for awkward sizes, empty / full grids,
+    isolated seeds and lines without any seed."""
+    rng = np.random.default_rng(23)
+    cases = []
+    for shape, frac in (((2, 2, 2), 0.5), ((7, 5, 33), 0.1), ((40, 37, 70), 0.01), ((33, 64, 31), 0.3),
+                        ((16, 16, 100), 0.002), ((50, 3, 65), 0.05)):
+        cases.append(np.where(rng.uniform(size=shape) < frac, np.inf, 0.0))
+    one = np.zeros((20, 20, 40)); one[3, 17, 38] = np.inf
+    hole = np.full((20, 20, 40), np.inf); hole[10, 2, 0] = 0.0
+    cases += [one, hole, np.zeros((5, 6, 7)), np.full((5, 6, 7), np.inf)]
+    for obs in cases:
+        pitch = 0.013
+        lens = [pitch * k for k in obs.shape]
+        engine.force_general_sdf(False)
+        fast = engine.sdf_build(obs, lens)
+        engine.force_general_sdf(True)
+        gen = engine.sdf_build(obs, lens)
+        engine.force_general_sdf(False)
+        ref = oracle.sdf_from_obsarray(obs, lens, flavour=flavour)
+        fin = np.isfinite(ref)
+        for got in (fast, gen):
+            assert np.array_equal(np.isfinite(got), fin), obs.shape
+            assert np.array_equal(got[~fin], ref[~fin]), obs.shape
+            assert np.max(np.abs(got[fin] - ref[fin]), initial=0.0) <= SDF_ATOL, obs.shape
+    # a grid that is not 0 / HUGE_VAL falls back to the general path on its own
+    o = cases[2].copy()
+    o[1, 1, 1] = 0.25
+    lens = [0.02 * k for k in o.shape]
+    got = engine.sdf_build(o, lens)
+    ref = oracle.sdf_from_obsarray(o, lens, flavour=flavour)
+    assert np.max(np.abs(got - ref)) <= SDF_ATOL
+
+
 def test_dt_sqeuc_device(engine, oracle, flavour):
     """cd_grid_double_dt_sqeuc alone, on HBM pointers, arbitrary finite heights."""
     rng = np.random.default_rng(4)
@@ -141,10 +176,13 @@ def test_full_size_sdf_properties(engine):
     assert 0.005 < float(occ.double().mean()) < 0.5
     assert bool((sdf[occ] < 0).all()) and bool((sdf[~occ] > 0).all())          # sign convention
     pitch = 0.01
-    for ax in range(3):                                                        # 1-Lipschitz along each axis
-        a = sdf.narrow(ax, 0, 399)
+    for ax in range(3):                          # 1-Lipschitz inside each region; the centre-to-centre
+        a = sdf.narrow(ax, 0, 399)               # convention gives +1 / -1 voxel across the obstacle boundary
         bb = sdf.narrow(ax, 1, 399)
-        assert float((a - bb).abs().max()) <= pitch * (1 + 1e-9)
+        same = (a > 0) == (bb > 0)
+        diff = (a - bb).abs()
+        assert float(diff[same].max()) <= pitch * (1 + 1e-9)
+        assert float(diff[~same].max()) <= 2 * pitch * (1 + 1e-9)
     # free cells next to an obstacle are exactly one voxel away, and vice versa
     near = occ[1:, :, :] ^ occ[:-1, :, :]
     assert float((sdf[1:, :, :][near].abs() - pitch).abs().max()) < 1e-12
