@@ -1,0 +1,85 @@
+/* orcdchomp_b200_module.h -- the module-command boundary of or_cdchomp, as a C ABI.
+ *
+ * The reference registers nine string commands on an OpenRAVE module called
+ * "orcdchomp" (src/orcdchomp_mod.h:55-71; entry point src/orcdchomp.cpp:50-74;
+ * stream -> argv adapter src/orcwrap.cpp:37-82, tokeniser
+ * src/libcd/util_shparse.c:37-128).  This header exposes the same commands, with
+ * the same grammar, return strings and error texts, on top of the B200 engine
+ * (include/orcdchomp_b200.h):
+ *
+ *   viewspheres            mod.cpp:175-289   (viewer only: lists the spheres as text)
+ *   computedistancefield   mod.cpp:297-589
+ *   addfield_fromobsarray  mod.cpp:592-722
+ *   viewfields             mod.cpp:724-797   (viewer only: lists the fields as text)
+ *   removefield            mod.cpp:799-847
+ *   create                 mod.cpp:1800-2688
+ *   iterate                mod.cpp:2690-2852
+ *   gettraj                mod.cpp:2854-3011
+ *   destroy                mod.cpp:3013-3037
+ *
+ * plus one extension, `createbatch`, which makes R runs behind one handle (the
+ * handle then works with iterate / gettraj / destroy exactly like a single run).
+ *
+ * OpenRAVE itself is not part of this build.  What the commands need from the
+ * environment -- named kinbodies with a pose and collision geometry, named robots
+ * with a kinematic tree, sphere table and current active-DOF values -- is held
+ * by a small stand-in (`ocb_env`).  In a live OpenRAVE plugin the same data is
+ * read from EnvironmentBase / KinBody / RobotBase.
+ *
+ * Differences from the reference that a caller can observe:
+ *   - occupancy uses analytic box / sphere primitives instead of
+ *     EnvironmentBase::CheckCollision(cube) (third party, mod.cpp:520);
+ *   - gettraj returns the waypoints in OpenRAVE's trajectory XML layout with a
+ *     uniform deltatime; the LinearTrajectoryRetimer and the collision sweep
+ *     (mod.cpp:2906-3006) are OpenRAVE's and are not reproduced -- the
+ *     no_collision_* flags are accepted and have no effect;
+ *   - floating_base, basegoal, starttraj, con_tsr, start_tsr, everyn_tsr,
+ *     start_cost and trajs_fileformstr are recognised and rejected with an error
+ *     (out of scope for the hot path); ee_force,
+ *     ee_force_at and ee_torque_weights are accepted and ignored, as in the
+ *     reference (mod.cpp:1323).
+ */
+#ifndef ORCDCHOMP_B200_MODULE_H
+#define ORCDCHOMP_B200_MODULE_H
+
+#include <stddef.h>
+#include "orcdchomp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ocb_env ocb_env;       /* stand-in for OpenRAVE::EnvironmentBase */
+typedef struct ocb_module ocb_module; /* stand-in for the orcdchomp ModuleBase  */
+
+int ocb_env_create(ocb_env **out);
+int ocb_env_destroy(ocb_env *env);
+/* a kinbody: name, world pose [x y z qx qy qz qw], geometry in the kinbody frame */
+int ocb_env_add_kinbody(ocb_env *env, const char *name, const double pose[7],
+                        const ocb_prim *prims, int n_prims);
+int ocb_env_set_kinbody_pose(ocb_env *env, const char *name, const double pose[7]);
+/* KinBody::Enable(): disabled bodies are ignored by the occupancy test */
+int ocb_env_enable_kinbody(ocb_env *env, const char *name, int enabled);
+/* a robot: name, description (deep-copied), current active-DOF values [n_dof].
+ * A robot is also a kinbody (no geometry) so fields can be attached to it. */
+int ocb_env_add_robot(ocb_env *env, const char *name, const ocb_robot *robot,
+                      const double *active_dof_values);
+int ocb_env_set_active_dof_values(ocb_env *env, const char *name, const double *values);
+
+/* RaveCreateModule(env, "orcdchomp") on GPU `device` */
+int ocb_module_create(ocb_env *env, int device, ocb_module **out);
+int ocb_module_destroy(ocb_module *m);
+/* ModuleBase::SendCommand: returns 0 and the command's output text on success;
+ * non-zero when the command threw (text of the exception in ocb_module_last_error()),
+ * like the RuntimeError openravepy raises.  out may be NULL; *out_len receives
+ * the full length even when it exceeds out_cap. */
+int ocb_module_send_command(ocb_module *m, const char *cmd, char *out, size_t out_cap, size_t *out_len);
+/* text of the exception thrown by the last failed command on this thread */
+const char *ocb_module_last_error(void);
+/* numeric access to a run handle returned by create / createbatch ("%p" text) */
+int ocb_module_run_batch(ocb_module *m, const char *handle, ocb_batch **batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

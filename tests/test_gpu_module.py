@@ -1,0 +1,138 @@
+"""The reference's module commands end to end on the GPU (scripts/test_wam7.py flow):
+computedistancefield -> runchomp = create / iterate / gettraj / destroy, plus error behaviour."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from or_cdchomp_b200 import capi, models, orcdchomp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def world(engine):
+    env = orcdchomp.Environment()
+    kin_pose, prims, apos, aext = models.table_scene()
+    table = env.AddKinBody("table", kin_pose, prims)
+    robot_desc = models.wam7_robot()
+    robot = env.AddRobot("BarrettWAM", robot_desc, models.WAM7_DEMO_START)
+    mod = orcdchomp.Module(env, 0)
+    yield env, mod, table, robot, robot_desc
+    mod.close()
+    env.close()
+
+
+def oracle_field_for_table(oracle, flavour, cube_extent=0.02, padding=0.2):
+    """what computedistancefield(kinbody=table) must produce, via the oracle"""
+    kin_pose, prims, apos, aext = models.table_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, cube_extent, padding)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    pa = capi.make_prims(gp)
+    obs, sdf = oracle.computedistancefield(pa, len(gp), sizes, lengths, cube_extent, flavour=flavour)
+    return capi.SdfDesc(sdf, lengths, models.pose_compose(kin_pose, gpose))
+
+
+def test_runchomp_matches_oracle(world, oracle, flavour):
+    env, mod, table, robot, robot_desc = world
+    mod.computedistancefield(kinbody=table, cube_extent=0.02)
+    cost = [None]
+    traj = mod.runchomp(robot=robot, n_iter=100, lambda_=100.0, obs_factor=500.0, n_points=100,
+                        adofgoal=list(models.WAM7_DEMO_GOAL), no_collision_exception=True, cost=cost)
+    sd = oracle_field_for_table(oracle, flavour)
+    params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
+    run = oracle.Run(robot_desc, params, [sd], models.WAM7_DEMO_START, models.WAM7_DEMO_GOAL, flavour=flavour)
+    ret, c, _, _ = run.iterate(100)
+    assert ret == 0 and traj.shape == (100, 7)
+    assert np.max(np.abs(traj - run.traj())) <= 1e-6
+    assert abs(cost[0] - c[0]) <= 1e-5 * abs(c[0])  # iterate prints 6 significant digits (mod.cpp:2849)
+    run.close()
+    # default n_points is 101 (mod.cpp:1840)
+    h = mod.create(robot=robot, adofgoal=list(models.WAM7_DEMO_GOAL))
+    assert mod.gettraj(run=h).shape == (101, 7)
+    mod.destroy(run=h)
+
+
+def test_field_attached_to_disabled_robot(world, oracle, flavour):
+    """scripts/test_wam7.py:76-80: the robot is disabled and the field for everything else is
+    attached to the robot body."""
+    env, mod, table, robot, robot_desc = world
+    env.Enable(robot, False)
+    mod.computedistancefield(kinbody=robot, cube_extent=0.04)
+    env.Enable(robot, True)
+    assert "BarrettWAM" in mod.viewfields()
+    traj = mod.runchomp(robot=robot, n_iter=5, lambda_=100.0, adofgoal=list(models.WAM7_DEMO_GOAL))
+    assert np.isfinite(traj).all()
+    mod.removefield(kinbody=robot)
+    with pytest.raises(RuntimeError, match="No signed distance fields"):
+        mod.create(robot=robot, adofgoal=list(models.WAM7_DEMO_GOAL))
+
+
+def test_addfield_fromobsarray_cache_and_errors(world, oracle, flavour, tmp_path):
+    env, mod, table, robot, robot_desc = world
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    rng = np.random.default_rng(0)
+    obs = np.where(rng.uniform(size=(12, 10, 8)) < 0.1, np.inf, 0.0)
+    p = libc.malloc(obs.nbytes)                       # the module takes ownership and frees it (mod.cpp:703-704)
+    C.memmove(p, obs.ctypes.data, obs.nbytes)
+    box = env.AddKinBody("box", models.pose_make((0.5, 0.0, 0.3)), [])
+    mod.addfield_fromobsarray(kinbody=box, obsarray="0x%x" % p, sizes=obs.shape, lengths=[0.6, 0.5, 0.4],
+                              pose=[-0.3, -0.25, -0.2, 0, 0, 0, 2.0])   # quaternion gets normalised
+    with pytest.raises(RuntimeError, match="already have an sdf"):
+        mod.addfield_fromobsarray(kinbody=box, obsarray="0x%x" % p, sizes=obs.shape, lengths=[0.6, 0.5, 0.4])
+    # the same run through the oracle
+    sdf = oracle.sdf_from_obsarray(obs, [0.6, 0.5, 0.4], flavour=flavour)
+    pose_world = models.pose_compose(models.pose_make((0.5, 0.0, 0.3)), models.pose_make((-0.3, -0.25, -0.2)))
+    sd = capi.SdfDesc(sdf, [0.6, 0.5, 0.4], pose_world)
+    params = capi.default_params(n_points=40, lambda_=50.0)
+    goal = [0.3, 0.8, 0.1, 1.2, 0.0, 0.3, 0.2]
+    traj = mod.runchomp(robot=robot, n_iter=30, lambda_=50.0, n_points=40, adofgoal=goal)
+    run = oracle.Run(robot_desc, params, [sd], models.WAM7_DEMO_START, goal, flavour=flavour)
+    run.iterate(30)
+    assert np.max(np.abs(traj - run.traj())) <= 1e-6
+    run.close()
+    # cache file: raw doubles, written then read back (mod.cpp:416-444, 571-580)
+    cache = str(tmp_path / "sdf_table.dat")
+    mod.computedistancefield(kinbody=table, cube_extent=0.04, cache_filename=cache)
+    assert os.path.getsize(cache) % 8 == 0
+    mod.removefield(kinbody=table)
+    mod.computedistancefield(kinbody=table, cube_extent=0.04, cache_filename=cache, require_cache=True)
+    mod.removefield(kinbody=table)
+    with pytest.raises(RuntimeError, match="require_cache"):
+        mod.computedistancefield(kinbody=table, cube_extent=0.03, cache_filename=cache, require_cache=True)
+    # error texts of the reference
+    with pytest.raises(RuntimeError, match="Bad arguments!"):
+        mod.SendCommand("create robot BarrettWAM adofgoal '0 0 0 0 0 0 0' no_report_cost")
+    with pytest.raises(RuntimeError, match="lambda must be >=0.01!"):
+        mod.create(robot=robot, adofgoal=goal, lambda_=0.001)
+    with pytest.raises(RuntimeError, match="n_points must be >=3!"):
+        mod.create(robot=robot, adofgoal=goal, n_points=2)
+    with pytest.raises(RuntimeError, match="size of adofgoal does not match"):
+        mod.create(robot=robot, adofgoal=[0, 1])
+    with pytest.raises(RuntimeError, match="not supported by the B200 engine"):
+        mod.create(robot=robot, adofgoal=goal, floating_base=True)
+    with pytest.raises(RuntimeError, match="you must pass a created run!"):
+        mod.iterate(run="0x1234", n_iter=1)
+    with pytest.raises(RuntimeError, match="Could not find kinbody"):
+        mod.computedistancefield(kinbody="nothing")
+
+
+def test_createbatch_and_dat_file(world, tmp_path):
+    env, mod, table, robot, robot_desc = world
+    mod.computedistancefield(kinbody=table, cube_extent=0.02)
+    starts, goals = models.random_endpoints(robot_desc, 16, shrink=0.3)
+    h = mod.createbatch(robot=robot, adofgoals=goals, adofstarts=starts, lambda_=100.0, n_points=100,
+                        obs_factor=500.0)
+    costs = [float(x) for x in mod.iterate(run=h, n_iter=20).split()]
+    trajs = mod.gettraj(run=h)
+    assert len(costs) == 16 and trajs.shape == (16, 100, 7)
+    assert np.array_equal(trajs[:, 0], starts)
+    mod.destroy(run=h)
+    dat = str(tmp_path / "run.dat")
+    h = mod.create(robot=robot, adofgoal=list(goals[0]), lambda_=100.0, dat_filename=dat)
+    mod.iterate(run=h, n_iter=7)
+    mod.destroy(run=h)
+    rows = [l.split() for l in open(dat)]
+    assert len(rows) == 7 and [int(r[0]) for r in rows] == list(range(7)) and all(len(r) == 5 for r in rows)
