@@ -154,6 +154,44 @@ def cpu_baseline(flavour, robot, params, sd, n_runs, n_iter, threads=1):
     return sum(done) / dt, dt
 
 
+def measure_sdf_build(eng, stream, device, n=400):
+    """cd_grid_double_bin_sdf equivalent on a synthetic cluttered 400^3 grid: occupancy grid in HBM ->
+    SDF in HBM (16 algorithmic bytes per voxel)."""
+    import torch
+    from or_cdchomp_b200 import models
+    prims, apos, aext = models.clutter_scene()
+    ce = 0.005 * 400 / n
+    sizes, lengths, gpose = models.field_geometry(apos, aext, ce, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    ncell = int(np.prod(sizes))
+    d_obs = torch.empty(ncell, dtype=torch.float64, device=device)
+    d_sdf = torch.empty(ncell, dtype=torch.float64, device=device)
+    eng.occupancy_device(gp, sizes, lengths, ce, d_obs.data_ptr())
+    eng.flood_relabel_device(d_obs.data_ptr(), sizes, 0)
+    times = []
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.sdf_build_device(d_obs.data_ptr(), sizes, lengths, d_sdf.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = min(times[1:])
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = 16.0 * ncell / (ms * 1e-3) / 1e9
+    del d_obs, d_sdf
+    return {"metric": "sdf_build_mvoxels_per_s", "value": ncell / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
+            "sizes": [int(x) for x in sizes], "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes_per_voxel": 16}}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -198,6 +236,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--runs", type=int, default=RUNS_PER_GPU, help="runs per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sdf", action="store_true", help="skip the secondary SDF-build measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -312,6 +351,11 @@ def main():
     h2d = 2 * R * n * 8
     d2h = R * P * n * 8 + R * 3 * 8 + R * 4
 
+    # ---- secondary metric: SDF build Mvoxels/s, BASELINE configs[2] (400^3, device resident) ----
+    sdf_build = None
+    if rank == 0 and not args.no_sdf:
+        sdf_build = measure_sdf_build(eng, stream, device)
+
     run_iters_per_step = total_runs * N_ITER
     value = run_iters_per_step * args.steps / (step_ms * 1e-3)
 
@@ -326,8 +370,14 @@ def main():
         abytes = algorithmic_bytes_per_run_iter(P, n, robot.n_spheres_active, 1, False)
         launch_s = (kern_ms * 1e-3) / args.steps
         achieved = abytes * R * N_ITER / launch_s / 1e9
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("chomp_iterate_kernel_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "chomp_iterate_kernel",
+                    "traffic": traffic, "kernel": "chomp_iterate_kernel",
                     "algorithmic_bytes_per_run_iteration": abytes,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "note": "fp64-issue/latency bound, not HBM bound: see DESIGN.md for the second ceiling"}
@@ -348,7 +398,7 @@ def main():
                     "what": "create+iterate+gettraj+destroy through the C ABI, host buffers, wall clock"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "runs_failed_joint_limits": n_failed, "wall_s_timed_region": t_wall,
-            "kernel_ms_per_step": kern_ms / args.steps,
+            "kernel_ms_per_step": kern_ms / args.steps, "sdf_build": sdf_build,
         }
         print(json.dumps(line))
     batch.close()

@@ -42,24 +42,24 @@ __device__ __forceinline__ double warp_sum(double v)
    return v;
 }
 
-/* deterministic block-wide sum; red has 33 doubles; every thread gets the result */
-__device__ __forceinline__ double block_sum(double v, double *red)
+/* deterministic block-wide sums of two values with ONE barrier: per-warp partials go to one
+ * of two alternating 16-double buffers in red[0..31]; every thread then adds the partials in
+ * warp order.  Two consecutive calls use different buffers and any later reuse of a buffer
+ * is separated from its readers by the barrier of the call in between. */
+__device__ __forceinline__ void block_sum2(double &v1, double &v2, double *red, int &parity)
 {
    const int tid = threadIdx.x;
    const int nwarps = (blockDim.x + 31) >> 5;
-   v = warp_sum(v);
-   if ((tid & 31) == 0) red[tid >> 5] = v;
+   double *buf = red + 16 * parity;
+   parity ^= 1;
+   v1 = warp_sum(v1);
+   v2 = warp_sum(v2);
+   if ((tid & 31) == 0) { buf[2 * (tid >> 5)] = v1; buf[2 * (tid >> 5) + 1] = v2; }
    __syncthreads();
-   if (tid < 32)
-   {
-      double x = (tid < nwarps) ? red[tid] : 0.0;
-      x = warp_sum(x);
-      if (tid == 0) red[32] = x;
-   }
-   __syncthreads();
-   double out = red[32];
-   __syncthreads();
-   return out;
+   double s1 = 0.0, s2 = 0.0;
+   for (int w = 0; w < nwarps; w++) { s1 += buf[2 * w]; s2 += buf[2 * w + 1]; }
+   v1 = s1;
+   v2 = s2;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -709,6 +709,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
    __syncthreads();
 
    double cost_obs = 0.0, cost_smooth = 0.0;
+   int red_parity = 0;
    for (int iter = 0; iter <= a.n_iter; iter++)
    {
       const bool final_pass = (iter == a.n_iter);
@@ -766,18 +767,22 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
             }
          }
       }
-      cost_obs = block_sum(csum, red) * inv_m;
       if (final_pass)
       {
-         cost_smooth = block_sum(ssum, red) + trC;
+         block_sum2(csum, ssum, red, red_parity);
+         cost_obs = csum * inv_m;
+         cost_smooth = ssum + trC;
          break;
       }
+      __syncthreads(); /* every row of G is complete */
 
       /* ---- AG = A^-1 G (banded solve, one thread per dof) ---- */
       if (tid < n) band_solve(a, Gs + tid * Pp + 1);
       __syncthreads();
 
-      /* ---- momentum / plain update, T -= AG/lambda (chomp.c:525-548, 604-605) ---- */
+      /* ---- momentum / plain update, T -= AG/lambda (chomp.c:525-548, 604-605); each thread
+       * also checks the rows it has just written against the joint limits ---- */
+      int violated = 0;
       {
          const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
          for (int t = tid + 1; t <= m; t += NT)
@@ -789,15 +794,17 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
                   step = fma(coef, step, AGs[j * Pp + t]);
                   AGs[j * Pp + t] = step;
                }
-               Ts[j * Pp + t] = fma(-inv_lambda, step, Ts[j * Pp + t]);
+               const double q = fma(-inv_lambda, step, Ts[j * Pp + t]);
+               Ts[j * Pp + t] = q;
+               violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
             }
          if (a.use_momentum) leapfrog_first = 0;
       }
-      __syncthreads();
+      const int any_violation = __syncthreads_or(violated);
 
       /* ---- joint-limit projection (chomp.c:608-655) ---- */
       int round = 0;
-      for (; round < 1000; round++)
+      for (; any_violation && round < 1000; round++)
       {
          ArgMax best;
          best.v = 0.0;
@@ -872,7 +879,9 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
             ssum += (0.5 * band_AT(a, Tj, t) + b) * Tj[t];
          }
       }
-      cost_smooth = block_sum(ssum, red) + trC;
+      block_sum2(csum, ssum, red, red_parity);
+      cost_obs = csum * inv_m;
+      cost_smooth = ssum + trC;
       if (a.trace_on && tid == 0)
       {
          double *tr = a.trace + ((size_t) run * a.n_iter + iter) * 3;

@@ -283,3 +283,44 @@ def test_full_size_batch_properties(engine, wam7, table):
     assert bi == int(np.argmin(cand)) and bc == cand[bi]
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_dense_sphere_robot_global_workspace(engine, oracle, flavour, table):
+    """config-5 shape at small scale: 200 spheres do not fit the shared-memory workspace, so the
+    kernel variant with the per-block HBM workspace runs; 4 SDFs with distinct rotated poses."""
+    robot = models.dense_sphere_arm(200, seed=5)
+    rng = np.random.default_rng(9)
+    sds = []
+    for k in range(4):
+        x = (np.arange(24) + 0.5) / 24
+        f = (0.15 + 0.5 * np.abs(x[:, None, None] - rng.uniform(0.3, 0.7)) + 0.4 * np.abs(x[None, :, None] - 0.5)
+             + 0.3 * np.abs(x[None, None, :] - rng.uniform(0.3, 0.7)))
+        pose = models.pose_make(rng.uniform(-1.2, -0.6, size=3),
+                                models.quat_from_axis_angle(rng.normal(size=3), rng.uniform(0, 1.0)))
+        sds.append(capi.SdfDesc(f, [2.0, 2.0, 2.0], pose))
+    params = capi.default_params(n_points=64, lambda_=200.0, obs_factor=100.0, epsilon=0.2)
+    starts, goals = models.random_endpoints(robot, 3, seed0=77, shrink=0.4)
+    ids = [engine.upload_sdf(s) for s in sds]
+    b = engine.create_batch(robot, params, ids, starts, goals)
+    b.capture_gradient(1)
+    b.iterate(1)
+    g = b.get_gradient()
+    for r in range(3):
+        run = oracle.Run(robot, params, sds, starts[r], goals[r], flavour=flavour)
+        _, _, _, gr = run.iterate(1, want_grads=True)
+        assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * np.max(np.abs(gr[0]))
+        run.close()
+    b.close()
+    b = engine.create_batch(robot, params, ids, starts, goals)
+    costs, status = b.iterate(8)
+    traj = b.get_traj()
+    for r in range(3):
+        run = oracle.Run(robot, params, sds, starts[r], goals[r], flavour=flavour)
+        ret, c, _, _ = run.iterate(8)
+        assert ret == 0 and status[r] == 0
+        assert np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL
+        assert np.allclose(costs[r], c, rtol=1e-8, atol=0)
+        run.close()
+    b.close()
+    for i in ids:
+        engine.remove_sdf(i)
