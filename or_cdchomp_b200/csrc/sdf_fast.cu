@@ -16,18 +16,23 @@
  *   - pass 1 (along z, the contiguous axis) never touches HBM per cell: the grid
  *     is packed to a bit mask once (8 B read per cell) and the distance along z to
  *     the nearest set / clear bit is recomputed from the mask words inside pass 2;
- *   - pass 2 (y) and pass 3 (x) keep the envelope stack of a 32-column tile in
- *     shared memory ([entry][lane], conflict free) and read / write HBM with one
- *     coalesced 128 B (int32) or 256 B (double) row per step.
- * HBM traffic per cell: 8 (input) + 4 + 4 (intermediate write / read) + 8 (output)
- * + ~0.4 (mask) = 24.4 B against 16 B algorithmic.
+ *   - pass 2 (y) and pass 3 (x) run the envelope scan with one thread per line and
+ *     32 adjacent z columns per warp, so HBM is read / written one coalesced 128 B (int32)
+ *     or 256 B (double) row at a time; the envelope stack is a column of 4-byte entries in
+ *     HBM scratch with its two top entries in registers.  (Two shared-memory-stack
+ *     variants were measured first -- a stack tile per warp, and a stack-free divide and
+ *     conquer on the monotone arg-min; both lose to this one because the scan is latency
+ *     bound and only massive thread-level parallelism hides that: 8.8 / 5.1 / 2.7 ms at 400^3.)
+ * HBM traffic per cell: 8 (input) + 4 + 4 + 4 (intermediate write / read / sign re-read)
+ * + 8 (output) + envelope stack (<= 8 per pass) + ~0.4 (mask), against 16 B algorithmic.
  *
- * Limits: every axis <= 1024 cells (stack entry = 10-bit apex | 22-bit height).
+ * Limits: every axis <= 1024 cells (16-bit z distances, int32 squared distances).
  * Anything else (anisotropic cells, finite non-zero heights, longer axes) takes
  * the general fp64 path in sdf_kernels.cu.
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "ocb_internal.h"
 
 namespace
@@ -126,10 +131,13 @@ __device__ __forceinline__ int dz2_nearest(uint32_t bits, int lane, int zbase, i
 /* One lower-envelope pass over `len` samples of a 32-column tile (one column per lane).
  * load8(q0, vals) fills the parabola heights of q0..q0+7 (INF_I = none, also past the end):
  * batching keeps eight independent loads / bit scans in flight ahead of the serial stack
- * logic.  emit(q, value) receives the transformed value.  stack: [len][32] words,
- * entry = apex << 22 | height; the two top entries live in registers. */
+ * logic.  emit(q, value) receives the transformed value.  The stack lives in HBM scratch,
+ * one column per line ([entry][line], so a warp whose lanes sit at similar depths touches
+ * one or two sectors per access); entry = apex << 22 | height; the two top entries stay
+ * in registers, so memory sees each parabola at most once on the way in and once out.
+ * One thread per line: tens of thousands of lines in flight hide the serial latency. */
 template <class Load8, class Emit>
-__device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ stack, int lane, Load8 load8, Emit emit)
+__device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ stack, size_t stride, Load8 load8, Emit emit)
 {
    int np = 0;
    int v1 = 0, g1 = 0; /* top entry    */
@@ -161,7 +169,7 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
                v1 = v0; g1 = g0;
                if (np >= 2)
                {
-                  const uint32_t e = stack[(np - 2) * 32 + lane];
+                  const uint32_t e = stack[(size_t) (np - 2) * stride];
                   v0 = (int) (e >> 22); g0 = (int) (e & 0x3fffffu);
                }
             }
@@ -169,7 +177,7 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
                break;
          }
          /* push: the old second entry goes to memory */
-         if (np >= 2) stack[(np - 2) * 32 + lane] = ((uint32_t) v0 << 22) | (uint32_t) g0;
+         if (np >= 2) stack[(size_t) (np - 2) * stride] = ((uint32_t) v0 << 22) | (uint32_t) g0;
          v0 = v1; g0 = g1;
          v1 = q; g1 = gq;
          np++;
@@ -181,16 +189,16 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
       return;
    }
    /* spill the two register entries so the read-back is uniform */
-   if (np >= 2) stack[(np - 2) * 32 + lane] = ((uint32_t) v0 << 22) | (uint32_t) g0;
-   stack[(np - 1) * 32 + lane] = ((uint32_t) v1 << 22) | (uint32_t) g1;
+   if (np >= 2) stack[(size_t) (np - 2) * stride] = ((uint32_t) v0 << 22) | (uint32_t) g0;
+   stack[(size_t) (np - 1) * stride] = ((uint32_t) v1 << 22) | (uint32_t) g1;
    int k = 0;
-   uint32_t e = stack[lane];
+   uint32_t e = stack[0];
    int va = (int) (e >> 22), ga = (int) (e & 0x3fffffu);
    int vb = 0, gb = 0;
    bool has_next = np > 1;
    if (has_next)
    {
-      e = stack[32 + lane];
+      e = stack[stride];
       vb = (int) (e >> 22); gb = (int) (e & 0x3fffffu);
    }
    for (int q = 0; q < len; q++)
@@ -207,7 +215,7 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
             has_next = (k + 1 < np);
             if (has_next)
             {
-               e = stack[(k + 1) * 32 + lane];
+               e = stack[(size_t) (k + 1) * stride];
                vb = (int) (e >> 22); gb = (int) (e & 0x3fffffu);
             }
          }
@@ -218,31 +226,26 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
    }
 }
 
-/* ---- passes 1+2: z distances from the bit mask, envelope along y.
- * tile = (x, word wz): 32 columns.  blockIdx.y selects the field (0 obstacle, 1 free).
- * output: signed int32 per cell, > 0 free cell (squared distance to obstacles in its
- * x-slab), < 0 obstacle cell (minus squared distance to free cells), +-INF_I none. */
-__global__ void __launch_bounds__(32)
+
+/* ---- passes 1+2: z distances recomputed from the bit mask, lower envelope along y.
+ * One warp per (x, z-word) tile, one thread per line; blockIdx.y selects the field
+ * (0 obstacle, 1 free).  Output: signed int32 per cell, > 0 free cell (squared distance to
+ * the obstacles of its x-slab), < 0 obstacle cell (minus squared distance to free cells),
+ * +-INF_I none. ---- */
+__global__ void __launch_bounds__(256)
 edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums, int *__restrict__ inter,
-              int nx, int ny, int nz, int nwz)
+                   uint32_t *__restrict__ stacks, int nx, int ny, int nz, int nwz)
 {
-   extern __shared__ uint32_t smem_u[];
-   uint32_t *stack = smem_u;                                    /* [ny][32]          */
-   uint32_t *mw = smem_u + (size_t) ny * 32;                    /* [ny] mask words    */
-   RowSum *ms = reinterpret_cast<RowSum *>(mw + ny + (ny & 1)); /* [ny] row summaries */
-   const int lane = threadIdx.x;
-   const int tile = blockIdx.x;
-   const int x = tile / nwz, wz = tile % nwz;
+   const int lane = threadIdx.x & 31;
+   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (tile >= nx * nwz) return;
    const int field = blockIdx.y;
+   const int x = tile / nwz, wz = tile % nwz;
    const int z = wz * 32 + lane;
    const uint32_t valid = (nz - wz * 32 >= 32) ? 0xffffffffu : ((1u << (nz - wz * 32)) - 1u);
    const size_t tbase = ((size_t) x * nwz + wz) * ny;
-   for (int y = lane; y < ny; y += 32)
-   {
-      mw[y] = __ldg(mask + tbase + y);
-      ms[y] = sums[tbase + y];
-   }
-   __syncwarp();
+   const size_t nlines = (size_t) nx * nwz * 32;
+   uint32_t *stack = stacks + (size_t) field * ny * nlines + (size_t) tile * 32 + lane;
    auto load8 = [&](int y0, int vals[8])
    {
 #pragma unroll
@@ -252,8 +255,8 @@ edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums
          int v = INF_I;
          if (y < ny)
          {
-            const uint32_t w = mw[y];
-            const RowSum s = ms[y];
+            const uint32_t w = __ldg(mask + tbase + y);
+            const RowSum s = sums[tbase + y];
             v = (field == 0) ? dz2_nearest(w, lane, wz * 32, s.obs_before, s.obs_after)
                              : dz2_nearest(~w & valid, lane, wz * 32, s.emp_before, s.emp_after);
          }
@@ -264,29 +267,29 @@ edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums
    auto emit = [&](int y, int val)
    {
       if (z >= nz) return;
-      const bool is_obs = (mw[y] >> lane) & 1u;
-      /* each field owns the cells of the other polarity (its own seeds are zeros) */
+      const bool is_obs = (__ldg(mask + tbase + y) >> lane) & 1u;
       if (field == 0 && !is_obs) inter[((rowbase + y) * (size_t) nz) + z] = val;
       if (field == 1 && is_obs) inter[((rowbase + y) * (size_t) nz) + z] = -val;
    };
-   envelope_pass(ny, stack, lane, load8, emit);
+   envelope_pass(ny, stack, nlines, load8, emit);
 }
 
-/* ---- pass 3: envelope along x, final sqrt and sign.  tile = (y, word wz). ---- */
-__global__ void __launch_bounds__(32)
-edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, int nx, int ny, int nz, int nwz, double pitch2)
+/* ---- pass 3: lower envelope along x, final sqrt and sign; one warp per (y, z-word) tile ---- */
+__global__ void __launch_bounds__(256)
+edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, uint32_t *__restrict__ stacks,
+                  int nx, int ny, int nz, int nwz, double pitch2)
 {
-   extern __shared__ uint32_t smem_u[];
-   uint32_t *stack = smem_u;                 /* [nx][32]                         */
-   uint32_t *pol = smem_u + (size_t) nx * 32; /* [nx] bit lane = obstacle cell     */
-   const int lane = threadIdx.x;
-   const int tile = blockIdx.x;
-   const int y = tile / nwz, wz = tile % nwz;
+   const int lane = threadIdx.x & 31;
+   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (tile >= ny * nwz) return;
    const int field = blockIdx.y;
+   const int y = tile / nwz, wz = tile % nwz;
    const int z = wz * 32 + lane;
    const bool in = z < nz;
    const size_t slab = (size_t) ny * nz;
    const size_t col = (size_t) y * nz + (in ? z : 0);
+   const size_t nlines = (size_t) ny * nwz * 32;
+   uint32_t *stack = stacks + (size_t) field * nx * nlines + (size_t) tile * 32 + lane;
    auto load8 = [&](int x0, int vals[8])
    {
       int raw[8];
@@ -296,8 +299,6 @@ edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, int nx, in
       for (int k = 0; k < 8; k++)
       {
          const int v = raw[k];
-         const uint32_t pw = __ballot_sync(FULL, v < 0);
-         if (lane == 0 && x0 + k < nx) pol[x0 + k] = pw;
          int g = INF_I;
          if (in && x0 + k < nx)
             g = (field == 0) ? (v > 0 ? v : 0)   /* obstacle cells are the zeros of the obstacle field */
@@ -308,12 +309,12 @@ edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, int nx, in
    auto emit = [&](int x, int val)
    {
       if (!in) return;
-      const bool is_obs = (pol[x] >> lane) & 1u;
+      const int v = __ldg(inter + (size_t) x * slab + col);
       const double d = (val >= INF_I) ? (double) HUGE_VAL : sqrt((double) val * pitch2);
-      if (field == 0 && !is_obs) sdf[x * slab + col] = d;  /* free cell: + distance to obstacles */
-      if (field == 1 && is_obs) sdf[x * slab + col] = -d;  /* obstacle cell: - distance to free  */
+      if (field == 0 && v > 0) sdf[x * slab + col] = d;   /* free cell: + distance to obstacles */
+      if (field == 1 && v < 0) sdf[x * slab + col] = -d;  /* obstacle cell: - distance to free  */
    };
-   envelope_pass(nx, stack, lane, load8, emit);
+   envelope_pass(nx, stack, nlines, load8, emit);
 }
 
 } /* namespace */
@@ -335,7 +336,11 @@ extern "C" size_t ocb_sdf_fast_scratch_bytes(const int sizes[3])
    const size_t nwz = (sizes[2] + 31) / 32;
    const size_t rows = (size_t) sizes[0] * sizes[1];
    const size_t n = rows * sizes[2];
-   return 256 + rows * nwz * (sizeof(uint32_t) + sizeof(RowSum)) + n * sizeof(int) + 1024;
+   const size_t mx = sizes[0] > sizes[1] ? sizes[0] : sizes[1];
+   const size_t lines = (sizes[0] > sizes[1] ? (size_t) sizes[0] : (size_t) sizes[1]) * nwz * 32;
+   (void) lines;
+   const size_t stacks = 2 * mx * ((size_t) (sizes[0] > sizes[1] ? sizes[0] : sizes[1]) * nwz * 32) * sizeof(uint32_t);
+   return 256 + rows * nwz * (sizeof(uint32_t) + sizeof(RowSum)) + n * sizeof(int) + 1024 + stacks + 256;
 }
 
 /* returns cudaSuccess and *used_fast = 1 when the fast path produced d_sdf; *used_fast = 0
@@ -367,19 +372,10 @@ extern "C" cudaError_t ocb_launch_bin_sdf_fast(const double *d_obs, double *d_sd
    if (e != cudaSuccess) return e;
    if (h) return cudaSuccess; /* not a 0 / HUGE_VAL grid */
 
-   static int configured = 0;
-   const int mx = (ny > nx ? ny : nx);
-   const int need = mx * 32 * (int) sizeof(uint32_t) + (mx + 2) * 12;
-   if (need > configured)
-   {
-      e = cudaFuncSetAttribute(edt_zy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(edt_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-      if (e != cudaSuccess) return e;
-      configured = need;
-   }
    const double pitch = lengths[0] / sizes[0];
-   edt_zy_kernel<<<dim3(nx * nwz, 2), 32, ny * 32 * sizeof(uint32_t) + (ny + 2) * 12, st>>>(mask, sums, inter, nx, ny, nz, nwz);
-   edt_x_kernel<<<dim3(ny * nwz, 2), 32, nx * 32 * sizeof(uint32_t) + (nx + 2) * 4, st>>>(inter, d_sdf, nx, ny, nz, nwz, pitch * pitch);
+   uint32_t *stacks = (uint32_t *) (((uintptr_t) (inter + (size_t) rows * nz) + 255) & ~(uintptr_t) 255);
+   edt_zy_kernel<<<dim3((nx * nwz + 7) / 8, 2), 256, 0, st>>>(mask, sums, inter, stacks, nx, ny, nz, nwz);
+   edt_x_kernel<<<dim3((ny * nwz + 7) / 8, 2), 256, 0, st>>>(inter, d_sdf, stacks, nx, ny, nz, nwz, pitch * pitch);
    if (launches) (*launches) += 2;
    e = cudaGetLastError();
    if (e == cudaSuccess) *used_fast = 1;
