@@ -123,8 +123,34 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class _StdoutToStderr:
+    """libcd printf()s diagnostics ("ran too many joint limit fixes!", chomp.c:653) on the C
+    stdout; keep them off this script's stdout, which must carry exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def cpu_baseline(flavour, robot, params, sd, n_runs, n_iter, threads=1):
     """run-iterations/s of the CPU oracle on `threads` host threads (one run each at a time)."""
+    with _StdoutToStderr():
+        return _cpu_baseline(flavour, robot, params, sd, n_runs, n_iter, threads)
+
+
+def _cpu_baseline(flavour, robot, params, sd, n_runs, n_iter, threads=1):
     from oracle import pyoracle as po
     from or_cdchomp_b200 import models
     starts, goals = models.random_endpoints(robot, n_runs)

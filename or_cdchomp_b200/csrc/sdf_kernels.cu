@@ -133,9 +133,10 @@ struct PrimDev
    double e[3];   /* half extents (box) / e[0] = radius (sphere) */
    double R[9];   /* box axes = columns */
    double A[9];   /* |R| + 1e-12 */
+   double reach2; /* conservative (bounding sphere + cube half-diagonal)^2: beyond it nothing can touch */
 };
 
-__global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n)
+__global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n, double h)
 {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) return;
@@ -151,6 +152,14 @@ __global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n)
    d.R[3] = 2 * (qxqy + qzqw);     d.R[4] = -qx2 + qy2 - qz2 + qw2; d.R[5] = 2 * (qyqz - qxqw);
    d.R[6] = 2 * (qxqz - qyqw);     d.R[7] = 2 * (qyqz + qxqw);      d.R[8] = -qx2 - qy2 + qz2 + qw2;
    for (int k = 0; k < 9; k++) d.A[k] = fabs(d.R[k]) + 1e-12;
+   {
+      /* early-out radius: primitive bounding sphere + cube half diagonal, inflated so rounding can
+       * never reject a pair the exact predicate accepts (the exact test still decides every hit) */
+      const double rp = (p.type == OCB_PRIM_SPHERE) ? p.extents[0]
+                        : sqrt(p.extents[0] * p.extents[0] + p.extents[1] * p.extents[1] + p.extents[2] * p.extents[2]);
+      const double reach = (rp + h * 1.7320508075688774) * (1.0 + 1e-9) + 1e-9;
+      d.reach2 = reach * reach;
+   }
    out[i] = d;
 }
 
@@ -158,6 +167,10 @@ __global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n)
  * operation order is the contract shared with oracle/orcdchomp_port.c */
 __device__ __forceinline__ bool cube_hits(const double c[3], double h, const PrimDev &p)
 {
+   {
+      const double ux = p.c[0] - c[0], uy = p.c[1] - c[1], uz = p.c[2] - c[2];
+      if (ux * ux + uy * uy + uz * uz > p.reach2) return false;
+   }
    if (p.type == OCB_PRIM_SPHERE)
    {
       double d2 = 0.0;
@@ -398,7 +411,7 @@ extern "C" cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, co
    if (e != cudaSuccess) return e;
    (void) raw;
    if (n_prims > 0)
-      prep_prims_kernel<<<(n_prims + 127) / 128, 128, 0, st>>>((const ocb_prim *) d_prims, prep, n_prims);
+      prep_prims_kernel<<<(n_prims + 127) / 128, 128, 0, st>>>((const ocb_prim *) d_prims, prep, n_prims, cube_extent);
    const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
    occupancy_kernel<<<grid_blocks(n, 256), 256, 64 * sizeof(PrimDev), st>>>(
       prep, n_prims, sizes[0], sizes[1], sizes[2], lengths[0], lengths[1], lengths[2], cube_extent, d_grid);
