@@ -97,7 +97,7 @@ typedef struct ocb_params
    int derivative;              /* D of cd_chomp_create, default 1                    */
    double lambda;               /* default 10, must be >= 0.01                        */
    int use_momentum;
-   int use_hmc;
+   int use_hmc;                 /* 1 = on; 2 = on, momentum drawn by the serial generator (test hook, same stream) */
    double hmc_resample_lambda;  /* default 0.02                                       */
    double epsilon;              /* default 0.1                                        */
    double epsilon_self;         /* default 0.04                                       */

@@ -86,7 +86,7 @@ __host__ __device__ inline SmemLayout smem_layout(const OcbChompArgs &a, int ws_
    l.sdf = b; b += a.nsdf * (int) sizeof(OcbSdfDev);
    l.sph = b; b += ws_in_smem ? a.nsa * (int) sizeof(OcbSphereDev) : 0;
    l.desc = b; b += ws_in_smem ? a.n_desc * 4 : 0;
-   l.mt = b; b += a.use_hmc ? 626 * 4 : 0;
+   l.mt = b; b += a.use_hmc ? (626 + 626 + 16) * 4 : 0; /* state, saved copy (serial fallback), scratch */
    l.ired = b; b += 40 * 4;
    l.bytes = b;
    return l;
@@ -613,6 +613,154 @@ __device__ double mt_gaussian(uint32_t *mt, double sigma)
    return sigma * y * sqrt(-2.0 * log(r2) / r2);
 }
 
+/* ---- block-parallel HMC momentum resample --------------------------------------------
+ * Produces exactly the stream of the serial code above (gsl_ran_gaussian draws for AG in
+ * row-major (i, j) order, then one gsl_rng_uniform), but cooperatively:
+ *   - the MT19937 state is "twisted" 624 words at a time in three dependency phases;
+ *   - the tempered words of a chunk are consumed as (x, y) pairs by all threads at once,
+ *     accepted pairs are ranked by a block-wide prefix count so variate k lands in AG[k];
+ *   - consumption stops at the pair that yields the last variate; the next raw word is
+ *     the uniform for the resample gap.
+ * gsl_rng_uniform_pos re-draws a zero word (probability 2^-32 each), which would shift the
+ * pairing: if any zero word shows up the caller redoes the resample with the serial code
+ * from a saved copy of the state, so the result is exact in every case.
+ * scratch: >= 16 ints of shared memory.  Returns false when a zero word was met. */
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+   y ^= (y >> 11);
+   y ^= (y << 7) & 0x9d2c5680u;
+   y ^= (y << 15) & 0xefc60000u;
+   y ^= (y >> 18);
+   return y;
+}
+
+__device__ __forceinline__ uint32_t mt_twist_word(uint32_t a, uint32_t b, uint32_t far)
+{
+   const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+   return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ void mt_twist_parallel(uint32_t *mt)
+{
+   const int tid = threadIdx.x, NT = blockDim.x;
+   /* phase bounds: [0,227) reads old only; [227,454) and [454,623) read words made by the
+    * previous phase; word 623 reads new[0] and new[396] */
+   const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
+   for (int ph = 0; ph < 4; ph++)
+   {
+      uint32_t val[8];
+      int cnt = 0;
+      for (int k = lo[ph] + tid; k < hi[ph]; k += NT)
+         val[cnt++] = mt_twist_word(mt[k], mt[(k + 1) % 624], mt[(k + 397) % 624]);
+      __syncthreads();
+      cnt = 0;
+      for (int k = lo[ph] + tid; k < hi[ph]; k += NT) mt[k] = val[cnt++];
+      __syncthreads();
+   }
+}
+
+__device__ bool hmc_resample_parallel(uint32_t *mt, int *scratch, double *AGs, int Pp, int m, int n, double sigma,
+                                      double *uniform_out)
+{
+   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+   const int need = m * n;
+   int produced = 0;      /* variates written so far (uniform over the block) */
+   int idx = (int) mt[624];
+   bool have_x = false;   /* a pair's x was the last word of the previous chunk */
+   double carry_x = 0.0;
+   int *wtot = scratch;   /* [8] accepted pairs per warp */
+   int *zero_seen = scratch + 8;
+   int *stop_at = scratch + 9; /* word position right after the pair that produced the last variate */
+   if (tid == 0) { *zero_seen = 0; *stop_at = -1; }
+   __syncthreads();
+   for (;;)
+   {
+      if (idx >= 624)
+      {
+         mt_twist_parallel(mt);
+         idx = 0;
+      }
+      /* words idx..623 are available; with a carried x the first word is that pair's y */
+      const int first = idx + (have_x ? 1 : 0);
+      const int npairs = (624 - first) >> 1;
+      const bool tail_x = ((624 - first) & 1) != 0; /* an x left without its y */
+      bool done = false;
+      /* the carried pair, handled by thread 0 as pair -1 of this chunk */
+      for (int base = have_x ? -1 : 0; base < npairs && !done; base += NT)
+      {
+         const int j = base + tid;
+         bool ok = false;
+         double z = 0.0;
+         int end_pos = 0;
+         if (j < npairs)
+         {
+            double x, y;
+            uint32_t wx, wy;
+            if (j < 0) { wx = 1; wy = mt_temper(mt[idx]); x = carry_x; y = -1.0 + 2.0 * (wy / 4294967296.0); end_pos = idx + 1; }
+            else
+            {
+               wx = mt_temper(mt[first + 2 * j]);
+               wy = mt_temper(mt[first + 2 * j + 1]);
+               x = -1.0 + 2.0 * (wx / 4294967296.0);
+               y = -1.0 + 2.0 * (wy / 4294967296.0);
+               end_pos = first + 2 * j + 2;
+            }
+            if (wx == 0 || wy == 0) atomicOr(zero_seen, 1);
+            const double r2 = x * x + y * y;
+            ok = !(r2 > 1.0 || r2 == 0.0);
+            if (ok) z = sigma * y * sqrt(-2.0 * log(r2) / r2);
+         }
+         const unsigned bal = __ballot_sync(FULL_MASK, ok);
+         if (lane == 0) wtot[warp] = __popc(bal);
+         __syncthreads();
+         int before = 0, total = 0;
+         for (int w = 0; w < nwarps; w++)
+         {
+            const int c = wtot[w];
+            if (w < warp) before += c;
+            total += c;
+         }
+         const int rank = produced + before + __popc(bal & ((1u << lane) - 1u));
+         if (ok && rank < need)
+         {
+            AGs[(rank % n) * Pp + (rank / n) + 1] = z; /* AG[i][j], i = rank / n */
+            if (rank == need - 1) *stop_at = end_pos;
+         }
+         produced += total;
+         __syncthreads();
+         if (produced >= need) done = true;
+      }
+      if (*zero_seen) return false;
+      if (done)
+      {
+         idx = *stop_at; /* uniform over the block after the barrier above */
+         break;
+      }
+      /* chunk exhausted without finishing */
+      if (tail_x)
+      {
+         const uint32_t wx = mt_temper(mt[623]);
+         if (wx == 0) return false;
+         carry_x = -1.0 + 2.0 * (wx / 4294967296.0);
+         have_x = true;
+      }
+      else
+         have_x = false;
+      idx = 624;
+   }
+   /* one more raw word (zero allowed) for the resample gap */
+   if (idx >= 624)
+   {
+      mt_twist_parallel(mt);
+      idx = 0;
+   }
+   *uniform_out = mt_temper(mt[idx]) / 4294967296.0;
+   __syncthreads();
+   if (tid == 0) mt[624] = (uint32_t) (idx + 1);
+   __syncthreads();
+   return true;
+}
+
 /* ------------------------------------------------------------------------- */
 struct ArgMax
 {
@@ -635,7 +783,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
    const int tid = threadIdx.x;
    const int NT = blockDim.x;
    const int run = blockIdx.x;
-   const int P = a.P, m = a.m, n = a.n, Pp = a.Ppad, bw = a.bw;
+   const int P = a.P, m = a.m, n = a.n, Pp = a.Ppad;
 
    /* ---- shared memory carve-up ---- */
    const SmemLayout lay = smem_layout(a, WS_SMEM ? 1 : 0);
@@ -717,17 +865,30 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       /* ---- HMC momentum resample (mod.cpp:2755-2768) ---- */
       if (a.use_hmc && !final_pass && iter == hmc_next)
       {
-         if (tid == 0)
-         {
-            const double alpha = 100.0 * exp(0.02 * iter);
-            const double sigma = 1.0 / sqrt(alpha);
-            for (int i = 0; i < m; i++)
-               for (int j = 0; j < n; j++) AGs[j * Pp + i + 1] = mt_gaussian(mts, sigma);
-            const double u = mt_uniform(mts);
-            ired[32] = hmc_next + 1 + (int) (-log(u) / a.hmc_lambda);
-         }
+         const double alpha = 100.0 * exp(0.02 * iter);
+         const double sigma = 1.0 / sqrt(alpha);
+         uint32_t *saved = mts + 626;
+         int *scratch = reinterpret_cast<int *>(mts + 1252);
+         for (int e = tid; e < 625; e += NT) saved[e] = mts[e];
          __syncthreads();
-         hmc_next = ired[32];
+         double u = 0.0;
+         if (a.use_hmc == 2 || !hmc_resample_parallel(mts, scratch, AGs, Pp, m, n, sigma, &u))
+         {
+            /* a zero word was drawn (or use_hmc == 2, the test hook that forces this path): redo this
+             * resample serially, with the exact gsl_rng_uniform_pos semantics */
+            __syncthreads();
+            for (int e = tid; e < 625; e += NT) mts[e] = saved[e];
+            __syncthreads();
+            if (tid == 0)
+            {
+               for (int i = 0; i < m; i++)
+                  for (int j = 0; j < n; j++) AGs[j * Pp + i + 1] = mt_gaussian(mts, sigma);
+               red[35] = mt_uniform(mts);
+            }
+            __syncthreads();
+            u = red[35];
+         }
+         hmc_next = hmc_next + 1 + (int) (-log(u) / a.hmc_lambda);
          leapfrog_first = 1;
          __syncthreads();
       }

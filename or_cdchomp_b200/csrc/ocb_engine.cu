@@ -883,7 +883,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    if (n_runs < 1) return fail(OCB_ERR_ARG, "need at least one run");
    /* use_hmc without use_momentum: the reference resamples AG and then overwrites it with
     * Ainv G (beta = 0, chomp.c:529-530), so nothing observable changes -> same as no hmc */
-   const int use_hmc = (params->use_hmc && params->use_momentum) ? 1 : 0;
+   const int use_hmc = (params->use_hmc && params->use_momentum) ? (params->use_hmc == 2 ? 2 : 1) : 0;
    for (int i = 0; i < n_sdfs; i++)
       if (sdf_ids[i] < 0 || sdf_ids[i] >= (int) e->sdfs.size() || !e->sdfs[sdf_ids[i]].used)
          return fail(OCB_ERR_ARG, "bad sdf id %d", sdf_ids[i]);

@@ -172,6 +172,14 @@ def test_momentum_hmc_seeds(engine, oracle, flavour, wam7, table):
         run.close()
     # different seeds really give different trajectories
     assert np.max(np.abs(traj[0] - traj[1])) > 1e-4
+    # the block-parallel momentum generator and its serial fallback produce the same stream
+    p2 = capi.default_params(n_points=48, lambda_=40.0, obs_factor=300.0, use_momentum=1, use_hmc=2,
+                             hmc_resample_lambda=0.08)
+    b2 = engine.create_batch(wam7, p2, [sid], st, go, seeds=seeds)
+    b2.iterate(35)
+    c2, s2 = b2.iterate(25)
+    assert np.array_equal(b2.get_traj(), traj) and np.array_equal(c2, costs)
+    b2.close()
     bi, bc = b.best()
     assert bi == int(np.argmin(costs[:, 0])) and bc == costs[bi, 0]
     b.close()
@@ -324,3 +332,41 @@ def test_dense_sphere_robot_global_workspace(engine, oracle, flavour, table):
     b.close()
     for i in ids:
         engine.remove_sdf(i)
+
+
+def test_set_traj_and_derivative3(engine, oracle, flavour, wam7, table):
+    """starttraj variant (mod.cpp:2373-2415: every row, end points included, comes from the caller)
+    and a wider metric (derivative 3 -> hepta-diagonal A)."""
+    params = capi.default_params(n_points=60, lambda_=150.0, obs_factor=300.0)
+    starts, goals = models.random_endpoints(wam7, 3, seed0=4321, shrink=0.3)
+    rng = np.random.default_rng(12)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    init = b.get_traj()
+    bump = 0.05 * np.sin(np.linspace(0, np.pi, 60))[None, :, None] * rng.normal(size=(3, 1, 7))
+    seeded = init + bump  # end rows unchanged because sin(0) = sin(pi) ~ 0 up to rounding
+    seeded[:, 0], seeded[:, -1] = init[:, 0], init[:, -1]
+    b.set_traj(seeded)
+    costs, status = b.iterate(25)
+    for r in range(3):
+        run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
+        run.set_traj(seeded[r])
+        ret, c, _, _ = run.iterate(25)
+        assert ret == 0 and status[r] == 0
+        assert np.max(np.abs(b.get_traj()[r] - run.traj())) <= TRAJ_ATOL
+        assert np.allclose(costs[r], c, rtol=1e-8, atol=0)
+        run.close()
+    b.close()
+    params = capi.default_params(n_points=40, lambda_=500.0, derivative=3)
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(15)
+    for r in range(3):
+        run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
+        ret, c, _, _ = run.iterate(15)
+        assert (ret == 0) == (status[r] == 0)
+        if ret == 0:
+            assert np.max(np.abs(b.get_traj()[r] - run.traj())) <= TRAJ_ATOL
+            assert np.allclose(costs[r], c, rtol=1e-7, atol=0)
+        run.close()
+    b.close()
+    engine.remove_sdf(sid)
