@@ -147,10 +147,14 @@ int ocb_dt_sqeuc_device(ocb_engine *e, const double *d_func, const int sizes[3],
  * an obstacle iff the axis-aligned cube of half-extent cube_extent centred at
  * the voxel centre (grid frame) overlaps any primitive.  Primitives are given
  * in the GRID frame.  OCB_PRIM_BOX: pose[7] + half extents (oriented box, SAT
- * test); OCB_PRIM_SPHERE: centre + radius.  d_grid receives 1.0 (free) or
+ * test); OCB_PRIM_SPHERE: centre + radius; OCB_PRIM_TRIANGLE: three vertices (triangle
+ * meshes, the usual OpenRAVE geometry).  d_grid receives 1.0 (free) or
  * HUGE_VAL (obstacle) exactly as mod.cpp:398,522 leave it.                     */
-#define OCB_PRIM_BOX    0
-#define OCB_PRIM_SPHERE 1
+#define OCB_PRIM_BOX      0
+#define OCB_PRIM_SPHERE   1
+#define OCB_PRIM_TRIANGLE 2   /* one triangle of a mesh: v0 = pose[0..2], v1 = pose[3..5],
+                                 v2 = (pose[6], extents[0], extents[1]); cube-vs-triangle by the
+                                 13-axis separating-axis test (touching counts as a hit) */
 typedef struct ocb_prim
 {
    int type;

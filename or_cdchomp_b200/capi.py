@@ -25,7 +25,7 @@ OCB_ERR_NODEVICE = -4
 OCB_ERR_JLIMIT = -5
 
 JOINT_FIXED, JOINT_REVOLUTE, JOINT_PRISMATIC = 0, 1, 2
-PRIM_BOX, PRIM_SPHERE = 0, 1
+PRIM_BOX, PRIM_SPHERE, PRIM_TRIANGLE = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -188,7 +188,7 @@ class SdfDesc:
 
 
 def make_prims(prims):
-    """prims: list of ('box', pose7, half_extents3) / ('sphere', centre3, radius)."""
+    """prims: list of ('box', pose7, half_extents3) / ('sphere', centre3, radius) / ('tri', v0, v1, v2)."""
     arr = (OcbPrim * max(1, len(prims)))()
     for i, p in enumerate(prims):
         if p[0] == "box":
@@ -203,6 +203,12 @@ def make_prims(prims):
                 arr[i].pose[k] = float(p[1][k])
             arr[i].pose[6] = 1.0
             arr[i].extents[0] = float(p[2])
+        elif p[0] == "tri":
+            arr[i].type = PRIM_TRIANGLE
+            v = [float(x) for vert in p[1:4] for x in vert]
+            for k in range(7):
+                arr[i].pose[k] = v[k]
+            arr[i].extents[0], arr[i].extents[1] = v[7], v[8]
         else:
             raise ValueError(p[0])
     return arr

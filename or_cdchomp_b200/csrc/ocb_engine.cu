@@ -449,8 +449,34 @@ extern "C" int ocb_occupancy_device(ocb_engine *e, const ocb_prim *prims, int n_
    if (rc) return rc;
    if (n_prims > 0)
       CU(cudaMemcpyAsync(e->scratch, prims, n_prims * sizeof(ocb_prim), cudaMemcpyHostToDevice, e->stream));
-   CU(ocb_launch_occupancy(e->scratch, n_prims, sizes, lengths, cube_extent, d_grid, e->stream));
-   e->launches++;
+   /* blocks per primitive from the mean size of the voxel ranges (host estimate, bounds only) */
+   int slices = 1;
+   if (n_prims > 0)
+   {
+      double vox = 0.0;
+      for (int i = 0; i < n_prims; i++)
+      {
+         double v = 1.0;
+         for (int k = 0; k < 3; k++)
+         {
+            double w;
+            if (prims[i].type == OCB_PRIM_TRIANGLE)
+            {
+               const double a = prims[i].pose[k], b = prims[i].pose[3 + k];
+               const double c = (k == 0) ? prims[i].pose[6] : prims[i].extents[k - 1];
+               w = std::max(a, std::max(b, c)) - std::min(a, std::min(b, c));
+            }
+            else if (prims[i].type == OCB_PRIM_SPHERE) w = 2.0 * prims[i].extents[0];
+            else w = 2.0 * sqrt(prims[i].extents[0] * prims[i].extents[0] + prims[i].extents[1] * prims[i].extents[1] +
+                                prims[i].extents[2] * prims[i].extents[2]);
+            v *= w / (lengths[k] / sizes[k]) + 3.0;
+         }
+         vox += v;
+      }
+      slices = (int) std::min(64.0, std::max(1.0, vox / n_prims / 4096.0));
+   }
+   CU(ocb_launch_occupancy(e->scratch, n_prims, sizes, lengths, cube_extent, d_grid, slices, e->stream));
+   e->launches += 3;
    /* the primitives live in the shared scratch: finish before anyone reuses it */
    CU(cudaStreamSynchronize(e->stream));
    return OCB_OK;

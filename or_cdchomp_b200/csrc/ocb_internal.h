@@ -126,7 +126,7 @@ cudaError_t ocb_launch_bin_sdf_fast(const double *d_obs, double *d_sdf, const in
                                     cudaStream_t st, long *launches, int *used_fast);
 cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, const int sizes[3],
                                  const double lengths[3], double cube_extent, double *d_grid,
-                                 cudaStream_t st);
+                                 int slices, cudaStream_t st);
 cudaError_t ocb_launch_flood_relabel(double *d_grid, const int sizes[3], size_t index_start,
                                      void *scratch, size_t scratch_bytes, cudaStream_t st,
                                      long *launches);

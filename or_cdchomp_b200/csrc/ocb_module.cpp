@@ -128,6 +128,38 @@ void quat_rows(const double *q, double R[9])
    R[6] = 2 * (qx * qz - qy * qw); R[7] = 2 * (qy * qz + qx * qw); R[8] = -qx * qx - qy * qy + qz * qz + qw * qw;
 }
 
+/* apply a rigid frame to a primitive: boxes carry a pose, spheres a centre, triangles three vertices */
+void pose_apply(const double frame[7], const double p[3], double out[3])
+{
+   const double in[7] = {p[0], p[1], p[2], 0, 0, 0, 1};
+   double r[7];
+   pose_compose(frame, in, r);
+   out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
+}
+
+ocb_prim prim_transform(const double frame[7], const ocb_prim &p)
+{
+   ocb_prim q = p;
+   if (p.type == OCB_PRIM_TRIANGLE)
+   {
+      double v[9] = {p.pose[0], p.pose[1], p.pose[2], p.pose[3], p.pose[4], p.pose[5], p.pose[6], p.extents[0], p.extents[1]};
+      double w[9];
+      for (int i = 0; i < 3; i++) pose_apply(frame, v + 3 * i, w + 3 * i);
+      for (int k = 0; k < 7; k++) q.pose[k] = w[k];
+      q.extents[0] = w[7];
+      q.extents[1] = w[8];
+   }
+   else if (p.type == OCB_PRIM_SPHERE)
+   {
+      double c[3];
+      pose_apply(frame, p.pose, c);
+      q.pose[0] = c[0]; q.pose[1] = c[1]; q.pose[2] = c[2];
+   }
+   else
+      pose_compose(frame, p.pose, q.pose);
+   return q;
+}
+
 struct Kinbody
 {
    std::string name;
@@ -309,18 +341,29 @@ struct ocb_module
       double lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
       double kb_inv[7];
       pose_invert(kb.pose, kb_inv);
-      auto grow = [&](const ocb_prim &p, const double frame[7])
+      auto grow = [&](const ocb_prim &p0, const double frame[7])
       {
-         double pp[7], R[9];
-         pose_compose(frame, p.pose, pp);
-         quat_rows(pp + 3, R);
+         const ocb_prim p = prim_transform(frame, p0);
+         if (p.type == OCB_PRIM_TRIANGLE)
+         {
+            const double v[9] = {p.pose[0], p.pose[1], p.pose[2], p.pose[3], p.pose[4], p.pose[5], p.pose[6], p.extents[0], p.extents[1]};
+            for (int i = 0; i < 3; i++)
+               for (int k = 0; k < 3; k++)
+               {
+                  if (v[3 * i + k] < lo[k]) lo[k] = v[3 * i + k];
+                  if (v[3 * i + k] > hi[k]) hi[k] = v[3 * i + k];
+               }
+            return;
+         }
+         double R[9];
+         quat_rows(p.pose + 3, R);
          for (int k = 0; k < 3; k++)
          {
             double e = (p.type == OCB_PRIM_SPHERE)
                           ? p.extents[0]
                           : fabs(R[3 * k]) * p.extents[0] + fabs(R[3 * k + 1]) * p.extents[1] + fabs(R[3 * k + 2]) * p.extents[2];
-            if (pp[k] - e < lo[k]) lo[k] = pp[k] - e;
-            if (pp[k] + e > hi[k]) hi[k] = pp[k] + e;
+            if (p.pose[k] - e < lo[k]) lo[k] = p.pose[k] - e;
+            if (p.pose[k] + e > hi[k]) hi[k] = p.pose[k] + e;
          }
       };
       double ident[7];
@@ -380,12 +423,7 @@ struct ocb_module
             if (!kv.second.enabled) continue;
             double rel[7];
             pose_compose(gsdf_world, kv.second.pose, rel);
-            for (const ocb_prim &p : kv.second.prims)
-            {
-               ocb_prim q = p;
-               pose_compose(rel, p.pose, q.pose);
-               prims.push_back(q);
-            }
+            for (const ocb_prim &p : kv.second.prims) prims.push_back(prim_transform(rel, p));
          }
          if (ocb_computedistancefield_host(engine, prims.data(), (int) prims.size(), f.sizes, f.lengths, cube_extent,
                                            nullptr, f.data.data()) != OCB_OK)

@@ -133,10 +133,11 @@ struct PrimDev
    double e[3];   /* half extents (box) / e[0] = radius (sphere) */
    double R[9];   /* box axes = columns */
    double A[9];   /* |R| + 1e-12 */
-   double reach2; /* conservative (bounding sphere + cube half-diagonal)^2: beyond it nothing can touch */
+   double V[9];   /* triangle vertices (OCB_PRIM_TRIANGLE) */
+   double lo[3], hi[3]; /* axis-aligned bounds of the primitive in the grid frame (conservative) */
 };
 
-__global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n, double h)
+__global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n)
 {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) return;
@@ -152,25 +153,96 @@ __global__ void prep_prims_kernel(const ocb_prim *prims, PrimDev *out, int n, do
    d.R[3] = 2 * (qxqy + qzqw);     d.R[4] = -qx2 + qy2 - qz2 + qw2; d.R[5] = 2 * (qyqz - qxqw);
    d.R[6] = 2 * (qxqz - qyqw);     d.R[7] = 2 * (qyqz + qxqw);      d.R[8] = -qx2 - qy2 + qz2 + qw2;
    for (int k = 0; k < 9; k++) d.A[k] = fabs(d.R[k]) + 1e-12;
+   for (int k = 0; k < 7; k++) d.V[k] = p.pose[k];
+   d.V[7] = p.extents[0];
+   d.V[8] = p.extents[1];
+   /* bounds used only to choose which voxels to test (the exact predicate decides every hit) */
+   for (int k = 0; k < 3; k++)
    {
-      /* early-out radius: primitive bounding sphere + cube half diagonal, inflated so rounding can
-       * never reject a pair the exact predicate accepts (the exact test still decides every hit) */
-      const double rp = (p.type == OCB_PRIM_SPHERE) ? p.extents[0]
-                        : sqrt(p.extents[0] * p.extents[0] + p.extents[1] * p.extents[1] + p.extents[2] * p.extents[2]);
-      const double reach = (rp + h * 1.7320508075688774) * (1.0 + 1e-9) + 1e-9;
-      d.reach2 = reach * reach;
+      if (p.type == OCB_PRIM_TRIANGLE)
+      {
+         d.lo[k] = fmin(d.V[k], fmin(d.V[3 + k], d.V[6 + k]));
+         d.hi[k] = fmax(d.V[k], fmax(d.V[3 + k], d.V[6 + k]));
+      }
+      else
+      {
+         const double w = (p.type == OCB_PRIM_SPHERE) ? p.extents[0]
+                          : d.A[3 * k] * p.extents[0] + d.A[3 * k + 1] * p.extents[1] + d.A[3 * k + 2] * p.extents[2];
+         d.lo[k] = p.pose[k] - w;
+         d.hi[k] = p.pose[k] + w;
+      }
    }
    out[i] = d;
 }
 
 /* cube (centre c, half extent h, axes = grid axes) against one primitive; the
  * operation order is the contract shared with oracle/orcdchomp_port.c */
+/* cube against a triangle: 9 edge cross products, 3 cube face normals, the triangle plane
+ * (Akenine-Moller 2001); strict inequalities, touching is a hit */
+__device__ __forceinline__ bool cube_hits_triangle(const double c[3], double h, const double *V)
+{
+   double v[3][3], e[3][3], n[3], vmin[3], vmax[3];
+#pragma unroll
+   for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) v[i][k] = V[3 * i + k] - c[k];
+#pragma unroll
+   for (int k = 0; k < 3; k++)
+   {
+      e[0][k] = v[1][k] - v[0][k];
+      e[1][k] = v[2][k] - v[1][k];
+      e[2][k] = v[0][k] - v[2][k];
+   }
+#pragma unroll
+   for (int i = 0; i < 3; i++)
+   {
+      const double ex = e[i][0], ey = e[i][1], ez = e[i][2];
+      const double fx = fabs(ex), fy = fabs(ey), fz = fabs(ez);
+      double p0, p1, p2, lo, hi, rad;
+      p0 = ey * v[0][2] - ez * v[0][1]; p1 = ey * v[1][2] - ez * v[1][1]; p2 = ey * v[2][2] - ez * v[2][1];
+      lo = p0; hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      if (p2 < lo) lo = p2; if (p2 > hi) hi = p2;
+      rad = fz * h + fy * h;
+      if (lo > rad || hi < -rad) return false;
+      p0 = ez * v[0][0] - ex * v[0][2]; p1 = ez * v[1][0] - ex * v[1][2]; p2 = ez * v[2][0] - ex * v[2][2];
+      lo = p0; hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      if (p2 < lo) lo = p2; if (p2 > hi) hi = p2;
+      rad = fz * h + fx * h;
+      if (lo > rad || hi < -rad) return false;
+      p0 = ex * v[0][1] - ey * v[0][0]; p1 = ex * v[1][1] - ey * v[1][0]; p2 = ex * v[2][1] - ey * v[2][0];
+      lo = p0; hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      if (p2 < lo) lo = p2; if (p2 > hi) hi = p2;
+      rad = fy * h + fx * h;
+      if (lo > rad || hi < -rad) return false;
+   }
+#pragma unroll
+   for (int k = 0; k < 3; k++)
+   {
+      double lo = v[0][k], hi = v[0][k];
+      if (v[1][k] < lo) lo = v[1][k]; if (v[1][k] > hi) hi = v[1][k];
+      if (v[2][k] < lo) lo = v[2][k]; if (v[2][k] > hi) hi = v[2][k];
+      if (lo > h || hi < -h) return false;
+   }
+   n[0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+   n[1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+   n[2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+#pragma unroll
+   for (int k = 0; k < 3; k++)
+   {
+      if (n[k] > 0.0) { vmin[k] = -h - v[0][k]; vmax[k] = h - v[0][k]; }
+      else { vmin[k] = h - v[0][k]; vmax[k] = -h - v[0][k]; }
+   }
+   if (n[0] * vmin[0] + n[1] * vmin[1] + n[2] * vmin[2] > 0.0) return false;
+   if (n[0] * vmax[0] + n[1] * vmax[1] + n[2] * vmax[2] >= 0.0) return true;
+   return false;
+}
+
 __device__ __forceinline__ bool cube_hits(const double c[3], double h, const PrimDev &p)
 {
-   {
-      const double ux = p.c[0] - c[0], uy = p.c[1] - c[1], uz = p.c[2] - c[2];
-      if (ux * ux + uy * uy + uz * uz > p.reach2) return false;
-   }
+   if (p.type == OCB_PRIM_TRIANGLE) return cube_hits_triangle(c, h, p.V);
    if (p.type == OCB_PRIM_SPHERE)
    {
       double d2 = 0.0;
@@ -220,42 +292,58 @@ __device__ __forceinline__ bool cube_hits(const double c[3], double h, const Pri
    return true;
 }
 
+/* every voxel starts free (mod.cpp:398) */
+__global__ void fill_kernel(double *__restrict__ grid, size_t n, double value)
+{
+   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+      grid[i] = value;
+}
+
+/* The reference asks OpenRAVE, voxel by voxel, whether a cube collides with anything
+ * (mod.cpp:498-525).  Here each primitive rasterises itself: blockIdx.x = primitive,
+ * blockIdx.y = a slice of its bounding range of voxels; every voxel in range runs the exact
+ * predicate and a hit stores HUGE_VAL (idempotent, so overlapping primitives need no
+ * atomics and the result does not depend on scheduling). */
 __global__ void __launch_bounds__(256)
-occupancy_kernel(const PrimDev *__restrict__ prims, int n_prims, int sx, int sy, int sz,
+rasterize_kernel(const PrimDev *__restrict__ prims, int sx, int sy, int sz,
                  double lx, double ly, double lz, double h, double *__restrict__ grid)
 {
-   extern __shared__ __align__(16) unsigned char osm[];
-   PrimDev *sp = reinterpret_cast<PrimDev *>(osm);
-   const size_t total = (size_t) sx * sy * sz;
-   for (size_t base = blockIdx.x * (size_t) blockDim.x; base < total; base += (size_t) gridDim.x * blockDim.x)
+   __shared__ PrimDev P;
    {
-      const size_t idx = base + threadIdx.x;
-      double c[3] = {0, 0, 0};
-      if (idx < total)
-      {
-         const int z = (int) (idx % sz), y = (int) ((idx / sz) % sy), x = (int) (idx / ((size_t) sz * sy));
-         /* cd_grid_center_index: ((0.5 + sub) / size) * length   (grid.c:184-187) */
-         c[0] = (0.5 + x) / sx * lx;
-         c[1] = (0.5 + y) / sy * ly;
-         c[2] = (0.5 + z) / sz * lz;
-      }
-      bool hit = false;
-      for (int p0 = 0; p0 < n_prims; p0 += 64)
-      {
-         const int cnt = min(64, n_prims - p0);
-         __syncthreads();
-         {
-            const int words = cnt * (int) (sizeof(PrimDev) / 4);
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(prims + p0);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(sp);
-            for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-         }
-         __syncthreads();
-         if (idx < total && !hit)
-            for (int k = 0; k < cnt; k++)
-               if (cube_hits(c, h, sp[k])) { hit = true; break; }
-      }
-      if (idx < total) grid[idx] = hit ? HUGE_VAL : 1.0; /* mod.cpp:398, 522 */
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(prims + blockIdx.x);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+      for (int w = threadIdx.x; w < (int) (sizeof(PrimDev) / 4); w += blockDim.x) dst[w] = src[w];
+   }
+   __syncthreads();
+   const int size[3] = {sx, sy, sz};
+   const double len[3] = {lx, ly, lz};
+   int lo[3], cnt[3];
+#pragma unroll
+   for (int k = 0; k < 3; k++)
+   {
+      /* voxel centres within (bounds +- h), widened by one voxel against rounding */
+      const double pitch = len[k] / size[k];
+      int a = (int) floor((P.lo[k] - h) / pitch) - 1;
+      int b = (int) floor((P.hi[k] + h) / pitch) + 1;
+      if (a < 0) a = 0;
+      if (b > size[k] - 1) b = size[k] - 1;
+      lo[k] = a;
+      cnt[k] = b - a + 1;
+   }
+   if (cnt[0] <= 0 || cnt[1] <= 0 || cnt[2] <= 0) return;
+   const long long vol = (long long) cnt[0] * cnt[1] * cnt[2];
+   for (long long lin = blockIdx.y * (long long) blockDim.x + threadIdx.x; lin < vol;
+        lin += (long long) gridDim.y * blockDim.x)
+   {
+      const int z = lo[2] + (int) (lin % cnt[2]);
+      const int y = lo[1] + (int) ((lin / cnt[2]) % cnt[1]);
+      const int x = lo[0] + (int) (lin / ((long long) cnt[2] * cnt[1]));
+      double c[3];
+      /* cd_grid_center_index: ((0.5 + sub) / size) * length   (grid.c:184-187) */
+      c[0] = (0.5 + x) / sx * lx;
+      c[1] = (0.5 + y) / sy * ly;
+      c[2] = (0.5 + z) / sz * lz;
+      if (cube_hits(c, h, P)) grid[((size_t) x * sy + y) * sz + z] = HUGE_VAL; /* mod.cpp:522 */
    }
 }
 
@@ -402,7 +490,7 @@ extern "C" cudaError_t ocb_launch_bin_sdf(const double *d_obs, double *d_sdf, co
 
 extern "C" cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, const int sizes[3],
                                             const double lengths[3], double cube_extent, double *d_grid,
-                                            cudaStream_t st)
+                                            int slices, cudaStream_t st)
 {
    /* the raw ocb_prim array sits at the start of the scratch; the prepared form follows it */
    const size_t raw = ((size_t) (n_prims > 0 ? n_prims : 1) * sizeof(ocb_prim) + 255) & ~(size_t) 255;
@@ -410,11 +498,21 @@ extern "C" cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, co
    cudaError_t e = cudaMallocAsync((void **) &prep, (size_t) (n_prims > 0 ? n_prims : 1) * sizeof(PrimDev), st);
    if (e != cudaSuccess) return e;
    (void) raw;
-   if (n_prims > 0)
-      prep_prims_kernel<<<(n_prims + 127) / 128, 128, 0, st>>>((const ocb_prim *) d_prims, prep, n_prims, cube_extent);
    const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
-   occupancy_kernel<<<grid_blocks(n, 256), 256, 64 * sizeof(PrimDev), st>>>(
-      prep, n_prims, sizes[0], sizes[1], sizes[2], lengths[0], lengths[1], lengths[2], cube_extent, d_grid);
+   fill_kernel<<<grid_blocks(n, 256), 256, 0, st>>>(d_grid, n, 1.0);
+   if (n_prims > 0)
+   {
+      prep_prims_kernel<<<(n_prims + 127) / 128, 128, 0, st>>>((const ocb_prim *) d_prims, prep, n_prims);
+      /* `slices` blocks share one primitive's voxel range (large boxes vs. small mesh triangles) */
+      if (slices < 1) slices = 1;
+      if (slices > 64) slices = 64;
+      for (int p0 = 0; p0 < n_prims; p0 += 32768)
+      {
+         const int cntp = (n_prims - p0 < 32768) ? n_prims - p0 : 32768;
+         rasterize_kernel<<<dim3(cntp, slices), 256, 0, st>>>(prep + p0, sizes[0], sizes[1], sizes[2], lengths[0],
+                                                          lengths[1], lengths[2], cube_extent, d_grid);
+      }
+   }
    e = cudaGetLastError();
    cudaFreeAsync(prep, st);
    return e;

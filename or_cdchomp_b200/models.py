@@ -250,6 +250,9 @@ def prims_to_grid_frame(prims, pose_grid_in_kinbody):
     for p in prims:
         if p[0] == "box":
             out.append(("box", pose_compose(inv, np.asarray(p[1], dtype=np.float64)), p[2]))
+        elif p[0] == "tri":
+            out.append(("tri",) + tuple(tuple(quat_rotate(inv[3:], np.asarray(v, dtype=np.float64)) + inv[:3])
+                                        for v in p[1:4]))
         else:
             c = quat_rotate(inv[3:], np.asarray(p[1], dtype=np.float64)) + inv[:3]
             out.append(("sphere", tuple(c), p[2]))
@@ -269,3 +272,67 @@ def random_endpoints(robot, n_runs, seed0=20260217, shrink=0.05):
         starts[r] = mid + half * rng.uniform(-1, 1, size=robot.n_dof)
         goals[r] = mid + half * rng.uniform(-1, 1, size=robot.n_dof)
     return starts, goals
+
+
+def icosphere_mesh(centre, radius, subdivisions=2):
+    """Triangle mesh of a sphere (subdivided icosahedron): list of ('tri', v0, v1, v2)."""
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+    verts = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+             (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    verts = [np.array(v, dtype=np.float64) / np.linalg.norm(v) for v in verts]
+    faces = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2),
+             (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11),
+             (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(subdivisions):
+        cache, new_faces = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            new_faces += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = new_faces
+    c = np.asarray(centre, dtype=np.float64)
+    return [("tri", tuple(c + radius * verts[a]), tuple(c + radius * verts[b]), tuple(c + radius * verts[d]))
+            for a, b, d in faces]
+
+
+def box_mesh(pose, half):
+    """12 triangles of an oriented box given as (pose7, half extents)."""
+    pose = np.asarray(pose, dtype=np.float64)
+    corners = {}
+    for sx in (-1, 1):
+        for sy in (-1, 1):
+            for sz in (-1, 1):
+                local = np.array([sx * half[0], sy * half[1], sz * half[2]])
+                corners[(sx, sy, sz)] = tuple(quat_rotate(pose[3:], local) + pose[:3])
+    tris = []
+    for ax in range(3):
+        for sgn in (-1, 1):
+            o = [a for a in range(3) if a != ax]
+            def key(u, v):
+                k = [0, 0, 0]
+                k[ax], k[o[0]], k[o[1]] = sgn, u, v
+                return tuple(k)
+            a, b, c, d = corners[key(-1, -1)], corners[key(1, -1)], corners[key(1, 1)], corners[key(-1, 1)]
+            tris += [("tri", a, b, c), ("tri", a, c, d)]
+    return tris
+
+
+def mesh_scene(seed=11, half_span=0.8):
+    """A small triangle-mesh kinbody: two icospheres and three rotated box meshes."""
+    rng = np.random.default_rng(seed)
+    prims = []
+    for _ in range(2):
+        prims += icosphere_mesh(rng.uniform(-half_span + 0.3, half_span - 0.3, size=3), rng.uniform(0.1, 0.25), 2)
+    for _ in range(3):
+        q = quat_from_axis_angle(rng.normal(size=3), rng.uniform(0, math.pi))
+        prims += box_mesh(pose_make(rng.uniform(-half_span + 0.3, half_span - 0.3, size=3), q),
+                          rng.uniform(0.05, 0.2, size=3))
+    return prims, (0.0, 0.0, 0.0), (half_span, half_span, half_span)

@@ -655,8 +655,80 @@ static void quat_to_rows(const double pose[7], double R[9])
  * in include/orcdchomp_b200.h.  c = cube centre (grid frame), h = half extent.
  * Compiled with -ffp-contract=off so every product/sum rounds once, matching
  * the device code's explicit __dmul_rn/__dadd_rn sequence bit for bit. */
+/* cube (centre c, half extent h) against a triangle: separating-axis test over the 9 edge
+ * cross products, the 3 cube face normals and the triangle plane (Akenine-Moller 2001);
+ * strict inequalities, so touching is a hit.  Straight-line arithmetic, same order as the
+ * device code. */
+static int cube_hits_triangle(const double c[3], double h, const double V[9])
+{
+   double v[3][3], e[3][3], n[3], vmin[3], vmax[3];
+   int i, k;
+   for (i = 0; i < 3; i++)
+      for (k = 0; k < 3; k++) v[i][k] = V[3 * i + k] - c[k];
+   for (k = 0; k < 3; k++)
+   {
+      e[0][k] = v[1][k] - v[0][k];
+      e[1][k] = v[2][k] - v[1][k];
+      e[2][k] = v[0][k] - v[2][k];
+   }
+   for (i = 0; i < 3; i++)
+   {
+      const double ex = e[i][0], ey = e[i][1], ez = e[i][2];
+      const double fx = fabs(ex), fy = fabs(ey), fz = fabs(ez);
+      double p0, p1, p2, lo, hi, rad;
+      /* axis x cross e */
+      p0 = ey * v[0][2] - ez * v[0][1]; p1 = ey * v[1][2] - ez * v[1][1]; p2 = ey * v[2][2] - ez * v[2][1];
+      lo = p0; hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      if (p2 < lo) lo = p2; if (p2 > hi) hi = p2;
+      rad = fz * h + fy * h;
+      if (lo > rad || hi < -rad) return 0;
+      /* axis y cross e */
+      p0 = ez * v[0][0] - ex * v[0][2]; p1 = ez * v[1][0] - ex * v[1][2]; p2 = ez * v[2][0] - ex * v[2][2];
+      lo = p0; hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      if (p2 < lo) lo = p2; if (p2 > hi) hi = p2;
+      rad = fz * h + fx * h;
+      if (lo > rad || hi < -rad) return 0;
+      /* axis z cross e */
+      p0 = ex * v[0][1] - ey * v[0][0]; p1 = ex * v[1][1] - ey * v[1][0]; p2 = ex * v[2][1] - ey * v[2][0];
+      lo = p0; hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      if (p2 < lo) lo = p2; if (p2 > hi) hi = p2;
+      rad = fy * h + fx * h;
+      if (lo > rad || hi < -rad) return 0;
+   }
+   for (k = 0; k < 3; k++)
+   {
+      double lo = v[0][k], hi = v[0][k];
+      if (v[1][k] < lo) lo = v[1][k]; if (v[1][k] > hi) hi = v[1][k];
+      if (v[2][k] < lo) lo = v[2][k]; if (v[2][k] > hi) hi = v[2][k];
+      if (lo > h || hi < -h) return 0;
+   }
+   n[0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+   n[1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+   n[2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+   for (k = 0; k < 3; k++)
+   {
+      if (n[k] > 0.0) { vmin[k] = -h - v[0][k]; vmax[k] = h - v[0][k]; }
+      else { vmin[k] = h - v[0][k]; vmax[k] = -h - v[0][k]; }
+   }
+   if (n[0] * vmin[0] + n[1] * vmin[1] + n[2] * vmin[2] > 0.0) return 0;
+   if (n[0] * vmax[0] + n[1] * vmax[1] + n[2] * vmax[2] >= 0.0) return 1;
+   return 0;
+}
+
 static int cube_hits_prim(const double c[3], double h, const struct ocb_prim *p)
 {
+   if (p->type == OCB_PRIM_TRIANGLE)
+   {
+      double V[9];
+      int k;
+      for (k = 0; k < 7; k++) V[k] = p->pose[k];
+      V[7] = p->extents[0];
+      V[8] = p->extents[1];
+      return cube_hits_triangle(c, h, V);
+   }
    if (p->type == OCB_PRIM_SPHERE)
    {
       double d2 = 0.0, r = p->extents[0];

@@ -79,6 +79,17 @@ def occupancy():
                         sdf=sdf.astype(np.float64))
 
 
+def mesh():
+    prims, apos, aext = models.mesh_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.02, 0.1)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    pa = capi.make_prims(gp)
+    occ = po.occupancy(pa, len(gp), sizes, lengths, 0.02, flavour=FL)
+    obs, sdf = po.computedistancefield(pa, len(gp), sizes, lengths, 0.02, flavour=FL)
+    np.savez_compressed(os.path.join(OUT, "mesh.npz"), sizes=np.array(sizes), occ_hit=np.packbits(np.isinf(occ)),
+                        obs_hit=np.packbits(np.isinf(obs)), sdf=sdf)
+
+
 def chomp():
     robot = models.wam7_robot()
     kin_pose, prims, apos, aext = models.table_scene()
@@ -135,5 +146,5 @@ def mt():
 
 if __name__ == "__main__":
     assert po.available("reference"), "build oracle/_ref first (needs /root/reference)"
-    sdf_kat(); sdf_build(); occupancy(); chomp(); mt()
+    sdf_kat(); sdf_build(); occupancy(); mesh(); chomp(); mt()
     print("golden fixtures written to", OUT)

@@ -114,6 +114,32 @@ def test_occupancy_flood_sdf_pipeline(engine, oracle, flavour):
     assert np.max(np.abs(sdf_g - sdf_r)) <= SDF_ATOL
 
 
+def test_triangle_mesh_pipeline(engine, oracle, flavour):
+    """triangle-mesh kinbody (icospheres + box meshes): occupancy, flood fill and SDF against the
+    golden vectors and the oracle; the voxel set must be bit-exact."""
+    gold = np.load(golden_path("mesh.npz"))
+    prims, apos, aext = models.mesh_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.02, 0.1)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    n = int(np.prod(sizes))
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    engine.occupancy_device(gp, sizes, lengths, 0.02, d.data_ptr())
+    occ = d.cpu().numpy().reshape(sizes)
+    assert np.array_equal(np.packbits(np.isinf(occ)), gold["occ_hit"])
+    obs, sdf = engine.computedistancefield(gp, sizes, lengths, 0.02)
+    assert np.array_equal(np.packbits(np.isinf(obs)), gold["obs_hit"])
+    assert np.max(np.abs(sdf - gold["sdf"])) <= SDF_ATOL
+    # a finer, larger mesh directly against the oracle (many small triangles per voxel and vice versa)
+    tri = models.icosphere_mesh((0.05, -0.1, 0.0), 0.45, 4) + models.box_mesh(
+        models.pose_make((-0.2, 0.3, 0.1), models.quat_from_axis_angle((1, 2, 3), 0.7)), (0.5, 0.05, 0.3))
+    sizes, lengths, gpose = models.field_geometry((0, 0, 0), (0.7, 0.7, 0.7), 0.0125, 0.1)
+    gp = models.prims_to_grid_frame(tri, gpose)
+    obs_g, _ = engine.computedistancefield(gp, sizes, lengths, 0.0125, want_sdf=False)
+    obs_r, _ = oracle.computedistancefield(capi.make_prims(gp), len(gp), sizes, lengths, 0.0125, flavour=flavour,
+                                           want_sdf=False)
+    assert np.array_equal(obs_g, obs_r)
+
+
 def test_flood_encloses_pocket(engine):
     t, h = 0.03, 0.3
     slabs = []

@@ -101,6 +101,50 @@ def test_occupancy_and_flood_golden(oracle):
     assert np.isinf(obs).sum() >= np.isinf(occ).sum()  # enclosed pockets can only add obstacles
 
 
+def test_triangle_mesh_voxeliser(oracle):
+    """cube-vs-triangle predicate: golden, containment in the analytic solid,
+    and an independent sampling check of the separating-axis test."""
+    gold = np.load(golden_path("mesh.npz"))
+    prims, apos, aext = models.mesh_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.02, 0.1)
+    assert list(sizes) == list(gold["sizes"])
+    gp = models.prims_to_grid_frame(prims, gpose)
+    pa = capi.make_prims(gp)
+    occ = oracle.occupancy(pa, len(gp), sizes, lengths, 0.02)
+    obs, sdf = oracle.computedistancefield(pa, len(gp), sizes, lengths, 0.02)
+    assert np.array_equal(np.packbits(np.isinf(occ)), gold["occ_hit"])
+    assert np.array_equal(np.packbits(np.isinf(obs)), gold["obs_hit"])
+    assert np.array_equal(sdf, gold["sdf"])
+    assert np.isinf(obs).sum() > np.isinf(occ).sum()          # closed meshes: the flood fill fills the inside
+    # a meshed sphere's shell lies inside the solid sphere's voxel set and the filled mesh nearly equals it
+    c, r = (0.1, 0.0, -0.2), 0.3
+    tri = models.icosphere_mesh(c, r, 3)
+    sizes, lengths, gpose = models.field_geometry((0, 0, 0), (0.6, 0.6, 0.6), 0.02, 0.1)
+    shell = oracle.occupancy(capi.make_prims(models.prims_to_grid_frame(tri, gpose)), len(tri), sizes, lengths, 0.02)
+    solid = oracle.occupancy(capi.make_prims(models.prims_to_grid_frame([("sphere", c, r)], gpose)), 1, sizes, lengths, 0.02)
+    assert not (np.isinf(shell) & ~np.isinf(solid)).any()
+    filled, _ = oracle.computedistancefield(capi.make_prims(models.prims_to_grid_frame(tri, gpose)), len(tri),
+                                            sizes, lengths, 0.02, want_sdf=False)
+    assert abs(int(np.isinf(filled).sum()) - int(np.isinf(solid).sum())) < 0.02 * np.isinf(solid).sum()
+    # sampling check: a voxel is hit iff some point of the triangle lies in the (closed) cube
+    rng = np.random.default_rng(3)
+    sizes, lengths = [6, 6, 6], [0.6, 0.6, 0.6]
+    for _ in range(40):
+        v = rng.uniform(0.05, 0.55, size=(3, 3))
+        occ = oracle.occupancy(capi.make_prims([("tri", v[0], v[1], v[2])]), 1, sizes, lengths, 0.05)
+        u = rng.uniform(size=(20000, 2))
+        flip = u.sum(1) > 1
+        u[flip] = 1 - u[flip]
+        pts = v[0] + u[:, :1] * (v[1] - v[0]) + u[:, 1:] * (v[2] - v[0])
+        cells = np.unique(np.floor(pts / 0.1).astype(int), axis=0)
+        assert all(np.isinf(occ[tuple(cell)]) for cell in cells)      # sampled points prove a hit
+        # and every reported hit is within half a cube diagonal of the triangle's bounding box
+        hit = np.argwhere(np.isinf(occ))
+        centres = (hit + 0.5) * 0.1
+        lo, hi = v.min(0) - 0.05 - 1e-12, v.max(0) + 0.05 + 1e-12
+        assert ((centres >= lo) & (centres <= hi)).all()
+
+
 def test_flood_fill_encloses_pocket(oracle):
     """a hollow box: the inside is not reachable from voxel 0 and becomes obstacle (mod.cpp:543-548)."""
     # two nested boxes are not expressible as a hollow primitive; build the shell from 6 slabs
