@@ -331,8 +331,9 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
             acc[k] = (pc * -2.0 + pm + pp) * invdt2;
          }
          const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
-         const double vn = sqrt(vn2);
-         const double iv2 = 1.0 / vn2; /* unguarded, as mod.cpp:1239 */
+         const double rv = rsqrt(vn2);
+         const double vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
+         const double iv2 = rv * rv; /* 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
          const bool moving = vn > 0.000001;
          const double radius = tb.radius[s];
          double cost_s = 0.0;
