@@ -534,6 +534,7 @@ struct ocb_batch
    OcbChompArgs args;
    int threads = 128;
    size_t smem = 0;
+   size_t tile_smem = 0, run_smem = 0; /* tiled path (args.tiled) */
    int trace_cap = 0; /* iterations the trace buffer can hold */
    int last_n_iter = 0;
    std::vector<void *> owned; /* device allocations to free */
@@ -680,6 +681,7 @@ struct CompiledRobot
    std::vector<double> cut2, radius; /* [nsa][NS], [NS] */
    int n_groups = 0;
    std::vector<int> desc;
+   std::vector<int> ganc; /* [n_groups + 1] offsets, then joints above each group (see OcbChompArgs) */
    std::vector<double> inactive_pos;
    std::vector<double> inactive_radius;
    std::vector<int> inactive_link;
@@ -845,6 +847,16 @@ int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
       }
       C.joints[k].desc_end = (int) C.desc.size();
    }
+   /* the same relation by group: the joints whose subtree carries it */
+   C.ganc.assign(C.n_groups + 1, 0);
+   for (int g = 0; g < C.n_groups; g++)
+   {
+      C.ganc[g] = (int) C.ganc.size();
+      for (int k = 0; k < nj; k++)
+         for (int di = C.joints[k].desc_begin; di < C.joints[k].desc_end; di++)
+            if (C.desc[di] == g) C.ganc.push_back(k);
+   }
+   C.ganc[C.n_groups] = (int) C.ganc.size();
    return OCB_OK;
 }
 
@@ -984,6 +996,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    TRY(batch_upload(b, &a.cut2, C.cut2));
    TRY(batch_upload(b, &a.radius, C.radius));
    TRY(batch_upload(b, &a.desc, C.desc));
+   TRY(batch_upload(b, &a.ganc, C.ganc));
    TRY(batch_upload(b, &a.inactive_pos, C.inactive_pos));
    TRY(batch_upload(b, &a.sdfs, sd));
    TRY(batch_upload(b, &a.Aband, M.Aband));
@@ -1035,20 +1048,27 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    }
 
    /* workspace: per waypoint 3*nsa sphere coordinates + 12 per saved branch frame
-    * + 6 per sphere-carrying joint frame (wrench accumulators) */
+    * + 6 per sphere-carrying joint frame (wrench accumulators).  When a run does not fit in
+    * one SM's shared memory the iteration is tiled over waypoints (chomp_tiled.cu). */
    a.ws_stride = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
-   a.ws_in_smem = 1;
-   b->smem = ocb_chomp_smem_bytes(&a, 1);
+   b->smem = ocb_chomp_smem_bytes(&a);
    if (b->smem > (size_t) e->smem_optin)
    {
-      a.ws_in_smem = 0;
-      b->smem = ocb_chomp_smem_bytes(&a, 0);
-      if (b->smem > (size_t) e->smem_optin)
+      a.tiled = 1;
+      a.tile_w = 0;
+      for (int tw = 32; tw >= 8; tw /= 2)
+         if (ocb_tile_smem_bytes(&a, tw) <= (size_t) e->smem_optin) { a.tile_w = tw; break; }
+      b->run_smem = ocb_run_update_smem_bytes(&a);
+      if (!a.tile_w || b->run_smem > (size_t) e->smem_optin)
       {
          ocb_batch_destroy(b);
-         return fail(OCB_ERR_ARG, "trajectory too long for shared memory (%zu bytes)", b->smem);
+         return fail(OCB_ERR_ARG, "problem too large for shared memory (%d spheres, %d waypoints, %d dofs)",
+                     a.nsa, P, n);
       }
-      TRY(batch_alloc(b, &a.ws_global, R * a.ws_stride));
+      b->tile_smem = ocb_tile_smem_bytes(&a, a.tile_w);
+      a.n_tiles = (m + a.tile_w - 1) / a.tile_w;
+      TRY(batch_alloc(b, &a.G_obs, R * m * n));
+      TRY(batch_alloc(b, &a.tile_cost, R * a.n_tiles));
    }
    b->threads = std::min(256, ((P + 31) / 32) * 32);
    err = cudaStreamSynchronize(e->stream);
@@ -1150,6 +1170,14 @@ extern "C" int ocb_batch_iterate_async(ocb_batch *b, int n_iter)
    }
    a.n_iter = n_iter;
    b->last_n_iter = n_iter;
+   if (a.tiled)
+   {
+      /* the persistent kernel restarts status and costs on every call; same here */
+      CU(cudaMemsetAsync(a.costs, 0, (size_t) a.R * 3 * sizeof(double), b->e->stream));
+      CU(cudaMemsetAsync(a.status, 0, (size_t) a.R * sizeof(int), b->e->stream));
+      CU(ocb_launch_chomp_tiled(&a, b->tile_smem, b->run_smem, 256, b->e->stream, &b->e->launches));
+      return OCB_OK;
+   }
    CU(ocb_launch_chomp(&a, b->smem, b->threads, b->e->stream));
    b->e->launches++;
    return OCB_OK;

@@ -59,12 +59,15 @@ struct OcbChompArgs
    int nj, nsa, nsi, nsdf;
    int bw, n_slots, Ppad, n_iter;
    int use_momentum, use_hmc, trace_on, grad_mode; /* grad_mode 0 none, 1 full G, 2 obstacle only */
-   int ws_in_smem, ng;     /* ng: joint frames that carry spheres (wrench accumulators) */
+   int tiled, ng;          /* tiled: large-robot path (chomp_tiled.cu); ng: joint frames that carry spheres */
    int n_desc, NAp;        /* NAp: padded active part of a cut2 row (>= nsa + 3); row = NAp + nsi */
+   int tile_w, n_tiles;    /* tiled path: waypoints per tile (32, 16 or 8), tiles per run */
    /* robot */
    OcbJointDev joints[OCB_MAX_JOINTS];
    const OcbSphereDev *spheres;
    const int *desc;        /* [n_desc] group indices, see OcbJointDev::desc_begin */
+   const int *ganc;        /* inverse of desc: [ng + 1] offsets into this same array, then the joints
+                              whose subtree carries group g (tiled path) */
    const double *inactive_pos;
    /* self-collision tables over NS = nsa + nsi spheres (active first):
     * cut2[s][o] = (r_s + r_o + epsilon_self)^2, or -1 when s and o sit on the same link
@@ -94,8 +97,9 @@ struct OcbChompArgs
    int *status;           /* [R] */
    double *trace;         /* [R][n_iter][3] */
    double *grad_out;      /* [R][m][n] */
-   double *ws_global;     /* per-block workspace when it does not fit in shared memory */
-   size_t ws_stride;      /* doubles per block */
+   double *G_obs;         /* [R][m][n] obstacle + self-collision gradient, unscaled (tiled path) */
+   double *tile_cost;     /* [R][n_tiles] cost partials (tiled path) */
+   size_t ws_stride;      /* doubles of per-run workspace in shared memory (persistent kernel) */
 };
 
 #ifdef __cplusplus
@@ -103,7 +107,12 @@ extern "C" {
 #endif
 /* kernels' host launchers (defined in the .cu files) */
 cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st);
-size_t ocb_chomp_smem_bytes(const OcbChompArgs *args, int ws_in_smem);
+size_t ocb_chomp_smem_bytes(const OcbChompArgs *args);
+/* chomp_tiled.cu */
+size_t ocb_tile_smem_bytes(const OcbChompArgs *args, int tile_w);
+size_t ocb_run_update_smem_bytes(const OcbChompArgs *args);
+cudaError_t ocb_launch_chomp_tiled(const OcbChompArgs *args, size_t tile_smem, size_t run_smem,
+                                   int run_threads, cudaStream_t st, long *launches);
 cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const double *q_goal,
                                  int R, int P, int n, cudaStream_t st);
 cudaError_t ocb_launch_best(const double *costs, const int *status, int R, int *best_run,

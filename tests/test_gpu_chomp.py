@@ -293,9 +293,10 @@ def test_full_size_batch_properties(engine, wam7, table):
     engine.remove_sdf(sid)
 
 
-def test_dense_sphere_robot_global_workspace(engine, oracle, flavour, table):
-    """config-5 shape at small scale: 200 spheres do not fit the shared-memory workspace, so the
-    kernel variant with the per-block HBM workspace runs; 4 SDFs with distinct rotated poses."""
+def test_dense_sphere_robot_tiled_path(engine, oracle, flavour, table):
+    """config-5 shape at small scale: 200 spheres do not fit the persistent kernel's shared-memory
+    workspace, so the tiled two-kernel path runs (62 moving waypoints = one full and one ragged
+    tile); 4 SDFs with distinct rotated poses."""
     robot = models.dense_sphere_arm(200, seed=5)
     rng = np.random.default_rng(9)
     sds = []
