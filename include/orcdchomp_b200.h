@@ -141,6 +141,8 @@ int ocb_engine_force_general_sdf(ocb_engine *e, int on);
 /* squared Euclidean distance transform alone: cd_grid_double_dt_sqeuc (grid.c:462-569) */
 int ocb_dt_sqeuc_device(ocb_engine *e, const double *d_func, const int sizes[3],
                         const double lengths[3], double *d_out);
+int ocb_dt_sqeuc_host(ocb_engine *e, const double *func, const int sizes[3],
+                      const double lengths[3], double *out);
 
 /* --- occupancy pipeline of computedistancefield (mod.cpp:386-410, 498-548) --- */
 /* Analytic stand-in for the per-voxel OpenRAVE CheckCollision(cube): a voxel is
@@ -170,6 +172,8 @@ int ocb_occupancy_device(ocb_engine *e, const ocb_prim *prims, int n_prims,
  * becomes HUGE_VAL.  Works in place on an HBM grid.                            */
 int ocb_flood_relabel_device(ocb_engine *e, double *d_grid, const int sizes[3],
                              size_t index_start);
+int ocb_flood_relabel_host(ocb_engine *e, double *grid, const int sizes[3],
+                           size_t index_start);
 /* whole pipeline with host buffers (what `computedistancefield` does after the
  * AABB sizing): occupancy -> flood/relabel -> SDF.  obs_out may be NULL.       */
 int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prims, int n_prims,

@@ -252,8 +252,10 @@ EXPORTS = {
     "ocb_sdf_build_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, c_double_p, C.c_void_p]),
     "ocb_engine_force_general_sdf": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_dt_sqeuc_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, c_double_p, C.c_void_p]),
+    "ocb_dt_sqeuc_host": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, c_double_p]),
     "ocb_occupancy_device": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p, C.c_double, C.c_void_p]),
     "ocb_flood_relabel_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, C.c_size_t]),
+    "ocb_flood_relabel_host": (C.c_int, [C.c_void_p, c_double_p, c_int_p, C.c_size_t]),
     "ocb_computedistancefield_host": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p, C.c_double, c_double_p, c_double_p]),
     "ocb_batch_create": (C.c_int, [C.c_void_p, C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_int, c_int_p, C.c_int, c_double_p, c_double_p, c_uint_p, C.POINTER(C.c_void_p)]),
     "ocb_batch_reset": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_uint_p]),

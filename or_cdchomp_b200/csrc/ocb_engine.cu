@@ -438,6 +438,38 @@ extern "C" int ocb_sdf_build_host(ocb_engine *e, const double *obs, const int si
    return OCB_OK;
 }
 
+extern "C" int ocb_dt_sqeuc_host(ocb_engine *e, const double *func, const int sizes[3],
+                                 const double lengths[3], double *out)
+{
+   if (!e || !func || !out) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
+   double *d_in = nullptr, *d_out = nullptr;
+   if (cudaMalloc((void **) &d_in, bytes) != cudaSuccess || cudaMalloc((void **) &d_out, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      cudaFree(d_in);
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of 2 x %zu bytes failed", bytes);
+   }
+   cudaError_t err = cudaMemcpyAsync(d_in, func, bytes, cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess)
+   {
+      rc = ocb_dt_sqeuc_device(e, d_in, sizes, lengths, d_out);
+      if (rc == OCB_OK)
+      {
+         err = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, e->stream);
+         if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+      }
+   }
+   cudaFree(d_in);
+   cudaFree(d_out);
+   if (rc) return rc;
+   if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "dt_sqeuc_host: %s", cudaGetErrorString(err));
+   return OCB_OK;
+}
+
 extern "C" int ocb_occupancy_device(ocb_engine *e, const ocb_prim *prims, int n_prims, const int sizes[3],
                                     const double lengths[3], double cube_extent, double *d_grid)
 {
@@ -491,6 +523,35 @@ extern "C" int ocb_flood_relabel_device(ocb_engine *e, double *d_grid, const int
    int rc = engine_scratch(e, ocb_flood_scratch_bytes(sizes));
    if (rc) return rc;
    CU(ocb_launch_flood_relabel(d_grid, sizes, index_start, e->scratch, e->scratch_bytes, e->stream, &e->launches));
+   return OCB_OK;
+}
+
+extern "C" int ocb_flood_relabel_host(ocb_engine *e, double *grid, const int sizes[3], size_t index_start)
+{
+   if (!e || !grid) return fail(OCB_ERR_ARG, "null argument");
+   if (sizes[0] < 1 || sizes[1] < 1 || sizes[2] < 1) return fail(OCB_ERR_ARG, "bad grid sizes");
+   CU(cudaSetDevice(e->device));
+   const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
+   double *d = nullptr;
+   if (cudaMalloc((void **) &d, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu bytes failed", bytes);
+   }
+   int rc = OCB_OK;
+   cudaError_t err = cudaMemcpyAsync(d, grid, bytes, cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess)
+   {
+      rc = ocb_flood_relabel_device(e, d, sizes, index_start);
+      if (rc == OCB_OK)
+      {
+         err = cudaMemcpyAsync(grid, d, bytes, cudaMemcpyDeviceToHost, e->stream);
+         if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+      }
+   }
+   cudaFree(d);
+   if (rc) return rc;
+   if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "flood_relabel_host: %s", cudaGetErrorString(err));
    return OCB_OK;
 }
 

@@ -69,3 +69,36 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert "pyoracle" not in text and "liboracle" not in text and "import oracle" not in text, f
+
+
+def test_libcd_compat_library_exports_and_refuses_without_gpu():
+    """include/libcd_b200.h: every declared function is exported under libcd's own names; without a
+    GPU the calls fail with -3 (no CPU path), a wrong cell type with libcd's -2."""
+    import numpy as np
+    from or_cdchomp_b200 import libcd
+    src = open(os.path.join(ROOT, "include", "libcd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(cd_grid_[a-z0-9_]+)\s*\(", src)))
+    assert declared == sorted(libcd.EXPORTS)
+    lib = libcd.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    # struct layout against the C compiler
+    import subprocess
+    import tempfile
+    probe = '#include <stdio.h>\n#include "libcd_b200.h"\nint main(void){ printf("%zu\\n", sizeof(struct cd_grid)); return 0; }\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(probe)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
+        assert int(subprocess.check_output([os.path.join(d, "p")])) == C.sizeof(libcd.CdGrid)
+    # cell type check comes first, as grid.c:648-649
+    g = libcd.HostGrid(np.zeros((4, 4, 4)), [1, 1, 1], cell_size=1)
+    out = C.POINTER(libcd.CdGrid)()
+    assert lib.cd_grid_double_bin_sdf(C.byref(out), C.byref(g.c)) == -2
+    g2 = libcd.HostGrid(np.zeros((4, 4)), [1, 1])
+    assert lib.cd_grid_double_bin_sdf(C.byref(out), C.byref(g2.c)) == -2
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(libcd.LibcdError) as ei:
+            libcd.bin_sdf(np.zeros((4, 4, 4)), [1, 1, 1])
+        assert ei.value.code == -3 and "no CPU path" in str(ei.value)

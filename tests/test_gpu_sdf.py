@@ -221,3 +221,40 @@ def test_full_size_sdf_properties(engine):
             continue
         d = ((oc - p.double()) * pitch).pow(2).sum(1).min().sqrt()
         assert abs(float(d) - float(sdf[p[0], p[1], p[2]])) < 1e-12
+
+
+def test_libcd_named_entry_points(oracle, flavour):
+    """libcd_b200.so: cd_grid_double_bin_sdf / dt_sqeuc / sedt under libcd's names and struct
+    layout (grid.h:29-41, 84-93) return freshly malloc'ed grids holding the oracle's values;
+    the fused flood + relabel call works in place on a caller-owned grid."""
+    from or_cdchomp_b200 import libcd
+    rng = np.random.default_rng(31)
+    gold = np.load(golden_path("sdf_build.npz"))
+    for k in ("iso", "aniso", "heights"):
+        sdf, lens = libcd.bin_sdf(gold[k + "_obs"], gold[k + "_len"])
+        ref = gold[k + "_sdf"]
+        fin = np.isfinite(ref)
+        assert np.allclose(lens, gold[k + "_len"], rtol=0, atol=0)
+        assert np.array_equal(np.isfinite(sdf), fin) and np.max(np.abs(sdf[fin] - ref[fin]), initial=0.0) <= SDF_ATOL
+    obs = np.where(rng.uniform(size=(21, 34, 18)) < 0.04, np.inf, 0.0)
+    lens = [0.42, 0.68, 0.36]
+    sdf, _ = libcd.bin_sdf(obs, lens)
+    assert np.max(np.abs(sdf - oracle.sdf_from_obsarray(obs, lens, flavour=flavour))) <= SDF_ATOL
+    func = np.where(rng.uniform(size=(12, 9, 20)) < 0.1, 0.0, np.inf)
+    func[rng.uniform(size=func.shape) < 0.05] = 0.37  # parabola heights (grid.c:274-304)
+    ref = oracle.dt_sqeuc(func, [1.2, 0.9, 2.0], flavour=flavour)
+    for legacy in (False, True):
+        dt, _ = libcd.dt_sqeuc(func, [1.2, 0.9, 2.0], legacy_name=legacy)
+        assert np.max(np.abs(dt - ref)) <= SDF_ATOL
+    # flood + relabel: closed shell around a pocket (mod.cpp:536-548)
+    g = np.ones((16, 16, 16))
+    g[4:12, 4:12, 4:12] = np.inf
+    g[6:10, 6:10, 6:10] = 1.0
+    out = libcd.flood_relabel(g, [1, 1, 1], 0)
+    want = np.zeros_like(g)
+    want[4:12, 4:12, 4:12] = np.inf
+    assert np.array_equal(out, want)
+    # error paths keep libcd's codes
+    with pytest.raises(libcd.LibcdError) as ei:
+        libcd.bin_sdf(np.zeros((4, 4)), [1, 1])
+    assert ei.value.code == -2
