@@ -32,6 +32,8 @@
 #define LIBCD_B200_H
 
 #include <stddef.h>
+#include <time.h>
+#include "orcdchomp_b200.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -62,6 +64,92 @@ int cd_grid_b200_flood_relabel(struct cd_grid *g, size_t index_start);
 /* GPU used by the calls above (default: $OCB_DEVICE or 0); takes effect on the next call */
 int cd_grid_b200_set_device(int device);
 const char *cd_grid_b200_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * The cd_chomp C interface (src/libcd/chomp.h:106-140) for ONE run, GPU-backed.
+ *
+ * Same four entry points, same public struct (chomp.h:38-101), same meaning of the fields
+ * the reference's module pokes between calls (mod.cpp:2521-2660, 2752-2831):
+ *   n, m, D, T / ldt (the caller's trajectory rows, not owned, chomp.h:45), lambda, dt,
+ *   inits[0] / finals[0] (end points), jlimit_lower / jlimit_upper, use_momentum,
+ *   leapfrog_first, AG (momentum; the module resamples it for HMC), T_points / AG_points.
+ * What cannot cross to the device are the host callbacks cost_pre / cost / cost_extra: the
+ * obstacle + self-collision cost of sphere_cost_pre / sphere_cost (mod.cpp:968-1327) is
+ * built in instead and configured by cd_chomp_b200_set_sphere_cost() where the module would
+ * assign c->cost_pre / c->cost (mod.cpp:2616-2618).  Constraints (cd_chomp_add_constraint)
+ * are not offered.  Members the reference materialises only for its own dense algebra
+ * (A, Ainv, B, Kvels, Evels, vels, cost_*, Gjlimit*, cons_*) are left NULL: the engine uses
+ * the banded factor.  G is allocated and filled with the gradient of the last iteration.
+ *
+ * cd_chomp_iterate copies T (and AG) in, runs one update (do_iteration != 0) or the cost
+ * evaluation alone, and copies T, AG, G back; costs as chomp.c:679-681.  Returns 0, or -1
+ * when the joint-limit projection gives up (chomp.c:651-655), -2 for an unsupported set-up
+ * (dt other than 1/(m+1), wds other than [0..0,1], free end points), -3 for CUDA failures.
+ * For throughput use the batched API (orcdchomp_b200.h); this facade exists so that code
+ * written against libcd keeps its shape.                                                   */
+#ifndef LIBCD_B200_NO_STRUCT
+struct cd_chomp_con;
+struct cd_chomp
+{
+   int n;
+   int m;
+   double lambda;
+   double dt;
+   double *T;
+   int ldt;
+   double **T_points;
+   double *G;
+   double **G_points;
+   double *AG;
+   double **AG_points;
+   int D;
+   double *wds;
+   double **inits;
+   double **finals;
+   double *initsfinals;
+   double *A;
+   double *Ainv;
+   double *B;
+   double trC;
+   double *jlimit_lower;
+   double *jlimit_upper;
+   double *Kvels;
+   double *Evels;
+   double *vels;
+   double *cost_nxn;
+   double *cost_mxn;
+   double *Gjlimit;
+   double *GjlimitAinv;
+   void *cptr;
+   int (*cost_pre)(void *cptr, struct cd_chomp *c, int m, double **T_points);
+   int (*cost)(void *cptr, struct cd_chomp *c, int ti, double *point, double *vel, double *costp, double *grad);
+   int (*cost_extra)(void *cptr, struct cd_chomp *c, double *T, double *costp, double *G);
+   int use_momentum;
+   int leapfrog_first;
+   struct cd_chomp_con *cons;
+   int cons_k;
+   double *cons_h;
+   double *cons_Jcol;
+   double *cons_JAJT;
+   int *cons_ipiv;
+   double *cons_delta;
+   struct timespec ticks_vels;
+   struct timespec ticks_callback_pre;
+   struct timespec ticks_callbacks;
+   struct timespec ticks_smoothgrad;
+   struct timespec ticks_smoothcost;
+};
+#endif
+
+int cd_chomp_create(struct cd_chomp **cp, int m, int n, int D, double *T, int ldt);
+void cd_chomp_free(struct cd_chomp *c);
+int cd_chomp_init(struct cd_chomp *c);
+int cd_chomp_iterate(struct cd_chomp *c, int do_iteration, double *costp_total, double *costp_obs,
+                     double *costp_smooth);
+/* robot->limit_* are ignored (c->jlimit_* rule, as in the reference); of params only epsilon,
+ * epsilon_self, obs_factor, obs_factor_self are read; sdfs[i].data are host grids, copied. */
+int cd_chomp_b200_set_sphere_cost(struct cd_chomp *c, const ocb_robot *robot, const ocb_params *params,
+                                  int n_sdfs, const ocb_sdf *sdfs);
 
 #ifdef __cplusplus
 }

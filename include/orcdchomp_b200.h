@@ -207,6 +207,12 @@ int ocb_batch_iterate(ocb_batch *b, int n_iter, double *cost_total, double *cost
 int ocb_batch_iterate_async(ocb_batch *b, int n_iter);
 int ocb_batch_get_costs(ocb_batch *b, double *cost_total, double *cost_obs,
                         double *cost_smooth, int *status);
+/* the public cd_chomp fields a caller may poke between iterations (chomp.h:40-41, 49-50,
+ * 95-96): the momentum matrix AG [R][m][n] with its leapfrog_first flags [R] -- the
+ * reference's module resamples AG itself for HMC (mod.cpp:2755-2768) -- and lambda. */
+int ocb_batch_set_momentum(ocb_batch *b, const double *AG, const int *leapfrog_first);
+int ocb_batch_get_momentum(ocb_batch *b, double *AG, int *leapfrog_first);
+int ocb_batch_set_lambda(ocb_batch *b, double lambda);
 /* per-iteration cost log of the last iterate call: [R][n_iter][3] (total, obs,
  * smooth) as RAVELOG_INFO prints them (mod.cpp:2798).  Enable before iterate. */
 int ocb_batch_enable_trace(ocb_batch *b, int enable);

@@ -1197,6 +1197,39 @@ extern "C" int ocb_batch_set_traj(ocb_batch *b, const double *traj)
    return OCB_OK;
 }
 
+extern "C" int ocb_batch_set_momentum(ocb_batch *b, const double *AG, const int *leapfrog_first)
+{
+   if (!b || !AG || !leapfrog_first) return fail(OCB_ERR_ARG, "null argument");
+   if (!b->args.use_momentum) return fail(OCB_ERR_ARG, "the batch was created without use_momentum");
+   CU(cudaSetDevice(b->e->device));
+   const OcbChompArgs &a = b->args;
+   CU(cudaMemcpyAsync(a.AG, AG, (size_t) a.R * a.m * a.n * sizeof(double), cudaMemcpyHostToDevice, b->e->stream));
+   CU(cudaMemcpyAsync(a.leapfrog_first, leapfrog_first, (size_t) a.R * sizeof(int), cudaMemcpyHostToDevice, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_get_momentum(ocb_batch *b, double *AG, int *leapfrog_first)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   if (!b->args.use_momentum) return fail(OCB_ERR_ARG, "the batch was created without use_momentum");
+   CU(cudaSetDevice(b->e->device));
+   const OcbChompArgs &a = b->args;
+   if (AG) CU(cudaMemcpyAsync(AG, a.AG, (size_t) a.R * a.m * a.n * sizeof(double), cudaMemcpyDeviceToHost, b->e->stream));
+   if (leapfrog_first)
+      CU(cudaMemcpyAsync(leapfrog_first, a.leapfrog_first, (size_t) a.R * sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_set_lambda(ocb_batch *b, double lambda)
+{
+   if (!b) return fail(OCB_ERR_ARG, "null batch");
+   if (!(lambda > 0.0)) return fail(OCB_ERR_ARG, "lambda must be positive");
+   b->args.lambda = lambda;
+   return OCB_OK;
+}
+
 extern "C" int ocb_batch_enable_trace(ocb_batch *b, int enable)
 {
    if (!b) return fail(OCB_ERR_ARG, "null batch");

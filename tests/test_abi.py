@@ -78,7 +78,7 @@ def test_libcd_compat_library_exports_and_refuses_without_gpu():
     from or_cdchomp_b200 import libcd
     src = open(os.path.join(ROOT, "include", "libcd_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    declared = sorted(set(re.findall(r"\b(cd_grid_[a-z0-9_]+)\s*\(", src)))
+    declared = sorted(set(re.findall(r"\b(cd_(?:grid|chomp)_[a-z0-9_]+)\s*\(", src)))
     assert declared == sorted(libcd.EXPORTS)
     lib = libcd.load()
     for name in declared:
@@ -91,6 +91,10 @@ def test_libcd_compat_library_exports_and_refuses_without_gpu():
         open(os.path.join(d, "p.c"), "w").write(probe)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
         assert int(subprocess.check_output([os.path.join(d, "p")])) == C.sizeof(libcd.CdGrid)
+        probe2 = probe.replace("struct cd_grid", "struct cd_chomp")
+        open(os.path.join(d, "q.c"), "w").write(probe2)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "q.c"), "-o", os.path.join(d, "q")])
+        assert int(subprocess.check_output([os.path.join(d, "q")])) == C.sizeof(libcd.CdChomp)
     # cell type check comes first, as grid.c:648-649
     g = libcd.HostGrid(np.zeros((4, 4, 4)), [1, 1, 1], cell_size=1)
     out = C.POINTER(libcd.CdGrid)()
@@ -102,3 +106,32 @@ def test_libcd_compat_library_exports_and_refuses_without_gpu():
         with pytest.raises(libcd.LibcdError) as ei:
             libcd.bin_sdf(np.zeros((4, 4, 4)), [1, 1, 1])
         assert ei.value.code == -3 and "no CPU path" in str(ei.value)
+
+
+def test_libcd_struct_layouts_match_reference_headers():
+    """field offsets of struct cd_grid / struct cd_chomp in include/libcd_b200.h against the
+    reference's own headers (only where the reference tree is mounted)."""
+    ref = "/root/reference/src"
+    if not os.path.isdir(os.path.join(ref, "libcd")):
+        pytest.skip("reference tree not present")
+    import subprocess
+    import tempfile
+    fields = ["n", "m", "lambda", "dt", "T", "ldt", "T_points", "G", "G_points", "AG", "AG_points", "D", "wds", "inits",
+              "finals", "initsfinals", "A", "Ainv", "B", "trC", "jlimit_lower", "jlimit_upper", "Kvels", "Evels", "vels",
+              "cost_nxn", "cost_mxn", "Gjlimit", "GjlimitAinv", "cptr", "cost_pre", "cost", "cost_extra", "use_momentum",
+              "leapfrog_first", "cons", "cons_k", "cons_h", "cons_Jcol", "cons_JAJT", "cons_ipiv", "cons_delta",
+              "ticks_vels", "ticks_callback_pre", "ticks_callbacks", "ticks_smoothgrad", "ticks_smoothcost"]
+    gfields = ["n", "sizes", "ncells", "cell_size", "data", "lengths"]
+    body = "".join('printf("%%zu\\n", offsetof(struct cd_chomp, %s));' % f for f in fields)
+    body += "".join('printf("%%zu\\n", offsetof(struct cd_grid, %s));' % f for f in gfields)
+    body += 'printf("%zu %zu\\n", sizeof(struct cd_chomp), sizeof(struct cd_grid));'
+    head = "#include <stdio.h>\n#include <stdlib.h>\n#include <stddef.h>\n#include <time.h>\n"
+    with tempfile.TemporaryDirectory() as d:
+        outs = []
+        for name, inc, flags in (("ref", "#include <libcd/grid.h>\n#include <libcd/chomp.h>\n", ["-I", ref]),
+                                 ("mine", '#include "libcd_b200.h"\n', ["-I", os.path.join(ROOT, "include")])):
+            c = os.path.join(d, name + ".c")
+            open(c, "w").write(head + inc + "int main(void){" + body + "return 0;}\n")
+            subprocess.check_call(["gcc"] + flags + [c, "-o", os.path.join(d, name)])
+            outs.append(subprocess.check_output([os.path.join(d, name)]))
+    assert outs[0] == outs[1]

@@ -371,3 +371,58 @@ def test_set_traj_and_derivative3(engine, oracle, flavour, wam7, table):
         run.close()
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_cd_chomp_facade_matches_reference(oracle, flavour, wam7, table):
+    """libcd_b200.so's cd_chomp_create / init / iterate / free (chomp.h:106-140), driven the way
+    the module drives libcd -- caller-owned trajectory, public fields poked on the struct, HMC
+    momentum resampled by the caller into c->AG (mod.cpp:2755-2768) -- against the oracle."""
+    from or_cdchomp_b200 import libcd
+    sd = table["desc"]
+    starts, goals = models.random_endpoints(wam7, 2, seed0=901, shrink=0.3)
+    # plain covariant descent
+    params = capi.default_params(n_points=48, lambda_=120.0, obs_factor=400.0)
+    run = oracle.Run(wam7, params, [sd], starts[0], goals[0], flavour=flavour)
+    fac = libcd.ChompRun(wam7, params, [sd], starts[0], goals[0])
+    for it in range(12):
+        ret, c, tr, gr = run.iterate(1, want_trace=True, want_grads=True)
+        rc, cf = fac.iterate(1)
+        assert rc == ret == 0
+        assert np.allclose(cf, tr[0], rtol=1e-9, atol=0)
+        assert np.max(np.abs(fac.gradient() - gr[0])) <= GRAD_RTOL * np.max(np.abs(gr[0]))
+        assert np.max(np.abs(fac.traj - run.traj())) <= TRAJ_ATOL
+    rc, cf = fac.iterate(0)  # cost evaluation only (do_iteration = 0)
+    _, c, _, _ = run.iterate(0)
+    assert rc == 0 and np.allclose(cf, c, rtol=1e-9, atol=0)
+    fac.close()
+    run.close()
+    # momentum + caller-side HMC resampling with the module's generator and draw order
+    params = capi.default_params(n_points=40, lambda_=150.0, obs_factor=300.0, use_momentum=1, use_hmc=1,
+                                 hmc_resample_lambda=0.1)
+    seed = 7
+    run = oracle.Run(wam7, params, [sd], starts[1], goals[1], seed=seed, flavour=flavour)
+    fac = libcd.ChompRun(wam7, params, [sd], starts[1], goals[1])
+    mt = oracle.MT(seed, flavour=flavour)
+    hmc_next = 0
+    resamples = 0
+    for it in range(25):
+        if it == hmc_next:
+            sigma = 1.0 / np.sqrt(100.0 * np.exp(0.02 * it))
+            ag = fac.momentum()
+            for i in range(fac.m):
+                for j in range(fac.n):
+                    ag[i, j] = mt.gaussian(sigma)
+            fac.c.contents.leapfrog_first = 1
+            hmc_next += 1 + int(-np.log(mt.uniform()) / 0.1)
+            resamples += 1
+        rc, cf = fac.iterate(1)
+        assert rc == 0
+    # the oracle resamples inside its own 25-iteration call (its counter restarts per call,
+    # mod.cpp:2752); compare the end state
+    ret, c, tr, _ = run.iterate(25, want_trace=True)
+    assert ret == 0 and resamples >= 2 and run.hmc_next() == hmc_next
+    assert np.max(np.abs(fac.traj - run.traj())) <= TRAJ_ATOL
+    assert np.max(np.abs(fac.momentum() - run.momentum())) <= 1e-9 * max(1.0, np.max(np.abs(run.momentum())))
+    assert np.allclose(cf, tr[-1], rtol=1e-9, atol=0)
+    fac.close()
+    run.close()
