@@ -19,9 +19,12 @@
  * What it replaces in the reference is what chomp_kernel.cu lists (cd_chomp_iterate,
  * sphere_cost_pre, sphere_cost); only the decomposition differs.
  *
- * Self collision is evaluated as in the reference, per ORDERED pair (mod.cpp:1251-1317):
- * sphere s takes +x(s, o) from its own visit of o and -x(o, s) from o's visit of s, so a
- * worker can finish its spheres without touching accumulators owned by another worker.
+ * Self collision: the reference visits every ordered pair (mod.cpp:1251-1317); here each
+ * unordered pair {s, o > s} is visited once by the worker that owns s.  Both directed terms
+ * are formed, their difference is the net force on s, its negative the reaction on o.  The
+ * reaction is summed per partner joint frame in registers while the partner sweep stays in
+ * that frame's sphere range and is folded into joint space when the sweep leaves it, so no
+ * worker touches accumulators owned by another one.
  */
 #include "chomp_device.cuh"
 
@@ -82,25 +85,45 @@ __device__ __forceinline__ void sphere_state(const double *__restrict__ pcol, in
    S.moving = S.vn > 0.000001;
 }
 
-/* sphere s (state S) is within range of partner at q (radius sum rsum): cost of s towards the
- * partner and, when want_grad, the net workspace force on s:  x(s, o) - x(o, s), the second
- * term only for a moving (active) partner whose centre column is po. */
-__device__ __forceinline__ void self_pair_term(const OcbChompArgs &a, const SphereState &S, const double q[3],
-                                               const double *__restrict__ po, int CS, double rsum,
-                                               bool want_grad, double &cost_s, double f[3])
+/* sphere s (state S) is within range of a partner centred at q (radius sum rsum).  Adds the
+ * cost of the pair -- seen from s and, for an active partner (po = its centre column), from
+ * the partner as well -- to cost_s and returns in x the net workspace force on s,
+ * x(s, o) - x(o, s); the reaction on an active partner is -x. */
+struct PairConst
 {
-   const double es = a.eps_self, inv_es = 1.0 / es, half_inv_es = 0.5 / es;
+   double es, inv_es, half_inv_es, inv2dt, obs_factor_self;
+};
+
+__device__ __forceinline__ void self_pair_term(const PairConst &K, const SphereState &S, const double q[3],
+                                               const double *__restrict__ po, int CS, double rsum,
+                                               bool want_grad, double &cost_s, double x[3])
+{
+   const double es = K.es, inv_es = K.inv_es, half_inv_es = K.half_inv_es;
    const double dx = S.p[0] - q[0], dy = S.p[1] - q[1], dz = S.p[2] - q[2];
    const double d2 = dx * dx + dy * dy + dz * dz;
    const double inv = rsqrt(d2);
    const double dd = d2 * inv - rsum;
    const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
-   const double ws_self = S.vn * a.obs_factor_self;
+   const double ws_self = S.vn * K.obs_factor_self;
    cost_s += ws_self * cshape;
+   double v2[3] = {0.0, 0.0, 0.0}, r2 = 0.0, w2 = 0.0;
+   bool moving2 = false;
+   if (po)
+   {
+      const double inv2dt = K.inv2dt;
+#pragma unroll
+      for (int r = 0; r < 3; r++) v2[r] = (po[r * CS + 1] - po[r * CS - 1]) * inv2dt;
+      const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+      r2 = rsqrt(v2n2);
+      const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
+      moving2 = v2n > 0.000001;
+      w2 = v2n * K.obs_factor_self;
+      cost_s += w2 * cshape; /* the partner's own cost_sphere term */
+   }
+   x[0] = x[1] = x[2] = 0.0;
    if (!want_grad) return;
    const double sc = (dd < 0.0) ? -1.0 : ((dd < es) ? (dd * inv_es - 1.0) : 1.0);
    const double gh[3] = {dx * inv, dy * inv, dz * inv};
-   double x[3];
    const double wa = sc * ws_self;
 #pragma unroll
    for (int r = 0; r < 3; r++) x[r] = gh[r] * wa;
@@ -113,18 +136,11 @@ __device__ __forceinline__ void self_pair_term(const OcbChompArgs &a, const Sphe
    if (po)
    {
       /* the pair seen from o: unit vector -gh, weighted by o's speed */
-      const double inv2dt = 1.0 / (2.0 * a.dt);
-      double v2[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) v2[r] = (po[r * CS + 1] - po[r * CS - 1]) * inv2dt;
-      const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-      const double r2 = rsqrt(v2n2);
-      const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
       double y[3];
-      const double wb = -sc * (v2n * a.obs_factor_self);
+      const double wb = -sc * w2;
 #pragma unroll
       for (int r = 0; r < 3; r++) y[r] = gh[r] * wb;
-      if (v2n > 0.000001)
+      if (moving2)
       {
          const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * (r2 * r2);
 #pragma unroll
@@ -133,8 +149,6 @@ __device__ __forceinline__ void self_pair_term(const OcbChompArgs &a, const Sphe
 #pragma unroll
       for (int r = 0; r < 3; r++) x[r] -= y[r];
    }
-#pragma unroll
-   for (int r = 0; r < 3; r++) f[r] += x[r];
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 1)
@@ -201,23 +215,23 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
    }
    __syncthreads();
 
-   /* ---- phase 2: a worker's lanes are the tile's waypoints; its spheres one contiguous chunk ---- */
+   /* ---- phase 2: a worker's lanes are the tile's waypoints ---- */
    const int worker = tid / TW, wp = tid - worker * TW;
    const bool lane_valid = t_first + wp <= m;
    const int wpc = lane_valid ? wp : (m - t_first); /* idle tail lanes shadow the last waypoint */
    const int c = wpc + 1;
    const double *pcol = pos + c;
-   const int sb = (worker * nsa) / NW, se = ((worker + 1) * nsa) / NW;
+   const int n_quads = (nsa + 3) >> 2;
    double *Gw = Gp + worker * n * TW + wp;
    const double inv2dt = 1.0 / (2.0 * a.dt), invdt2 = 1.0 / (a.dt * a.dt);
    const double es = a.eps_self;
+   const PairConst K = {es, 1.0 / es, 0.5 / es, inv2dt, a.obs_factor_self};
    const int row = a.NAp + a.nsi;
    double cost = 0.0;
 
-   int gcur = -1;
-   double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
-   /* J^T of a joint frame's wrench through the stored axes:  c0 axis . (M - org x F) */
-   auto flush_group = [&](int g)
+   /* J^T of a wrench (F, M about the world origin) acting on joint frame group g, through the
+    * stored axes of the joints above it:  c0 axis . (M - org x F), or c0 axis . F (prismatic) */
+   auto flush_group = [&](int g, const double F[3], const double M[3])
    {
       const int *ga = a.ganc;
       for (int e = __ldg(ga + g); e < __ldg(ga + g + 1); e++)
@@ -241,8 +255,16 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
       }
    };
 
-   for (int s0 = sb; s0 < se; s0 += 4)
+   int gcur = -1;
+   double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
+   /* own spheres are dealt to the workers four at a time, back and forth over the workers, so
+    * that every worker sees every part of the robot (in-range pairs cluster on neighbouring
+    * links) and long and short partner sweeps alike */
+   for (int round = 0; round * NW < n_quads; round++)
    {
+      const int quad = round * NW + ((round & 1) ? NW - 1 - worker : worker);
+      if (quad >= n_quads) continue;
+      const int s0 = quad << 2, se = nsa;
       /* four own spheres share every partner load of the range sweep */
       int sk[4], lk[4];
       double p[4][3], rk[4], f[4][3], cs[4];
@@ -250,49 +272,66 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
       for (int k = 0; k < 4; k++)
       {
          sk[k] = min(s0 + k, se - 1);
-         lk[k] = (s0 + k < se) ? link[sk[k]] : -1;
+         lk[k] = (s0 + k < se) ? link[sk[k]] : -1; /* a padded slot shadows the last sphere */
          rk[k] = rad[sk[k]] + es;
          const double *ps = pcol + 3 * sk[k] * CS;
          p[k][0] = ps[0]; p[k][1] = ps[CS]; p[k][2] = ps[2 * CS];
          f[k][0] = f[k][1] = f[k][2] = 0.0;
          cs[k] = 0.0;
       }
-      for (int ob = 0; ob < nsa; ob += 32)
+      /* partners above the own spheres, one joint frame's range at a time */
+      for (int j = 0; j < a.nj; j++)
       {
-         const int oe = min(32, nsa - ob);
-         unsigned mk[4] = {0u, 0u, 0u, 0u};
-         for (int i = 0; i < oe; i++)
+         const int ge = a.joints[j].sph_end;
+         const int o_lo = max(a.joints[j].sph_begin, s0 + 1);
+         if (o_lo >= ge) continue;
+         double Rf[3] = {0.0, 0.0, 0.0}, Rm[3] = {0.0, 0.0, 0.0}; /* reaction on this frame */
+         bool any = false;
+         for (int ob = o_lo; ob < ge; ob += 32)
          {
-            const int o = ob + i;
-            const double *po = pcol + 3 * o * CS;
-            const double q0 = po[0], q1 = po[CS], q2 = po[2 * CS];
-            const double ro = rad[o];
-            const int lo = link[o];
+            const int oe = min(32, ge - ob);
+            unsigned mk[4] = {0u, 0u, 0u, 0u};
+            for (int i = 0; i < oe; i++)
+            {
+               const int o = ob + i;
+               const double *po = pcol + 3 * o * CS;
+               const double q0 = po[0], q1 = po[CS], q2 = po[2 * CS];
+               const double ro = rad[o];
+               const int lo = link[o];
+#pragma unroll
+               for (int k = 0; k < 4; k++)
+               {
+                  const double dx = p[k][0] - q0, dy = p[k][1] - q1, dz = p[k][2] - q2;
+                  const double d2 = dx * dx + dy * dy + dz * dz;
+                  const double cut = rk[k] + ro; /* r_s + r_o + epsilon_self, mod.cpp:1268 */
+                  if (d2 <= cut * cut && lo != lk[k] && o > sk[k]) mk[k] |= 1u << i;
+               }
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++)
             {
-               const double dx = p[k][0] - q0, dy = p[k][1] - q1, dz = p[k][2] - q2;
-               const double d2 = dx * dx + dy * dy + dz * dz;
-               const double cut = rk[k] + ro; /* r_s + r_o + epsilon_self, mod.cpp:1268 */
-               if (d2 <= cut * cut && lo != lk[k]) mk[k] |= 1u << i;
+               unsigned mm = (lk[k] >= 0) ? mk[k] : 0u;
+               if (mm == 0u) continue;
+               any = true;
+               SphereState S;
+               sphere_state(pcol, CS, sk[k], inv2dt, invdt2, S);
+               while (mm)
+               {
+                  const int o = ob + __ffs(mm) - 1;
+                  mm &= mm - 1;
+                  const double *po = pcol + 3 * o * CS;
+                  const double q[3] = {po[0], po[CS], po[2 * CS]};
+                  double x[3];
+                  self_pair_term(K, S, q, po, CS, rk[k] - es + rad[o], want_grad != 0, cs[k], x);
+                  f[k][0] += x[0]; f[k][1] += x[1]; f[k][2] += x[2];
+                  Rf[0] -= x[0]; Rf[1] -= x[1]; Rf[2] -= x[2];
+                  Rm[0] -= q[1] * x[2] - q[2] * x[1];
+                  Rm[1] -= q[2] * x[0] - q[0] * x[2];
+                  Rm[2] -= q[0] * x[1] - q[1] * x[0];
+               }
             }
          }
-#pragma unroll
-         for (int k = 0; k < 4; k++)
-         {
-            unsigned mm = (lk[k] >= 0) ? mk[k] : 0u; /* a padded slot shadows the chunk's last sphere */
-            if (mm == 0u) continue;
-            SphereState S;
-            sphere_state(pcol, CS, sk[k], inv2dt, invdt2, S);
-            while (mm)
-            {
-               const int o = ob + __ffs(mm) - 1;
-               mm &= mm - 1;
-               const double *po = pcol + 3 * o * CS;
-               const double q[3] = {po[0], po[CS], po[2 * CS]};
-               self_pair_term(a, S, q, po, CS, rk[k] - es + rad[o], want_grad != 0, cs[k], f[k]);
-            }
-         }
+         if (any && want_grad) flush_group(a.spheres[o_lo].group, Rf, Rm);
       }
 #pragma unroll
       for (int k = 0; k < 4; k++)
@@ -310,7 +349,11 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
                                  __ldg(a.inactive_pos + 3 * i + 2)};
             const double dx = S.p[0] - q[0], dy = S.p[1] - q[1], dz = S.p[2] - q[2];
             if (dx * dx + dy * dy + dz * dz <= __ldg(crow + i))
-               self_pair_term(a, S, q, nullptr, CS, radius + __ldg(a.radius + nsa + i), want_grad != 0, cs[k], f[k]);
+            {
+               double x[3];
+               self_pair_term(K, S, q, nullptr, CS, radius + __ldg(a.radius + nsa + i), want_grad != 0, cs[k], x);
+               f[k][0] += x[0]; f[k][1] += x[1]; f[k][2] += x[2];
+            }
          }
          double co = 0.0, fo[3] = {0.0, 0.0, 0.0};
          obstacle_term(a, sdfs, S.p, S.vel, S.acc, S.vn, S.iv2, S.moving, radius, want_grad != 0, co, fo);
@@ -320,7 +363,7 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
             const int g = a.spheres[s].group;
             if (g != gcur)
             {
-               if (gcur >= 0) flush_group(gcur);
+               if (gcur >= 0) flush_group(gcur, F, M);
                gcur = g;
                F[0] = F[1] = F[2] = 0.0;
                M[0] = M[1] = M[2] = 0.0;
@@ -333,7 +376,7 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
          }
       }
    }
-   if (want_grad && gcur >= 0) flush_group(gcur);
+   if (want_grad && gcur >= 0) flush_group(gcur, F, M);
    cp[tid] = lane_valid ? cost : 0.0;
    __syncthreads();
 
