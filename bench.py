@@ -144,6 +144,9 @@ class _StdoutToStderr:
         return False
 
 
+CPU_SAMPLE_RUNS = 384  # ~12 s of single-core reference work at ~3.2 k run-iterations/s
+
+
 def cpu_baseline(flavour, robot, params, sd, n_runs, n_iter, threads=1):
     """run-iterations/s of the CPU oracle on `threads` host threads (one run each at a time)."""
     with _StdoutToStderr():
@@ -230,7 +233,7 @@ def reference_arm(args):
     _, sdf = po.computedistancefield(pa, len(gprims), sizes, lengths, 0.02, flavour=flavour)
     sd = capi.SdfDesc(sdf, lengths, pose_world)
     cores = os.cpu_count() or 1
-    runs_per_step = cores * 2
+    runs_per_step = cores * 32
     for _ in range(args.warmup):
         cpu_baseline(flavour, robot, params, sd, min(cores, 4), 10, threads=cores)
     t_total, it_total = 0.0, 0.0
@@ -411,10 +414,10 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import pyoracle as po
             flavour = po.best_flavour()
-            v, dt = cpu_baseline(flavour, robot, params, sd, 12, N_ITER, threads=1)
+            v, dt = cpu_baseline(flavour, robot, params, sd, CPU_SAMPLE_RUNS, N_ITER, threads=1)
             cpu = {"value": v, "unit": UNIT, "cores": 1,
                    "kind": "reference" if flavour == "reference" else "port",
-                   "sample": "first 12 runs of the batch x %d iterations, one thread (%.1f s)" % (N_ITER, dt)}
+                   "sample": "first %d runs of the batch x %d iterations, one thread (%.1f s)" % (CPU_SAMPLE_RUNS, N_ITER, dt)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms / args.steps, "higher_is_better": True,

@@ -24,10 +24,13 @@ for f in sorted(os.listdir(tmp)):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            if os.path.basename(m.group(1)) == os.path.basename(srcfile):
-                ctx = int(m.group(2)); cur = ctx
+            base = os.path.basename(m.group(1))
+            if base == os.path.basename(srcfile):
+                ctx = (base, int(m.group(2))); cur = ctx
+            elif os.path.exists(os.path.join(os.path.dirname(srcfile), base)):
+                cur = (base, int(m.group(2)))  # our own header next to the source file
             else:
-                cur = ctx  # header code: charge the enclosing line of our file
+                cur = ctx  # toolkit header code: charge the enclosing line of our file
             continue
         if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln):
             lines_of.append((cur, ln.split("*/", 1)[1].strip()))
@@ -54,7 +57,14 @@ for i, r in enumerate(body):
         v = r[ci[k]]
         if v and v != "0":
             a[k] += int(v)
-src = open(srcfile).read().splitlines()
+srcs = {}
+def text_of(key):
+    if not key:
+        return "?"
+    base, line = key
+    if base not in srcs:
+        srcs[base] = open(os.path.join(os.path.dirname(srcfile), base)).read().splitlines()
+    return srcs[base][line - 1].strip()[:80] if line <= len(srcs[base]) else "?"
 print("total samples", tot)
 glob = collections.Counter()
 for a in agg.values():
@@ -63,5 +73,5 @@ for a in agg.values():
 print("stall mix:", [(k, "%.1f%%" % (100.0 * v / tot)) for k, v in glob.most_common(8)])
 for line, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:topn]:
     top = sorted(((k, a[k]) for k in stalls if a[k]), key=lambda x: -x[1])[:3]
-    text = src[line - 1].strip()[:80] if line and line <= len(src) else "?"
-    print("%5s %5.1f%% inst=%-9d %-80s %s" % (line, 100.0 * a["samples"] / tot, a["inst"], text, [(k[6:], v) for k, v in top]))
+    where = "%s:%d" % (line[0].replace("chomp_", "").split(".")[0], line[1]) if line else "?"
+    print("%-12s %5.1f%% inst=%-10d %-80s %s" % (where, 100.0 * a["samples"] / tot, a["inst"], text_of(line), [(k[6:], v) for k, v in top]))
