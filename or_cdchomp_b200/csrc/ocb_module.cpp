@@ -540,10 +540,84 @@ struct ocb_module
       throw module_error("No field with that kinbody name exists!");
    }
 
+   /* `starttraj`: an OpenRAVE trajectory in its XML serialisation (what gettraj returns).  The
+    * reference deserialises it and samples the active-dof group at n_points evenly spaced times
+    * over its duration (mod.cpp:2005-2012, 2375-2415); here the two groups that matter are read
+    * directly -- "joint_values <robot> i0 i1 ..." (linear interpolation) and "deltatime" -- and
+    * sampled the same way.  out: [n_points][n]. */
+   static bool xml_attr(const std::string &tag, const char *name, std::string &val)
+   {
+      const std::string key = std::string(name) + "=\"";
+      size_t a = tag.find(key);
+      if (a == std::string::npos) return false;
+      a += key.size();
+      const size_t b = tag.find('"', a);
+      if (b == std::string::npos) return false;
+      val = tag.substr(a, b - a);
+      return true;
+   }
+
+   static void sample_starttraj(const std::string &xml, int n, int n_points, std::vector<double> &out)
+   {
+      int jv_off = -1, jv_dof = 0, dt_off = -1, stride = 0;
+      for (size_t pos = 0; (pos = xml.find("<group", pos)) != std::string::npos; pos++)
+      {
+         const size_t end = xml.find('>', pos);
+         if (end == std::string::npos) break;
+         const std::string tag = xml.substr(pos, end - pos);
+         std::string name, off, dof;
+         if (!xml_attr(tag, "name", name) || !xml_attr(tag, "offset", off) || !xml_attr(tag, "dof", dof)) continue;
+         const int o = atoi(off.c_str()), d = atoi(dof.c_str());
+         stride = std::max(stride, o + d);
+         if (name.compare(0, 12, "joint_values") == 0 && jv_off < 0) { jv_off = o; jv_dof = d; }
+         else if (name == "deltatime") dt_off = o;
+      }
+      if (jv_off < 0) throw module_error("starttraj has no joint_values group!");
+      if (jv_dof != n) throw module_error("starttraj joint_values group does not match the robot's active dofs!");
+      if (dt_off < 0) throw module_error("starttraj has no deltatime group (an untimed trajectory cannot be sampled)!");
+      const size_t d0 = xml.find("<data");
+      const size_t d1 = (d0 == std::string::npos) ? d0 : xml.find('>', d0);
+      const size_t d2 = (d1 == std::string::npos) ? d1 : xml.find("</data>", d1);
+      if (d2 == std::string::npos) throw module_error("starttraj has no data block!");
+      std::string cnt;
+      if (!xml_attr(xml.substr(d0, d1 - d0), "count", cnt)) throw module_error("starttraj data block has no count!");
+      const int count = atoi(cnt.c_str());
+      const std::vector<double> v = parse_doubles(xml.substr(d1 + 1, d2 - d1 - 1));
+      if (count < 2 || (size_t) count * stride != v.size()) throw module_error("starttraj data block has the wrong size!");
+      std::vector<double> tau(count);
+      double acc = 0.0;
+      for (int k = 0; k < count; k++)
+      {
+         const double dt = v[(size_t) k * stride + dt_off];
+         if (dt < 0.0) throw module_error("starttraj has a negative deltatime!");
+         acc += (k == 0) ? 0.0 : dt; /* the first waypoint's deltatime is not part of the duration */
+         tau[k] = acc;
+      }
+      const double duration = acc;
+      if (!(duration > 0.0)) throw module_error("starttraj has zero duration!");
+      out.assign((size_t) n_points * n, 0.0);
+      int seg = 0;
+      for (int i = 0; i < n_points; i++)
+      {
+         const double t = i * duration / (n_points - 1); /* mod.cpp:2411 */
+         while (seg < count - 2 && t > tau[seg + 1]) seg++;
+         const double span = tau[seg + 1] - tau[seg];
+         double w = (span > 0.0) ? (t - tau[seg]) / span : 1.0;
+         if (w < 0.0) w = 0.0;
+         if (w > 1.0) w = 1.0;
+         for (int j = 0; j < n; j++)
+         {
+            const double a = v[(size_t) seg * stride + jv_off + j], b = v[(size_t) (seg + 1) * stride + jv_off + j];
+            out[(size_t) i * n + j] = (w == 0.0) ? a : ((w == 1.0) ? b : a + (b - a) * w);
+         }
+      }
+   }
+
    /* mod.cpp:1800-2688 (single run) + the createbatch extension */
    int create(const std::vector<std::string> &argv, std::ostream &sout, bool batch_form)
    {
-      std::string robot_name, dat_filename;
+      std::string robot_name, dat_filename, starttraj;
+      bool have_starttraj = false;
       std::vector<double> adofgoal;
       ocb_params pr;
       ocb_params_default(&pr);
@@ -566,7 +640,15 @@ struct ocb_module
          else if (a == "adofgoal" && has1)
          {
             if (!adofgoal.empty()) throw module_error("Only one adofgoal can be passed!");
+            if (have_starttraj) throw module_error("Cannot pass both adofgoal and starttraj!");
             adofgoal = parse_doubles(argv[++i]);
+         }
+         else if (a == "starttraj" && has1)
+         {
+            if (have_starttraj) throw module_error("Only one starttraj can be passed!");
+            if (!adofgoal.empty()) throw module_error("Cannot pass both adofgoal and starttraj!");
+            starttraj = argv[++i];
+            have_starttraj = true;
          }
          else if (a == "lambda" && has1) pr.lambda = atof(argv[++i].c_str());
          else if (a == "n_points" && has1) pr.n_points = atoi(argv[++i].c_str());
@@ -582,7 +664,7 @@ struct ocb_module
          else if (a == "dat_filename" && has1) dat_filename = argv[++i];
          else if ((a == "ee_force" || a == "ee_force_at" || a == "ee_torque_weights") && has1) ++i; /* dead parameters, mod.cpp:1323 */
          else if (a == "floating_base") unsupported = "floating_base";
-         else if ((a == "basegoal" || a == "starttraj" || a == "start_tsr" || a == "everyn_tsr" || a == "start_cost") && has1)
+         else if ((a == "basegoal" || a == "start_tsr" || a == "everyn_tsr" || a == "start_cost") && has1)
          {
             unsupported = argv[i].c_str();
             ++i;
@@ -605,14 +687,20 @@ struct ocb_module
          throw module_error(std::string("'") + unsupported + "' is not supported by the B200 engine (see orcdchomp_b200_module.h)");
       /* validity checks in the reference's order (mod.cpp:2091-2101) */
       if (robot_name.empty()) throw module_error("Did not pass a robot!");
-      if (adofgoal.empty() && !goals_ptr) throw module_error("Did not pass either adofgoal or starttraj!");
+      if (adofgoal.empty() && !goals_ptr && !have_starttraj) throw module_error("Did not pass either adofgoal or starttraj!");
       if (sdfs.empty()) throw module_error("No signed distance fields have yet been computed!");
       if (pr.lambda < 0.01) throw module_error("lambda must be >=0.01!");
       if (pr.n_points < 3) throw module_error("n_points must be >=3!");
       Robot &rb = *env->robots[robot_name];
       const int n = rb.desc.n_dof;
-      if (!goals_ptr && (int) adofgoal.size() != n) throw module_error("size of adofgoal does not match active dofs!");
+      if (!goals_ptr && !have_starttraj && (int) adofgoal.size() != n) throw module_error("size of adofgoal does not match active dofs!");
       if (n_runs < 1) throw module_error("n_runs must be >=1!");
+      std::vector<double> seed_traj; /* [n_points][n] when starttraj was passed */
+      if (have_starttraj)
+      {
+         if (goals_ptr || starts_ptr) throw module_error("Cannot pass both adofgoals/adofstarts and starttraj!");
+         sample_starttraj(starttraj, n, pr.n_points, seed_traj);
+      }
 
       std::unique_ptr<Run> r(new Run());
       r->robot_name = robot_name;
@@ -642,6 +730,13 @@ struct ocb_module
       for (int k = 0; k < n_runs; k++)
          for (int j = 0; j < n; j++)
          {
+            if (have_starttraj)
+            {
+               /* the end rows of the sampled trajectory are the fixed end points (mod.cpp:2578-2580) */
+               starts[(size_t) k * n + j] = seed_traj[j];
+               goals[(size_t) k * n + j] = seed_traj[(size_t) (pr.n_points - 1) * n + j];
+               continue;
+            }
             starts[(size_t) k * n + j] = starts_ptr ? starts_ptr[(size_t) k * n + j] : rb.q[j]; /* GetActiveDOFValues, mod.cpp:2447 */
             goals[(size_t) k * n + j] = goals_ptr ? goals_ptr[(size_t) k * n + j] : adofgoal[j];
          }
@@ -653,6 +748,17 @@ struct ocb_module
          for (int s : r->sdf_ids) ocb_sdf_remove(engine, s);
          /* the engine's argument messages are the reference's own texts where one exists */
          throw module_error(rc == OCB_ERR_ARG ? ocb_last_error() : std::string("Error initializing chomp instance. ") + ocb_last_error());
+      }
+      if (have_starttraj)
+      {
+         std::vector<double> all((size_t) n_runs * seed_traj.size());
+         for (int k = 0; k < n_runs; k++) std::copy(seed_traj.begin(), seed_traj.end(), all.begin() + (size_t) k * seed_traj.size());
+         if (ocb_batch_set_traj(r->batch, all.data()) != OCB_OK)
+         {
+            ocb_batch_destroy(r->batch);
+            for (int s : r->sdf_ids) ocb_sdf_remove(engine, s);
+            fail_engine("error creating chomp instance!");
+         }
       }
       if (!dat_filename.empty())
       {

@@ -136,3 +136,39 @@ def test_createbatch_and_dat_file(world, tmp_path):
     mod.destroy(run=h)
     rows = [l.split() for l in open(dat)]
     assert len(rows) == 7 and [int(r[0]) for r in rows] == list(range(7)) and all(len(r) == 5 for r in rows)
+
+
+def test_starttraj_seeding(world):
+    """create starttraj=<trajectory XML> (mod.cpp:2005-2012, 2375-2415): the run starts from the
+    passed trajectory, sampled at n_points evenly spaced times over its duration."""
+    env, mod, table, robot, robot_desc = world
+    mod.computedistancefield(kinbody=table, cube_extent=0.02)
+    goal = list(models.WAM7_DEMO_GOAL)
+    h = mod.create(robot=robot, adofgoal=goal, n_points=60, lambda_=100.0, obs_factor=300.0)
+    mod.iterate(run=h, n_iter=7)
+    xml = mod.SendCommand("gettraj run %s no_collision_check" % h)
+    t7 = mod.gettraj(run=h, no_collision_check=True)
+    # same number of points: the seed is reproduced and the optimisation continues identically
+    h2 = mod.create(robot=robot, starttraj=xml, n_points=60, lambda_=100.0, obs_factor=300.0)
+    assert np.max(np.abs(mod.gettraj(run=h2, no_collision_check=True) - t7)) <= 1e-14
+    mod.iterate(run=h, n_iter=5)
+    mod.iterate(run=h2, n_iter=5)
+    a, b = mod.gettraj(run=h, no_collision_check=True), mod.gettraj(run=h2, no_collision_check=True)
+    assert np.max(np.abs(a - b)) <= 1e-11 and np.max(np.abs(a - t7)) > 1e-4
+    mod.destroy(run=h2)
+    # resampling to another length: linear interpolation in time, same end points
+    h3 = mod.create(robot=robot, starttraj=xml, n_points=119)
+    t = mod.gettraj(run=h3, no_collision_check=True)
+    assert t.shape == (119, 7)
+    assert np.max(np.abs(t[0] - t7[0])) == 0.0 and np.max(np.abs(t[-1] - t7[-1])) <= 1e-15
+    assert np.max(np.abs(t[::2] - t7)) <= 1e-13   # 118 = 2 * 59: every second sample is a seed waypoint
+    assert np.max(np.abs(t[1::2] - 0.5 * (t7[:-1] + t7[1:]))) <= 1e-13
+    mod.destroy(run=h3)
+    mod.destroy(run=h)
+    for bad, text in ((dict(starttraj=xml, adofgoal=goal), "Cannot pass both adofgoal and starttraj!"),
+                      (dict(starttraj="<trajectory></trajectory>"), "joint_values"),
+                      (dict(starttraj=xml.replace('dof="7" interpolation="linear"', 'dof="6" interpolation="linear"')),
+                       "does not match")):
+        with pytest.raises(RuntimeError) as ei:
+            mod.create(robot=robot, **bad)
+        assert text in str(ei.value)
