@@ -33,7 +33,9 @@
  *     uniform deltatime; the LinearTrajectoryRetimer and the collision sweep
  *     (mod.cpp:2906-3006) are OpenRAVE's and are not reproduced -- the
  *     no_collision_* flags are accepted and have no effect;
- *   - floating_base, basegoal, starttraj, con_tsr, start_tsr, everyn_tsr,
+ *   - starttraj is read in the XML layout gettraj emits (joint_values + deltatime
+ *     groups) and sampled as mod.cpp:2375-2415 does;
+ *   - floating_base, basegoal, con_tsr, start_tsr, everyn_tsr,
  *     start_cost and trajs_fileformstr are recognised and rejected with an error
  *     (out of scope for the hot path); ee_force,
  *     ee_force_at and ee_torque_weights are accepted and ignored, as in the
