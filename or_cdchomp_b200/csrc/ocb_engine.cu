@@ -204,7 +204,23 @@ struct ocb_engine
    int smem_optin = 0;
    int sm_count = 0;
    int force_general_sdf = 0; /* test hook: always take the general fp64 distance transform */
+   /* every device buffer of batches, resident SDFs and host-call temporaries comes from this
+    * stream-ordered pool, which keeps what it is given back: create / destroy of a batch costs
+    * microseconds and never synchronises the device (cudaMalloc / cudaFree took 1 - 300 ms per
+    * batch in the end-to-end path) */
+   cudaMemPool_t pool = nullptr;
 };
+
+static cudaError_t pool_alloc(ocb_engine *e, void **p, size_t bytes)
+{
+   *p = nullptr;
+   return cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 1), e->pool, e->stream);
+}
+
+static void pool_free(ocb_engine *e, void *p)
+{
+   if (p) cudaFreeAsync(p, e->stream);
+}
 
 static int engine_scratch(ocb_engine *e, size_t bytes)
 {
@@ -251,6 +267,20 @@ extern "C" int ocb_engine_create(int device, ocb_engine **out)
       return fail(OCB_ERR_CUDA, "cudaStreamCreate failed");
    }
    e->stream = e->own_stream;
+   cudaMemPoolProps pp;
+   memset(&pp, 0, sizeof(pp));
+   pp.allocType = cudaMemAllocationTypePinned;
+   pp.handleTypes = cudaMemHandleTypeNone;
+   pp.location.type = cudaMemLocationTypeDevice;
+   pp.location.id = device;
+   if (cudaMemPoolCreate(&e->pool, &pp) != cudaSuccess)
+   {
+      cudaStreamDestroy(e->own_stream);
+      delete e;
+      return fail(OCB_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+   }
+   unsigned long long keep = ~0ull; /* never hand memory back to the driver between batches */
+   cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep);
    *out = e;
    return OCB_OK;
 }
@@ -261,8 +291,10 @@ extern "C" int ocb_engine_destroy(ocb_engine *e)
    cudaSetDevice(e->device);
    cudaStreamSynchronize(e->stream);
    for (auto &s : e->sdfs)
-      if (s.used && s.owned) cudaFree(s.d_data);
+      if (s.used && s.owned) pool_free(e, s.d_data);
    if (e->scratch) cudaFree(e->scratch);
+   cudaStreamSynchronize(e->stream);
+   if (e->pool) cudaMemPoolDestroy(e->pool);
    if (e->own_stream) cudaStreamDestroy(e->own_stream);
    delete e;
    return OCB_OK;
@@ -321,16 +353,16 @@ extern "C" int ocb_sdf_upload(ocb_engine *e, const ocb_sdf *sdf, int *id)
    CU(cudaSetDevice(e->device));
    const size_t cells = (size_t) sdf->sizes[0] * sdf->sizes[1] * sdf->sizes[2];
    double *d = nullptr;
-   if (cudaMalloc((void **) &d, cells * sizeof(double)) != cudaSuccess)
+   if (pool_alloc(e, (void **) &d, cells * sizeof(double)) != cudaSuccess)
    {
       cudaGetLastError();
-      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu SDF bytes failed", cells * sizeof(double));
+      return fail(OCB_ERR_ALLOC, "device allocation of %zu SDF bytes failed", cells * sizeof(double));
    }
    cudaError_t err = cudaMemcpyAsync(d, sdf->data, cells * sizeof(double), cudaMemcpyHostToDevice, e->stream);
    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
    if (err != cudaSuccess)
    {
-      cudaFree(d);
+      pool_free(e, d);
       return fail(OCB_ERR_CUDA, "SDF upload: %s", cudaGetErrorString(err));
    }
    const int slot = sdf_slot_new(e);
@@ -366,7 +398,7 @@ extern "C" int ocb_sdf_remove(ocb_engine *e, int id)
    if (!e || id < 0 || id >= (int) e->sdfs.size() || !e->sdfs[id].used) return fail(OCB_ERR_ARG, "bad sdf id %d", id);
    CU(cudaSetDevice(e->device));
    CU(cudaStreamSynchronize(e->stream));
-   if (e->sdfs[id].owned) cudaFree(e->sdfs[id].d_data);
+   if (e->sdfs[id].owned) pool_free(e, e->sdfs[id].d_data);
    e->sdfs[id] = SdfSlot();
    return OCB_OK;
 }
@@ -415,11 +447,11 @@ extern "C" int ocb_sdf_build_host(ocb_engine *e, const double *obs, const int si
    CU(cudaSetDevice(e->device));
    const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
    double *d_in = nullptr, *d_out = nullptr;
-   if (cudaMalloc((void **) &d_in, bytes) != cudaSuccess || cudaMalloc((void **) &d_out, bytes) != cudaSuccess)
+   if (pool_alloc(e, (void **) &d_in, bytes) != cudaSuccess || pool_alloc(e, (void **) &d_out, bytes) != cudaSuccess)
    {
       cudaGetLastError();
-      cudaFree(d_in);
-      return fail(OCB_ERR_ALLOC, "cudaMalloc of 2 x %zu bytes failed", bytes);
+      pool_free(e, d_in);
+      return fail(OCB_ERR_ALLOC, "device allocation of 2 x %zu bytes failed", bytes);
    }
    cudaError_t err = cudaMemcpyAsync(d_in, obs, bytes, cudaMemcpyHostToDevice, e->stream);
    if (err == cudaSuccess)
@@ -431,8 +463,8 @@ extern "C" int ocb_sdf_build_host(ocb_engine *e, const double *obs, const int si
          if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
       }
    }
-   cudaFree(d_in);
-   cudaFree(d_out);
+   pool_free(e, d_in);
+   pool_free(e, d_out);
    if (rc) return rc;
    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "sdf_build_host: %s", cudaGetErrorString(err));
    return OCB_OK;
@@ -447,11 +479,11 @@ extern "C" int ocb_dt_sqeuc_host(ocb_engine *e, const double *func, const int si
    CU(cudaSetDevice(e->device));
    const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
    double *d_in = nullptr, *d_out = nullptr;
-   if (cudaMalloc((void **) &d_in, bytes) != cudaSuccess || cudaMalloc((void **) &d_out, bytes) != cudaSuccess)
+   if (pool_alloc(e, (void **) &d_in, bytes) != cudaSuccess || pool_alloc(e, (void **) &d_out, bytes) != cudaSuccess)
    {
       cudaGetLastError();
-      cudaFree(d_in);
-      return fail(OCB_ERR_ALLOC, "cudaMalloc of 2 x %zu bytes failed", bytes);
+      pool_free(e, d_in);
+      return fail(OCB_ERR_ALLOC, "device allocation of 2 x %zu bytes failed", bytes);
    }
    cudaError_t err = cudaMemcpyAsync(d_in, func, bytes, cudaMemcpyHostToDevice, e->stream);
    if (err == cudaSuccess)
@@ -463,8 +495,8 @@ extern "C" int ocb_dt_sqeuc_host(ocb_engine *e, const double *func, const int si
          if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
       }
    }
-   cudaFree(d_in);
-   cudaFree(d_out);
+   pool_free(e, d_in);
+   pool_free(e, d_out);
    if (rc) return rc;
    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "dt_sqeuc_host: %s", cudaGetErrorString(err));
    return OCB_OK;
@@ -533,10 +565,10 @@ extern "C" int ocb_flood_relabel_host(ocb_engine *e, double *grid, const int siz
    CU(cudaSetDevice(e->device));
    const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
    double *d = nullptr;
-   if (cudaMalloc((void **) &d, bytes) != cudaSuccess)
+   if (pool_alloc(e, (void **) &d, bytes) != cudaSuccess)
    {
       cudaGetLastError();
-      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu bytes failed", bytes);
+      return fail(OCB_ERR_ALLOC, "device allocation of %zu bytes failed", bytes);
    }
    int rc = OCB_OK;
    cudaError_t err = cudaMemcpyAsync(d, grid, bytes, cudaMemcpyHostToDevice, e->stream);
@@ -549,7 +581,7 @@ extern "C" int ocb_flood_relabel_host(ocb_engine *e, double *grid, const int siz
          if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
       }
    }
-   cudaFree(d);
+   pool_free(e, d);
    if (rc) return rc;
    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "flood_relabel_host: %s", cudaGetErrorString(err));
    return OCB_OK;
@@ -565,11 +597,11 @@ extern "C" int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prim
    CU(cudaSetDevice(e->device));
    const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
    double *d_obs = nullptr, *d_sdf = nullptr;
-   if (cudaMalloc((void **) &d_obs, bytes) != cudaSuccess || cudaMalloc((void **) &d_sdf, bytes) != cudaSuccess)
+   if (pool_alloc(e, (void **) &d_obs, bytes) != cudaSuccess || pool_alloc(e, (void **) &d_sdf, bytes) != cudaSuccess)
    {
       cudaGetLastError();
-      cudaFree(d_obs);
-      return fail(OCB_ERR_ALLOC, "cudaMalloc of 2 x %zu bytes failed", bytes);
+      pool_free(e, d_obs);
+      return fail(OCB_ERR_ALLOC, "device allocation of 2 x %zu bytes failed", bytes);
    }
    rc = ocb_occupancy_device(e, prims, n_prims, sizes, lengths, cube_extent, d_obs);
    if (rc == OCB_OK) rc = ocb_flood_relabel_device(e, d_obs, sizes, 0);
@@ -581,8 +613,8 @@ extern "C" int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prim
       if (rc == OCB_OK) err = cudaMemcpyAsync(sdf_out, d_sdf, bytes, cudaMemcpyDeviceToHost, e->stream);
    }
    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-   cudaFree(d_obs);
-   cudaFree(d_sdf);
+   pool_free(e, d_obs);
+   pool_free(e, d_sdf);
    if (rc) return rc;
    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "computedistancefield_host: %s", cudaGetErrorString(err));
    return OCB_OK;
@@ -935,10 +967,10 @@ template <class T>
 static int batch_alloc(ocb_batch *b, T **ptr, size_t count)
 {
    *ptr = nullptr;
-   if (cudaMalloc((void **) ptr, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess)
+   if (pool_alloc(b->e, (void **) ptr, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess)
    {
       cudaGetLastError();
-      return fail(OCB_ERR_ALLOC, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+      return fail(OCB_ERR_ALLOC, "device allocation of %zu bytes failed", count * sizeof(T));
    }
    b->owned.push_back(*ptr);
    return OCB_OK;
@@ -961,7 +993,7 @@ extern "C" int ocb_batch_destroy(ocb_batch *b)
    if (!b) return OCB_OK;
    cudaSetDevice(b->e->device);
    cudaStreamSynchronize(b->e->stream);
-   for (void *p : b->owned) cudaFree(p);
+   for (void *p : b->owned) pool_free(b->e, p);
    delete b;
    return OCB_OK;
 }
