@@ -180,6 +180,20 @@ int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prims, int n_pr
                                   const int sizes[3], const double lengths[3],
                                   double cube_extent, double *obs_out, double *sdf_out);
 
+/* Device-resident variants: the field is built in HBM and stays there as SDF `*id` (no host
+ * round trip); ocb_sdf_build_resident is cd_grid_double_bin_sdf of a host obstacle array
+ * (addfield_fromobsarray, mod.cpp:592-722).  ocb_sdf_download copies a resident field out
+ * (cache files, mod.cpp:571-580).  ocb_sdf_alias makes a second id over the SAME grid with
+ * another world pose -- the per-run snapshot of a rooted field's pose (mod.cpp:2347-2369)
+ * without copying the grid; remove aliases before the field they point at. */
+int ocb_computedistancefield_resident(ocb_engine *e, const ocb_prim *prims, int n_prims,
+                                      const int sizes[3], const double lengths[3], double cube_extent,
+                                      const double pose_world_gsdf[7], int *id);
+int ocb_sdf_build_resident(ocb_engine *e, const double *obs, const int sizes[3], const double lengths[3],
+                           const double pose_world_gsdf[7], int *id);
+int ocb_sdf_download(ocb_engine *e, int id, double *out);
+int ocb_sdf_alias(ocb_engine *e, int id, const double pose_world_gsdf[7], int *alias_id);
+
 /* --- batched CHOMP runs (replaces struct run + cd_chomp, mod.cpp:887-966) ---- */
 /* R independent runs sharing robot, parameters and SDF set.  q_start/q_goal are
  * [R][n_dof]; seeds [R] (gsl_rng_set seed, mod.cpp:2303-2304; may be NULL = 0).

@@ -257,6 +257,11 @@ EXPORTS = {
     "ocb_flood_relabel_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int_p, C.c_size_t]),
     "ocb_flood_relabel_host": (C.c_int, [C.c_void_p, c_double_p, c_int_p, C.c_size_t]),
     "ocb_computedistancefield_host": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p, C.c_double, c_double_p, c_double_p]),
+    "ocb_computedistancefield_resident": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p,
+                                                    C.c_double, c_double_p, c_int_p]),
+    "ocb_sdf_build_resident": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, c_double_p, c_int_p]),
+    "ocb_sdf_download": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "ocb_sdf_alias": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p]),
     "ocb_batch_create": (C.c_int, [C.c_void_p, C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_int, c_int_p, C.c_int, c_double_p, c_double_p, c_uint_p, C.POINTER(C.c_void_p)]),
     "ocb_batch_reset": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_uint_p]),
     "ocb_batch_set_traj": (C.c_int, [C.c_void_p, c_double_p]),

@@ -620,6 +620,95 @@ extern "C" int ocb_computedistancefield_host(ocb_engine *e, const ocb_prim *prim
    return OCB_OK;
 }
 
+/* ---- fields that never leave the device ------------------------------------------------- */
+static int sdf_slot_own(ocb_engine *e, double *d, const int sizes[3], const double lengths[3],
+                        const double pose[7], bool owned, int *id)
+{
+   const int slot = sdf_slot_new(e);
+   SdfSlot &s = e->sdfs[slot];
+   s.used = true;
+   s.owned = owned;
+   s.d_data = d;
+   for (int i = 0; i < 3; i++) { s.sizes[i] = sizes[i]; s.lengths[i] = lengths[i]; }
+   memcpy(s.pose, pose, sizeof(s.pose));
+   *id = slot;
+   return OCB_OK;
+}
+
+extern "C" int ocb_computedistancefield_resident(ocb_engine *e, const ocb_prim *prims, int n_prims,
+                                                 const int sizes[3], const double lengths[3], double cube_extent,
+                                                 const double pose_world_gsdf[7], int *id)
+{
+   if (!e || !id || !pose_world_gsdf) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
+   double *d_obs = nullptr, *d_sdf = nullptr;
+   if (pool_alloc(e, (void **) &d_obs, bytes) != cudaSuccess || pool_alloc(e, (void **) &d_sdf, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      pool_free(e, d_obs);
+      return fail(OCB_ERR_ALLOC, "device allocation of 2 x %zu bytes failed", bytes);
+   }
+   rc = ocb_occupancy_device(e, prims, n_prims, sizes, lengths, cube_extent, d_obs);
+   if (rc == OCB_OK) rc = ocb_flood_relabel_device(e, d_obs, sizes, 0);
+   if (rc == OCB_OK) rc = ocb_sdf_build_device(e, d_obs, sizes, lengths, d_sdf);
+   pool_free(e, d_obs);
+   if (rc)
+   {
+      pool_free(e, d_sdf);
+      return rc;
+   }
+   return sdf_slot_own(e, d_sdf, sizes, lengths, pose_world_gsdf, true, id);
+}
+
+extern "C" int ocb_sdf_build_resident(ocb_engine *e, const double *obs, const int sizes[3], const double lengths[3],
+                                      const double pose_world_gsdf[7], int *id)
+{
+   if (!e || !obs || !id || !pose_world_gsdf) return fail(OCB_ERR_ARG, "null argument");
+   int rc = check_grid(sizes, lengths);
+   if (rc) return rc;
+   CU(cudaSetDevice(e->device));
+   const size_t bytes = (size_t) sizes[0] * sizes[1] * sizes[2] * sizeof(double);
+   double *d_obs = nullptr, *d_sdf = nullptr;
+   if (pool_alloc(e, (void **) &d_obs, bytes) != cudaSuccess || pool_alloc(e, (void **) &d_sdf, bytes) != cudaSuccess)
+   {
+      cudaGetLastError();
+      pool_free(e, d_obs);
+      return fail(OCB_ERR_ALLOC, "device allocation of 2 x %zu bytes failed", bytes);
+   }
+   cudaError_t err = cudaMemcpyAsync(d_obs, obs, bytes, cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess) rc = ocb_sdf_build_device(e, d_obs, sizes, lengths, d_sdf);
+   if (err == cudaSuccess && rc == OCB_OK) err = cudaStreamSynchronize(e->stream); /* obs is the caller's */
+   pool_free(e, d_obs);
+   if (rc || err != cudaSuccess)
+   {
+      pool_free(e, d_sdf);
+      return rc ? rc : fail(OCB_ERR_CUDA, "sdf_build_resident: %s", cudaGetErrorString(err));
+   }
+   return sdf_slot_own(e, d_sdf, sizes, lengths, pose_world_gsdf, true, id);
+}
+
+extern "C" int ocb_sdf_download(ocb_engine *e, int id, double *out)
+{
+   if (!e || !out || id < 0 || id >= (int) e->sdfs.size() || !e->sdfs[id].used) return fail(OCB_ERR_ARG, "bad sdf id %d", id);
+   CU(cudaSetDevice(e->device));
+   const SdfSlot &s = e->sdfs[id];
+   const size_t bytes = (size_t) s.sizes[0] * s.sizes[1] * s.sizes[2] * sizeof(double);
+   CU(cudaMemcpyAsync(out, s.d_data, bytes, cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_sdf_alias(ocb_engine *e, int id, const double pose_world_gsdf[7], int *alias_id)
+{
+   if (!e || !alias_id || !pose_world_gsdf || id < 0 || id >= (int) e->sdfs.size() || !e->sdfs[id].used)
+      return fail(OCB_ERR_ARG, "bad sdf id %d", id);
+   const SdfSlot src = e->sdfs[id]; /* copy: sdf_slot_new may grow the table */
+   return sdf_slot_own(e, src.d_data, src.sizes, src.lengths, pose_world_gsdf, false, alias_id);
+}
+
 /* -------------------------------------------------------------------- batch */
 struct ocb_batch
 {

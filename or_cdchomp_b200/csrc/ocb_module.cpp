@@ -217,7 +217,7 @@ struct Field
    double pose[7]; /* grid frame in the kinbody frame */
    int sizes[3];
    double lengths[3];
-   std::vector<double> data; /* host copy (cache file, viewfields) */
+   int sdf_id = -1; /* the grid, resident in HBM (engine SDF slot); runs alias it with their own pose */
 };
 
 /* struct run of the reference (mod.cpp:887-966), R runs behind one handle */
@@ -244,9 +244,11 @@ struct ocb_module
       for (Run *r : runs)
       {
          ocb_batch_destroy(r->batch);
+         for (int s : r->sdf_ids) ocb_sdf_remove(engine, s);
          if (r->fp_dat) fclose(r->fp_dat);
          delete r;
       }
+      for (const Field &f : sdfs) ocb_sdf_remove(engine, f.sdf_id);
       if (engine) ocb_engine_destroy(engine);
    }
 
@@ -392,7 +394,8 @@ struct ocb_module
       pose_identity(f.pose);
       for (int k = 0; k < 3; k++) f.pose[k] = aabb_pos[k] - 0.5 * f.lengths[k]; /* mod.cpp:407-409 */
       const size_t ncells = (size_t) f.sizes[0] * f.sizes[1] * f.sizes[2];
-      f.data.resize(ncells);
+      /* the grid lives in HBM; a host copy exists only while a cache file is read or written */
+      std::vector<double> host;
 
       bool loaded = false;
       if (!cache_filename.empty())
@@ -405,9 +408,18 @@ struct ocb_module
             if ((size_t) ftell(fp) == ncells * sizeof(double))
             {
                fseek(fp, 0L, SEEK_SET);
-               loaded = fread(f.data.data(), sizeof(double), ncells, fp) == ncells;
+               host.resize(ncells);
+               loaded = fread(host.data(), sizeof(double), ncells, fp) == ncells;
             }
             fclose(fp);
+         }
+         if (loaded)
+         {
+            ocb_sdf d;
+            for (int k = 0; k < 3; k++) { d.sizes[k] = f.sizes[k]; d.lengths[k] = f.lengths[k]; }
+            memcpy(d.pose_world_gsdf, f.pose, sizeof(f.pose));
+            d.data = host.data();
+            if (ocb_sdf_upload(engine, &d, &f.sdf_id) != OCB_OK) fail_engine("Not enough memory for distance field!");
          }
       }
       if (!loaded)
@@ -425,15 +437,16 @@ struct ocb_module
             pose_compose(gsdf_world, kv.second.pose, rel);
             for (const ocb_prim &p : kv.second.prims) prims.push_back(prim_transform(rel, p));
          }
-         if (ocb_computedistancefield_host(engine, prims.data(), (int) prims.size(), f.sizes, f.lengths, cube_extent,
-                                           nullptr, f.data.data()) != OCB_OK)
+         if (ocb_computedistancefield_resident(engine, prims.data(), (int) prims.size(), f.sizes, f.lengths, cube_extent,
+                                               f.pose, &f.sdf_id) != OCB_OK)
             fail_engine("Not enough memory for distance field!");
          if (!cache_filename.empty())
          {
             FILE *fp = fopen(cache_filename.c_str(), "wb"); /* mod.cpp:571-580 */
             if (fp)
             {
-               fwrite(f.data.data(), sizeof(double), ncells, fp);
+               host.resize(ncells);
+               if (ocb_sdf_download(engine, f.sdf_id, host.data()) == OCB_OK) fwrite(host.data(), sizeof(double), ncells, fp);
                fclose(fp);
             }
          }
@@ -504,8 +517,7 @@ struct ocb_module
       f.kinbody_name = name;
       memcpy(f.pose, pose, sizeof(pose));
       for (int k = 0; k < 3; k++) { f.sizes[k] = sizes[k]; f.lengths[k] = lengths[k]; }
-      f.data.resize((size_t) sizes[0] * sizes[1] * sizes[2]);
-      const int rc = ocb_sdf_build_host(engine, obsarray, sizes, lengths, f.data.data());
+      const int rc = ocb_sdf_build_resident(engine, obsarray, sizes, lengths, f.pose, &f.sdf_id);
       free(obsarray); /* the reference frees it through cd_grid_destroy (mod.cpp:703-704, 714) */
       if (rc != OCB_OK) fail_engine("Not enough memory for distance field!");
       sdfs.push_back(std::move(f));
@@ -534,6 +546,9 @@ struct ocb_module
       for (size_t k = 0; k < sdfs.size(); k++)
          if (sdfs[k].kinbody_name == name)
          {
+            /* runs created earlier hold aliases of this grid: they must be destroyed first, as the
+             * reference's runs hold raw grid pointers (mod.cpp:2347-2369, 836) */
+            ocb_sdf_remove(engine, sdfs[k].sdf_id);
             sdfs.erase(sdfs.begin() + k);
             return 0;
          }
@@ -713,12 +728,10 @@ struct ocb_module
          auto it = env->kinbodies.find(f.kinbody_name);
          if (it == env->kinbodies.end())
             throw module_error("KinBody " + f.kinbody_name + " referenced by active signed distance field does not exist!");
-         ocb_sdf d;
-         for (int k = 0; k < 3; k++) { d.sizes[k] = f.sizes[k]; d.lengths[k] = f.lengths[k]; }
-         pose_compose(it->second.pose, f.pose, d.pose_world_gsdf);
-         d.data = f.data.data();
+         double pose_world_gsdf[7];
+         pose_compose(it->second.pose, f.pose, pose_world_gsdf);
          int id = -1;
-         if (ocb_sdf_upload(engine, &d, &id) != OCB_OK)
+         if (ocb_sdf_alias(engine, f.sdf_id, pose_world_gsdf, &id) != OCB_OK)
          {
             for (int s : r->sdf_ids) ocb_sdf_remove(engine, s);
             fail_engine("error creating chomp instance!");

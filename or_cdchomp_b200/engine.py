@@ -90,6 +90,35 @@ class Engine:
             dptr(sdf) if want_sdf else None), "ocb_computedistancefield_host")
         return obs, sdf
 
+    def computedistancefield_resident(self, prims, sizes, lengths, cube_extent, pose_world_gsdf):
+        """the same pipeline, but the field stays in HBM: returns its SDF id"""
+        arr = capi.make_prims(prims)
+        sid = C.c_int()
+        pose = as_f64(pose_world_gsdf)
+        check(self.lib, self.lib.ocb_computedistancefield_resident(
+            self.h, arr, len(prims), _i3(sizes), _d3(lengths), float(cube_extent), dptr(pose), C.byref(sid)),
+            "ocb_computedistancefield_resident")
+        return sid.value
+
+    def sdf_build_resident(self, obs, lengths, pose_world_gsdf):
+        obs = as_f64(obs)
+        sid = C.c_int()
+        pose = as_f64(pose_world_gsdf)
+        check(self.lib, self.lib.ocb_sdf_build_resident(self.h, dptr(obs), _i3(obs.shape), _d3(lengths), dptr(pose),
+                                                       C.byref(sid)), "ocb_sdf_build_resident")
+        return sid.value
+
+    def download_sdf(self, sid, shape):
+        out = np.empty(tuple(int(x) for x in shape))
+        check(self.lib, self.lib.ocb_sdf_download(self.h, int(sid), dptr(out)), "ocb_sdf_download")
+        return out
+
+    def alias_sdf(self, sid, pose_world_gsdf):
+        out = C.c_int()
+        pose = as_f64(pose_world_gsdf)
+        check(self.lib, self.lib.ocb_sdf_alias(self.h, int(sid), dptr(pose), C.byref(out)), "ocb_sdf_alias")
+        return out.value
+
     # -- batches -----------------------------------------------------------
     def create_batch(self, robot, params, sdf_ids, q_start, q_goal, seeds=None):
         return Batch(self, robot, params, sdf_ids, q_start, q_goal, seeds)

@@ -258,3 +258,30 @@ def test_libcd_named_entry_points(oracle, flavour):
     with pytest.raises(libcd.LibcdError) as ei:
         libcd.bin_sdf(np.zeros((4, 4)), [1, 1])
     assert ei.value.code == -2
+
+
+def test_resident_fields_and_pose_aliases(engine, wam7, table):
+    """fields built without a host round trip (ocb_computedistancefield_resident,
+    ocb_sdf_build_resident) hold the same values as the host variants; an alias of a resident
+    grid with another pose behaves like an upload of the grid with that pose."""
+    sizes, lengths, gprims = table["sizes"], table["lengths"], table["gprims"]
+    obs, sdf = engine.computedistancefield(gprims, sizes, lengths, 0.02)
+    sid = engine.computedistancefield_resident(gprims, sizes, lengths, 0.02, table["pose_world"])
+    assert np.array_equal(engine.download_sdf(sid, sizes), sdf)
+    sid2 = engine.sdf_build_resident(obs, lengths, table["pose_world"])
+    assert np.array_equal(engine.download_sdf(sid2, sizes), sdf)
+    other = models.pose_compose(models.pose_make((0.1, -0.05, 0.02), models.quat_from_axis_angle((0, 0, 1), 0.3)),
+                                table["pose_world"])
+    alias = engine.alias_sdf(sid, other)
+    up = engine.upload_sdf(capi.SdfDesc(sdf, lengths, other))
+    params = capi.default_params(n_points=40, lambda_=100.0, obs_factor=400.0)
+    starts, goals = models.random_endpoints(wam7, 3, seed0=5, shrink=0.3)
+    res = []
+    for s in (alias, up):
+        b = engine.create_batch(wam7, params, [s], starts, goals)
+        b.iterate(6)
+        res.append(b.get_traj())
+        b.close()
+    assert np.array_equal(res[0], res[1])
+    for s in (alias, up, sid2, sid):
+        engine.remove_sdf(s)
