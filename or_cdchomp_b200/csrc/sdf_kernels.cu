@@ -348,52 +348,164 @@ rasterize_kernel(const PrimDev *__restrict__ prims, int sx, int sy, int sz,
 }
 
 /* --------------------------------------------------------------- flood fill */
-/* state: 0 = not fillable, 1 = fillable (cell == 1.0), 2 = filled */
-__global__ void flood_init_kernel(const double *__restrict__ grid, unsigned char *__restrict__ st,
-                                  size_t n, size_t start)
+/* cd_grid_flood_fill(g, start, no wrap, replace_1_to_0) + relabel (grid_flood.c:30-111,
+ * mod.cpp:143-151, 536-548) on bit masks.  32 consecutive z cells share one word of
+ *   open[(x NY + y) NZW + w]    the cell holds exactly 1.0 (it conducts the fill)
+ *   fill[...]                   the fill has reached the cell
+ * The fill spreads by whole-line sweeps: inside a word through the carry chain of an integer
+ * add, across words and along x / y by one AND + OR per 32 cells.  Both masks of a 400^3 grid
+ * are 8 MB each and stay in L2, so a round of three sweeps costs tens of microseconds; rounds
+ * repeat until nothing changes (6-connected reachability, independent of the sweep order). */
+
+/* all open bits connected, inside the word, to a seed bit (seeds must be open) */
+__device__ __forceinline__ unsigned ripple(unsigned open, unsigned seeds)
 {
-   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+   const unsigned up = (((open + seeds) ^ open) & open) | seeds;
+   const unsigned ro = __brev(open), rs = __brev(seeds);
+   const unsigned down = __brev((((ro + rs) ^ ro) & ro) | rs);
+   return up | down;
+}
+
+/* one warp per z line: 32 cells -> one word by ballot */
+__global__ void __launch_bounds__(256)
+flood_pack_kernel(const double *__restrict__ grid, unsigned *__restrict__ open, unsigned *__restrict__ fill,
+                  size_t nlines, int nz, int nzw, size_t start)
+{
+   const int lane = threadIdx.x & 31;
+   const size_t warp = (blockIdx.x * (size_t) blockDim.x + threadIdx.x) >> 5;
+   const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+   for (size_t line = warp; line < nlines; line += nwarps)
    {
-      unsigned char s = (grid[i] == 1.0) ? 1 : 0;
-      if (i == start && s == 1) s = 2;
-      st[i] = s;
+      const double *src = grid + line * (size_t) nz;
+      for (int w = 0; w < nzw; w++)
+      {
+         const int z = 32 * w + lane;
+         const bool is_open = (z < nz) && (src[z] == 1.0);
+         const unsigned m = __ballot_sync(0xffffffffu, is_open);
+         if (lane == 0)
+         {
+            unsigned f = 0;
+            const size_t first = line * (size_t) nz + 32 * (size_t) w;
+            if (start >= first && start < first + 32) f = (1u << (unsigned) (start - first)) & m;
+            open[line * nzw + w] = m;
+            fill[line * nzw + w] = f;
+         }
+      }
    }
 }
 
-/* propagate "filled" along whole lines of one axis, both directions */
+/* along z: one thread per (x, y) line, carry between its words */
 __global__ void __launch_bounds__(128)
-flood_sweep_kernel(unsigned char *st, int len, size_t stride, size_t inner, size_t nlines, int *changed)
+flood_z_kernel(const unsigned *__restrict__ open, unsigned *__restrict__ fill, size_t nlines, int nzw, int *changed)
 {
    const size_t line = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
    if (line >= nlines) return;
-   const size_t o = line / inner, i = line % inner;
-   unsigned char *base = st + o * inner * (size_t) len + i;
+   const unsigned *o = open + line * nzw;
+   unsigned *f = fill + line * nzw;
    bool any = false;
-   unsigned char prev = 0;
-   for (int q = 0; q < len; q++)
+   unsigned carry = 0;
+   for (int w = 0; w < nzw; w++)
    {
-      unsigned char s = base[(size_t) q * stride];
-      if (s == 1 && prev == 2) { s = 2; base[(size_t) q * stride] = 2; any = true; }
-      prev = s;
+      const unsigned m = o[w], old = f[w];
+      const unsigned now = ripple(m, (old | carry) & m);
+      if (now != old) { f[w] = now; any = true; }
+      carry = now >> 31;
    }
-   prev = 0;
-   for (int q = len - 1; q >= 0; q--)
+   carry = 0;
+   for (int w = nzw - 1; w >= 0; w--)
    {
-      unsigned char s = base[(size_t) q * stride];
-      if (s == 1 && prev == 2) { s = 2; base[(size_t) q * stride] = 2; any = true; }
-      prev = s;
+      const unsigned m = o[w], old = f[w];
+      const unsigned now = ripple(m, (old | carry) & m);
+      if (now != old) { f[w] = now; any = true; }
+      carry = (now & 1u) << 31;
    }
    if (any) *changed = 1;
 }
 
-/* filled -> 0.0 (replace_1_to_0, mod.cpp:143-151); still 1.0 -> HUGE_VAL (mod.cpp:546-548) */
-__global__ void flood_finish_kernel(double *__restrict__ grid, const unsigned char *__restrict__ st, size_t n)
+/* along x or y: one thread per (other axis, word); `len` steps of `stride` words, there and back */
+__global__ void __launch_bounds__(128)
+flood_xy_kernel(const unsigned *__restrict__ open, unsigned *__restrict__ fill, int len, size_t stride,
+                size_t outer_stride, int n_outer, int nzw, int *changed)
 {
-   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+   const size_t id = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+   if (id >= (size_t) n_outer * nzw) return;
+   const size_t base = (id / nzw) * outer_stride + (id % nzw);
+   bool any = false;
+   /* a thread owns its words for the whole launch, so a batch of them can be fetched ahead of the
+    * serial dependency (only ~5 k threads exist: the loads must overlap inside the thread) */
+   constexpr int B = 16;
+   unsigned prev = 0;
+   for (int q0 = 0; q0 < len; q0 += B)
    {
-      const unsigned char s = st[i];
-      if (s == 2) grid[i] = 0.0;
-      else if (s == 1) grid[i] = HUGE_VAL;
+      unsigned m[B], old[B];
+#pragma unroll
+      for (int k = 0; k < B; k++)
+      {
+         const int q = min(q0 + k, len - 1);
+         m[k] = open[base + (size_t) q * stride];
+         old[k] = fill[base + (size_t) q * stride];
+      }
+#pragma unroll
+      for (int k = 0; k < B; k++)
+      {
+         if (q0 + k >= len) break;
+         unsigned now = old[k];
+         const unsigned in = prev & m[k] & ~now;
+         if (in)
+         {
+            now = ripple(m[k], (now | in) & m[k]);
+            fill[base + (size_t) (q0 + k) * stride] = now;
+            any = true;
+         }
+         prev = now;
+      }
+   }
+   prev = 0;
+   for (int q0 = len - 1; q0 >= 0; q0 -= B)
+   {
+      unsigned m[B], old[B];
+#pragma unroll
+      for (int k = 0; k < B; k++)
+      {
+         const int q = max(q0 - k, 0);
+         m[k] = open[base + (size_t) q * stride];
+         old[k] = fill[base + (size_t) q * stride];
+      }
+#pragma unroll
+      for (int k = 0; k < B; k++)
+      {
+         if (q0 - k < 0) break;
+         unsigned now = old[k];
+         const unsigned in = prev & m[k] & ~now;
+         if (in)
+         {
+            now = ripple(m[k], (now | in) & m[k]);
+            fill[base + (size_t) (q0 - k) * stride] = now;
+            any = true;
+         }
+         prev = now;
+      }
+   }
+   if (any) *changed = 1;
+}
+
+/* reached -> 0.0 (replace_1_to_0, mod.cpp:143-151); open but not reached -> HUGE_VAL (mod.cpp:546-548) */
+__global__ void __launch_bounds__(256)
+flood_unpack_kernel(double *__restrict__ grid, const unsigned *__restrict__ open, const unsigned *__restrict__ fill,
+                    size_t nlines, int nz, int nzw)
+{
+   const int lane = threadIdx.x & 31;
+   const size_t warp = (blockIdx.x * (size_t) blockDim.x + threadIdx.x) >> 5;
+   const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+   for (size_t line = warp; line < nlines; line += nwarps)
+   {
+      double *dst = grid + line * (size_t) nz;
+      for (int w = 0; w < nzw; w++)
+      {
+         const unsigned m = open[line * nzw + w], f = fill[line * nzw + w];
+         const int z = 32 * w + lane;
+         if (z < nz && ((m >> lane) & 1u)) dst[z] = ((f >> lane) & 1u) ? 0.0 : HUGE_VAL;
+      }
    }
 }
 
@@ -520,7 +632,8 @@ extern "C" cudaError_t ocb_launch_occupancy(const void *d_prims, int n_prims, co
 
 extern "C" size_t ocb_flood_scratch_bytes(const int sizes[3])
 {
-   return (size_t) sizes[0] * sizes[1] * sizes[2] + 256;
+   const size_t nzw = ((size_t) sizes[2] + 31) / 32;
+   return 256 + 2 * (size_t) sizes[0] * sizes[1] * nzw * sizeof(unsigned);
 }
 
 extern "C" cudaError_t ocb_launch_flood_relabel(double *d_grid, const int sizes[3], size_t index_start,
@@ -528,23 +641,25 @@ extern "C" cudaError_t ocb_launch_flood_relabel(double *d_grid, const int sizes[
                                                 long *launches)
 {
    if (scratch_bytes < ocb_flood_scratch_bytes(sizes)) return cudaErrorInvalidValue;
-   const size_t n = (size_t) sizes[0] * sizes[1] * sizes[2];
+   const int nx = sizes[0], ny = sizes[1], nz = sizes[2], nzw = (nz + 31) / 32;
+   const size_t nlines = (size_t) nx * ny, nwords = nlines * nzw;
    int *changed = (int *) scratch;
-   unsigned char *state = (unsigned char *) scratch + 256;
-   flood_init_kernel<<<grid_blocks(n, 256), 256, 0, st>>>(d_grid, state, n, index_start);
+   unsigned *open = (unsigned *) ((char *) scratch + 256);
+   unsigned *fill = open + nwords;
+   const int pack_blocks = grid_blocks(nlines * 32, 256);
+   flood_pack_kernel<<<pack_blocks, 256, 0, st>>>(d_grid, open, fill, nlines, nz, nzw, index_start);
    if (launches) (*launches)++;
    for (int round = 0; round < 100000; round++)
    {
       cudaError_t e = cudaMemsetAsync(changed, 0, sizeof(int), st);
       if (e != cudaSuccess) return e;
-      for (int d = 2; d >= 0; d--)
-      {
-         size_t stride = 1;
-         for (int d2 = d + 1; d2 < 3; d2++) stride *= (size_t) sizes[d2];
-         const size_t nlines = n / (size_t) sizes[d];
-         flood_sweep_kernel<<<(unsigned) ((nlines + 127) / 128), 128, 0, st>>>(state, sizes[d], stride, stride, nlines, changed);
-         if (launches) (*launches)++;
-      }
+      flood_z_kernel<<<(unsigned) ((nlines + 127) / 128), 128, 0, st>>>(open, fill, nlines, nzw, changed);
+      /* along y: lines indexed by (x, w), step nzw words;  along x: by (y, w), step ny * nzw words */
+      flood_xy_kernel<<<(unsigned) (((size_t) nx * nzw + 127) / 128), 128, 0, st>>>(open, fill, ny, (size_t) nzw,
+                                                                                   (size_t) ny * nzw, nx, nzw, changed);
+      flood_xy_kernel<<<(unsigned) (((size_t) ny * nzw + 127) / 128), 128, 0, st>>>(open, fill, nx, (size_t) ny * nzw,
+                                                                                   (size_t) nzw, ny, nzw, changed);
+      if (launches) (*launches) += 3;
       int h = 0;
       e = cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, st);
       if (e != cudaSuccess) return e;
@@ -552,7 +667,7 @@ extern "C" cudaError_t ocb_launch_flood_relabel(double *d_grid, const int sizes[
       if (e != cudaSuccess) return e;
       if (!h) break;
    }
-   flood_finish_kernel<<<grid_blocks(n, 256), 256, 0, st>>>(d_grid, state, n);
+   flood_unpack_kernel<<<pack_blocks, 256, 0, st>>>(d_grid, open, fill, nlines, nz, nzw);
    if (launches) (*launches)++;
    return cudaGetLastError();
 }
