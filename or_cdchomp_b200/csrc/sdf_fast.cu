@@ -135,13 +135,22 @@ __device__ __forceinline__ int dz2_nearest(uint32_t bits, int lane, int zbase, i
  * one column per line ([entry][line], so a warp whose lanes sit at similar depths touches
  * one or two sectors per access); entry = apex << 22 | height; the two top entries stay
  * in registers, so memory sees each parabola at most once on the way in and once out.
- * One thread per line: tens of thousands of lines in flight hide the serial latency. */
-template <class Load8, class Emit>
+ * One thread per line: tens of thousands of lines in flight hide the serial latency.
+ *
+ * ONLY_AT_POSITIVE (the free-cell field): the caller reads the result only where the input
+ * height is positive (obstacle cells; everywhere else the cell is its own nearest free cell).
+ * Then (a) a zero-height sample whose two neighbours are zero-height too can never be the
+ * nearest source of a cell outside its run of zeros -- the end of the run is closer -- so it
+ * is not pushed, and (b) emit is called only between the first and the last positive sample.
+ * With a few percent of obstacle cells this leaves a handful of envelope entries per line. */
+template <bool ONLY_AT_POSITIVE, class Load8, class Emit>
 __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ stack, size_t stride, Load8 load8, Emit emit)
 {
    int np = 0;
    int v1 = 0, g1 = 0; /* top entry    */
    int v0 = 0, g0 = 0; /* second entry */
+   int q_lo = len, q_hi = -1; /* samples whose result is wanted */
+   int g_prev = 1;            /* height left of the batch (nothing there: treated as non-zero) */
    for (int q0 = 0; q0 < len; q0 += 8)
    {
       int vals[8];
@@ -151,6 +160,19 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
       {
          const int q = q0 + kk;
          const int gq = vals[kk];
+         if (ONLY_AT_POSITIVE)
+         {
+            if (gq > 0 && q < len)
+            {
+               q_lo = min(q_lo, q);
+               q_hi = q;
+            }
+            /* interior of a run of zeros (the right neighbour of a batch's last sample is not
+             * known yet: it is kept, which is always safe) */
+            const bool interior = (gq == 0) && (g_prev == 0) && (kk < 7) && (vals[kk < 7 ? kk + 1 : 7] == 0);
+            g_prev = gq;
+            if (interior) continue;
+         }
          if (gq >= INF_I) continue;
          if (np == 0)
          {
@@ -183,11 +205,17 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
          np++;
       }
    }
+   if (!ONLY_AT_POSITIVE)
+   {
+      q_lo = 0;
+      q_hi = len - 1;
+   }
    if (np == 0)
    {
-      for (int q = 0; q < len; q++) emit(q, INF_I);
+      for (int q = q_lo; q <= q_hi; q++) emit(q, INF_I);
       return;
    }
+   if (q_lo > q_hi) return;
    /* spill the two register entries so the read-back is uniform */
    if (np >= 2) stack[(size_t) (np - 2) * stride] = ((uint32_t) v0 << 22) | (uint32_t) g0;
    stack[(size_t) (np - 1) * stride] = ((uint32_t) v1 << 22) | (uint32_t) g1;
@@ -201,7 +229,7 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
       e = stack[stride];
       vb = (int) (e >> 22); gb = (int) (e & 0x3fffffu);
    }
-   for (int q = 0; q < len; q++)
+   for (int q = q_lo; q <= q_hi; q++)
    {
       /* advance while the boundary between k and k+1 lies left of q:
        *   N / (2 (vb-va)) < q  <=>  N < 2 q (vb-va) */
@@ -271,7 +299,8 @@ edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums
       if (field == 0 && !is_obs) inter[((rowbase + y) * (size_t) nz) + z] = val;
       if (field == 1 && is_obs) inter[((rowbase + y) * (size_t) nz) + z] = -val;
    };
-   envelope_pass(ny, stack, nlines, load8, emit);
+   if (field == 0) envelope_pass<false>(ny, stack, nlines, load8, emit);
+   else envelope_pass<true>(ny, stack, nlines, load8, emit);
 }
 
 /* ---- pass 3: lower envelope along x, final sqrt and sign; one warp per (y, z-word) tile ---- */
@@ -314,7 +343,8 @@ edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, uint32_t *
       if (field == 0 && v > 0) sdf[x * slab + col] = d;   /* free cell: + distance to obstacles */
       if (field == 1 && v < 0) sdf[x * slab + col] = -d;  /* obstacle cell: - distance to free  */
    };
-   envelope_pass(nx, stack, nlines, load8, emit);
+   if (field == 0) envelope_pass<false>(nx, stack, nlines, load8, emit);
+   else envelope_pass<true>(nx, stack, nlines, load8, emit);
 }
 
 } /* namespace */
