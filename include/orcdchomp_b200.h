@@ -103,6 +103,11 @@ typedef struct ocb_params
    double epsilon_self;         /* default 0.04                                       */
    double obs_factor;           /* default 200                                        */
    double obs_factor_self;      /* default 10                                         */
+   int floating_base;           /* `floating_base` (mod.cpp:991-1021, 1050-1086, 2424-2443): every waypoint
+                                   starts with the base pose [x y z qx qy qz qw], n = 7 + robot->n_dof,
+                                   q_start / q_goal rows are that long, robot->base_pose is not used, all
+                                   spheres are active, pose columns of the Jacobian are scaled by 0.01,
+                                   quaternions are re-normalised after every iteration              */
 } ocb_params;
 
 void ocb_params_default(ocb_params *p);

@@ -73,6 +73,7 @@ class OcbParams(C.Structure):
         ("epsilon_self", C.c_double),
         ("obs_factor", C.c_double),
         ("obs_factor_self", C.c_double),
+        ("floating_base", C.c_int),
     ]
 
 

@@ -73,6 +73,7 @@ struct Tables
 
 /* forward kinematics of waypoint t: world positions of the active spheres.
  * Replaces SetActiveDOFValues + GetTransform()*pos (mod.cpp:1026-1038). */
+template <bool FLOAT>
 __device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables &tb,
                                             const double *__restrict__ Ts, double *__restrict__ ws, int t)
 {
@@ -85,7 +86,7 @@ __device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables 
    for (int j = 0; j < a.nj; j++)
    {
       const OcbJointDev &J = a.joints[j];
-      fk_step<true>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org);
+      fk_step<true, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
       for (int s = J.sph_begin; s < J.sph_end; s++)
       {
          const double px = tb.sph[s].pos[0], py = tb.sph[s].pos[1], pz = tb.sph[s].pos[2];
@@ -103,6 +104,7 @@ __device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables 
  * the wrench of the joint's subtree:  dC/dq_j = c0 * axis . (M - origin x F)  for a
  * revolute joint, c0 * axis . F for a prismatic one.  This is the product with the
  * CalculateJacobian columns (mod.cpp:1048, 1244, 1314) without storing them. */
+template <bool FLOAT>
 __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tables &tb,
                                                const double *__restrict__ Ts, double *__restrict__ ws,
                                                double *__restrict__ Gs, int t)
@@ -117,7 +119,7 @@ __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tabl
    for (int j = 0; j < a.nj; j++)
    {
       const OcbJointDev &J = a.joints[j];
-      fk_step<false>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org);
+      fk_step<false, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
       double F0 = 0.0, F1 = 0.0, F2 = 0.0, M0 = 0.0, M1 = 0.0, M2 = 0.0;
       for (int di = J.desc_begin; di < J.desc_end; di++)
       {
@@ -137,6 +139,18 @@ __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tabl
          val = ax[0] * F0 + ax[1] * F1 + ax[2] * F2;
       Gs[J.dof * Pp + t] = fma(J.c0, val, Gs[J.dof * Pp + t]);
    }
+   if (FLOAT)
+   {
+      /* the base pose sees the total wrench of the waypoint */
+      double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
+      for (int g = 0; g < a.ng; g++)
+      {
+         const double *Wo = Wg + 6 * g * Pp;
+         F[0] += Wo[0]; F[1] += Wo[Pp]; F[2] += Wo[2 * Pp];
+         M[0] += Wo[3 * Pp]; M[1] += Wo[4 * Pp]; M[2] += Wo[5 * Pp];
+      }
+      pose_gradient(Ts + t, Pp, F, M, Gs + t, Pp);
+   }
 }
 
 /* ------------------------------------------------------------------------- */
@@ -149,6 +163,7 @@ __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tabl
  * directed terms x(s,o) and x(o,s) are formed, their difference is the net
  * workspace force on s and its negative the force on o.  Forces are gathered as
  * wrenches per joint frame in ws and mapped to joint space by flush_wrenches. */
+template <bool FLOAT>
 __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tables &tb,
                                                 const double *__restrict__ Ts,
                                                 double *__restrict__ ws, double *__restrict__ Gs,
@@ -311,12 +326,12 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
       }
    }
-   if (want_grad) flush_wrenches(a, tb, Ts, ws, Gs, t);
+   if (want_grad) flush_wrenches<FLOAT>(a, tb, Ts, ws, Gs, t);
    return cost;
 }
 
-template <int NT_MAX>
-__global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 3 : 1)
+template <int NT_MAX, bool FLOAT>
+__global__ void __launch_bounds__(NT_MAX, (NT_MAX == 128 && !FLOAT) ? 3 : 1)
 chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -427,7 +442,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       }
 
       /* ---- forward kinematics of all P waypoints ---- */
-      for (int t = tid; t < P; t += NT) fk_waypoint(a, tb, Ts, ws, t);
+      for (int t = tid; t < P; t += NT) fk_waypoint<FLOAT>(a, tb, Ts, ws, t);
       __syncthreads();
 
       /* ---- obstacle + self-collision cost / gradient, then G = G/m + A T + B ---- */
@@ -436,7 +451,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       {
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
-         csum += waypoint_cost(a, tb, Ts, ws, Gs, t, !final_pass);
+         csum += waypoint_cost<FLOAT>(a, tb, Ts, ws, Gs, t, !final_pass);
          if (!final_pass)
          {
             const double bi = __ldg(a.bcoef_i + t - 1), bf = __ldg(a.bcoef_f + t - 1);
@@ -508,6 +523,13 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
          tr[1] = cost_obs;
          tr[2] = cost_smooth;
       }
+      if (FLOAT)
+      {
+         /* base quaternions back to unit length (mod.cpp:2805-2808); the end rows are unit already */
+         __syncthreads();
+         for (int t = tid + 1; t <= m; t += NT) pose_normalize(Ts + t, Pp);
+         __syncthreads();
+      }
    }
 
    /* ---- write the run back ---- */
@@ -548,6 +570,13 @@ __global__ void init_traj_kernel(double *traj, const double *q_start, const doub
    }
 }
 
+/* floating base: every row's base quaternion to unit length after the interpolation (mod.cpp:2461-2464) */
+__global__ void normalize_rows_kernel(double *traj, size_t rows, int n)
+{
+   for (size_t r = blockIdx.x * (size_t) blockDim.x + threadIdx.x; r < rows; r += (size_t) gridDim.x * blockDim.x)
+      pose_normalize(traj + r * n, 1);
+}
+
 /* arg-min of cost_total over the runs of this GPU (first wins ties; failed runs skipped) */
 __global__ void best_kernel(const double *costs, const int *status, int R, int *best_run, double *best_cost)
 {
@@ -585,36 +614,46 @@ extern "C" size_t ocb_chomp_smem_bytes(const OcbChompArgs *a)
    return (size_t) smem_layout(*a).bytes;
 }
 
-template <int NT_MAX>
+template <int NT_MAX, bool FLOAT>
 static cudaError_t launch_variant(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    static size_t configured = 0;
    if (smem_bytes > configured)
    {
-      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel<NT_MAX>,
+      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel<NT_MAX, FLOAT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
       if (e != cudaSuccess) return e;
       configured = smem_bytes;
    }
-   chomp_iterate_kernel<NT_MAX><<<args->R, threads, smem_bytes, st>>>(*args);
+   chomp_iterate_kernel<NT_MAX, FLOAT><<<args->R, threads, smem_bytes, st>>>(*args);
    return cudaGetLastError();
 }
 
 extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    if (threads > 256 || threads % 32) return cudaErrorInvalidValue;
-   return threads <= 128 ? launch_variant<128>(args, smem_bytes, threads, st)
-                         : launch_variant<256>(args, smem_bytes, threads, st);
+   if (args->floating)
+      return threads <= 128 ? launch_variant<128, true>(args, smem_bytes, threads, st)
+                            : launch_variant<256, true>(args, smem_bytes, threads, st);
+   return threads <= 128 ? launch_variant<128, false>(args, smem_bytes, threads, st)
+                         : launch_variant<256, false>(args, smem_bytes, threads, st);
 }
 
 extern "C" cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const double *q_goal,
-                                            int R, int P, int n, cudaStream_t st)
+                                            int R, int P, int n, int floating, cudaStream_t st)
 {
    const size_t total = (size_t) R * P * n;
    int blocks = (int) ((total + 255) / 256);
    if (blocks > 148 * 8) blocks = 148 * 8;
    if (blocks < 1) blocks = 1;
    init_traj_kernel<<<blocks, 256, 0, st>>>(traj, q_start, q_goal, R, P, n);
+   if (floating)
+   {
+      const size_t rows = (size_t) R * P;
+      int nb = (int) ((rows + 255) / 256);
+      if (nb > 148 * 8) nb = 148 * 8;
+      normalize_rows_kernel<<<nb, 256, 0, st>>>(traj, rows, n);
+   }
    return cudaGetLastError();
 }
 

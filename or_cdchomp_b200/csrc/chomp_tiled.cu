@@ -195,7 +195,8 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
       for (int j = 0; j < a.nj; j++)
       {
          const OcbJointDev &J = a.joints[j];
-         fk_step<true>(J, Tr[J.dof], slots, CS, c, R, tr, ax, org);
+         if (a.floating) fk_step<true, true>(J, Tr[J.dof], slots, CS, c, R, tr, ax, org, Tr, 1);
+         else fk_step<true>(J, Tr[J.dof], slots, CS, c, R, tr, ax, org);
          if (c >= 1 && c <= TW)
          {
             double *fr = jfr + 6 * j * TW + (c - 1);
@@ -253,6 +254,8 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
             val = ax0 * F[0] + ax1 * F[1] + ax2 * F[2];
          Gw[J.dof * TW] = fma(J.c0, val, Gw[J.dof * TW]);
       }
+      /* floating base: the pose entries see every wrench (pose_gradient is linear in it) */
+      if (a.floating) pose_gradient(a.traj + ((size_t) run * P + (t_first + wpc)) * n, 1, F, M, Gw, TW);
    };
 
    int gcur = -1;
@@ -573,6 +576,15 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
    double ssum = 0.0, zero = 0.0;
    for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t);
    block_sum2(ssum, zero, red, red_parity);
+   if (a.floating)
+   {
+      /* base quaternions back to unit length, after the costs (mod.cpp:2805-2808) */
+      for (int t = tid + 1; t <= m; t += NT)
+      {
+         pose_normalize(Ts + t, Pp);
+         for (int k = 3; k < 7; k++) traj[(size_t) t * n + k] = Ts[k * Pp + t];
+      }
+   }
    if (tid == 0)
    {
       const double cost_obs = csum * inv_m, cost_smooth = ssum + trC;

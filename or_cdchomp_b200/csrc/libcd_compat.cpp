@@ -280,7 +280,7 @@ extern "C" int cd_chomp_b200_set_sphere_cost(struct cd_chomp *c, const ocb_robot
                                              int n_sdfs, const ocb_sdf *sdfs)
 {
    if (!c || !robot || !params || n_sdfs < 1 || !sdfs) return set_err(-2, "bad argument");
-   if (robot->n_dof != c->n) return set_err(-2, "robot active dofs differ from the run's n");
+   if (robot->n_dof + (params->floating_base ? 7 : 0) != c->n) return set_err(-2, "robot active dofs differ from the run's n");
    ChompPrivate *p = priv(c);
    const int nl = robot->n_links, ns = robot->n_spheres;
    p->parent.assign(robot->parent, robot->parent + nl);
@@ -347,8 +347,9 @@ extern "C" int cd_chomp_init(struct cd_chomp *c)
       p->sdf_ids.push_back(id);
    }
    ocb_robot rb = p->robot;
-   rb.limit_lower = c->jlimit_lower;
-   rb.limit_upper = c->jlimit_upper;
+   /* with a floating base the first seven entries of a row are the pose (unbounded, mod.cpp:2640-2652) */
+   rb.limit_lower = c->jlimit_lower + (p->params.floating_base ? 7 : 0);
+   rb.limit_upper = c->jlimit_upper + (p->params.floating_base ? 7 : 0);
    ocb_params pr = p->params;
    pr.n_points = c->m + 2;
    pr.derivative = c->D;

@@ -64,6 +64,7 @@ extern "C" void ocb_params_default(ocb_params *p)
    p->epsilon_self = 0.04;
    p->obs_factor = 200.0;
    p->obs_factor_self = 10.0;
+   p->floating_base = 0;
 }
 
 /* ------------------------------------------------------------ small algebra */
@@ -873,7 +874,7 @@ struct CompiledRobot
 /* Fold fixed / frozen links into joint frames with the moving axis on local z.
  * Replaces the OpenRAVE-side bookkeeping of mod::create (mod.cpp:2148-2300) and
  * prepares what sphere_cost_pre asks OpenRAVE for on every waypoint. */
-int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
+int compile_robot(const ocb_robot *rb, double eps_self, bool floating, CompiledRobot &C)
 {
    const int nl = rb->n_links;
    if (nl < 1 || rb->n_dof < 1) return fail(OCB_ERR_ARG, "robot needs links and active dofs");
@@ -881,7 +882,28 @@ int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
    std::vector<Xf> rel(nl);          /* link frame expressed in its anchor's joint frame (or world) */
    struct RawJoint { int parent; Xf X; int type, dof; double c0, c1; int link; };
    std::vector<RawJoint> raw;
-   rel[0] = xf_from_pose(rb->base_pose);
+   const int dof0 = floating ? 7 : 0; /* trajectory column of active dof 0 */
+   if (floating)
+   {
+      /* floating base (mod.cpp:991-1021): the base frame is a joint frame of its own whose
+       * transform the kernel takes from the waypoint's pose entries; it has no dof (c0 = 0),
+       * carries the spheres of every link that no active dof moves (all spheres are active,
+       * mod.cpp:2274) and is the parent of the root-level joints */
+      const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+      RawJoint B;
+      B.parent = -1;
+      B.X = xf_from_pose(ident);
+      B.type = OCB_JOINT_PRISMATIC;
+      B.dof = 0;
+      B.c0 = 0.0;
+      B.c1 = 0.0;
+      B.link = 0;
+      raw.push_back(B);
+      anchor[0] = 0;
+      rel[0] = xf_from_pose(ident);
+   }
+   else
+      rel[0] = xf_from_pose(rb->base_pose);
    for (int i = 1; i < nl; i++)
    {
       const int p = rb->parent[i];
@@ -897,7 +919,7 @@ int compile_robot(const ocb_robot *rb, double eps_self, CompiledRobot &C)
          J.parent = anchor[p];
          J.X = xf_mul(Xp, Q);
          J.type = type;
-         J.dof = rb->dof_index[i];
+         J.dof = dof0 + rb->dof_index[i];
          J.c0 = rb->dof_coeff[2 * i];
          J.c1 = rb->dof_coeff[2 * i + 1];
          J.link = i;
@@ -1110,9 +1132,10 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    CU(cudaSetDevice(e->device));
 
    CompiledRobot C;
-   int rc = compile_robot(robot, params->epsilon_self, C);
+   const bool floating = params->floating_base != 0;
+   int rc = compile_robot(robot, params->epsilon_self, floating, C);
    if (rc) return rc;
-   const int P = params->n_points, m = P - 2, n = robot->n_dof;
+   const int P = params->n_points, m = P - 2, n = robot->n_dof + (floating ? 7 : 0);
    if (m <= params->derivative) return fail(OCB_ERR_ARG, "n_points too small for derivative %d", params->derivative);
    Metric M;
    const double dt = 1.0 / (P - 1); /* mod.cpp:2567 */
@@ -1137,6 +1160,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    a.Ppad = P;
    a.use_momentum = params->use_momentum ? 1 : 0;
    a.use_hmc = use_hmc;
+   a.floating = floating ? 1 : 0;
    for (int j = 0; j < a.nj; j++) a.joints[j] = C.joints[j];
    a.trc_ss = M.ss; a.trc_sg = M.sg; a.trc_gg = M.gg;
    a.lambda = params->lambda;
@@ -1187,7 +1211,13 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    TRY(batch_upload(b, &a.bcoef_i, M.bi));
    TRY(batch_upload(b, &a.bcoef_f, M.bf));
    {
-      std::vector<double> lo(robot->limit_lower, robot->limit_lower + n), hi(robot->limit_upper, robot->limit_upper + n);
+      /* the pose entries of a floating base are unbounded (mod.cpp:2640-2652) */
+      std::vector<double> lo(n, -HUGE_VAL), hi(n, HUGE_VAL);
+      for (int j = 0; j < robot->n_dof; j++)
+      {
+         lo[(floating ? 7 : 0) + j] = robot->limit_lower[j];
+         hi[(floating ? 7 : 0) + j] = robot->limit_upper[j];
+      }
       TRY(batch_upload(b, &a.lim_lo, lo));
       TRY(batch_upload(b, &a.lim_hi, hi));
    }
@@ -1201,7 +1231,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    if (err == cudaSuccess) err = cudaMemsetAsync(a.status, 0, R * sizeof(int), e->stream);
    if (err == cudaSuccess) err = cudaMemcpyAsync(b->d_start, q_start, R * n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
    if (err == cudaSuccess) err = cudaMemcpyAsync(b->d_goal, q_goal, R * n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
-   if (err == cudaSuccess) err = ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, n_runs, P, n, e->stream);
+   if (err == cudaSuccess) err = ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, n_runs, P, n, a.floating, e->stream);
    e->launches++;
    if (a.use_momentum && err == cudaSuccess)
    {
@@ -1287,7 +1317,7 @@ extern "C" int ocb_batch_reset(ocb_batch *b, const double *q_start, const double
       CU(cudaMemcpyAsync(b->d_start, q_start, R * a.n * sizeof(double), cudaMemcpyHostToDevice, st));
       CU(cudaMemcpyAsync(b->d_goal, q_goal, R * a.n * sizeof(double), cudaMemcpyHostToDevice, st));
    }
-   CU(ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, a.R, a.P, a.n, st));
+   CU(ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, a.R, a.P, a.n, a.floating, st));
    b->e->launches++;
    CU(cudaMemsetAsync(a.costs, 0, R * 3 * sizeof(double), st));
    CU(cudaMemsetAsync(a.status, 0, R * sizeof(int), st));

@@ -62,6 +62,7 @@ struct OcbChompArgs
    int tiled, ng;          /* tiled: large-robot path (chomp_tiled.cu); ng: joint frames that carry spheres */
    int n_desc, NAp;        /* NAp: padded active part of a cut2 row (>= nsa + 3); row = NAp + nsi */
    int tile_w, n_tiles;    /* tiled path: waypoints per tile (32, 16 or 8), tiles per run */
+   int floating, pad0;     /* floating base: rows start with the base pose, joint 0 is the base frame */
    /* robot */
    OcbJointDev joints[OCB_MAX_JOINTS];
    const OcbSphereDev *spheres;
@@ -114,7 +115,7 @@ size_t ocb_run_update_smem_bytes(const OcbChompArgs *args);
 cudaError_t ocb_launch_chomp_tiled(const OcbChompArgs *args, size_t tile_smem, size_t run_smem,
                                    int run_threads, cudaStream_t st, long *launches);
 cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const double *q_goal,
-                                 int R, int P, int n, cudaStream_t st);
+                                 int R, int P, int n, int floating, cudaStream_t st);
 cudaError_t ocb_launch_best(const double *costs, const int *status, int R, int *best_run,
                             double *best_cost, cudaStream_t st);
 

@@ -224,6 +224,7 @@ struct Field
 struct Run
 {
    ocb_batch *batch = nullptr;
+   bool floating = false; /* rows start with the base pose (floating_base) */
    std::vector<int> sdf_ids;
    std::string robot_name;
    int n_runs = 1, n_points = 0, n_dof = 0;
@@ -633,7 +634,7 @@ struct ocb_module
    {
       std::string robot_name, dat_filename, starttraj;
       bool have_starttraj = false;
-      std::vector<double> adofgoal;
+      std::vector<double> adofgoal, basegoal;
       ocb_params pr;
       ocb_params_default(&pr);
       unsigned int seed = 0;
@@ -662,6 +663,7 @@ struct ocb_module
          {
             if (have_starttraj) throw module_error("Only one starttraj can be passed!");
             if (!adofgoal.empty()) throw module_error("Cannot pass both adofgoal and starttraj!");
+            if (!basegoal.empty()) throw module_error("Cannot pass both basegoal and starttraj!");
             starttraj = argv[++i];
             have_starttraj = true;
          }
@@ -678,8 +680,15 @@ struct ocb_module
          else if (a == "obs_factor_self" && has1) pr.obs_factor_self = atof(argv[++i].c_str());
          else if (a == "dat_filename" && has1) dat_filename = argv[++i];
          else if ((a == "ee_force" || a == "ee_force_at" || a == "ee_torque_weights") && has1) ++i; /* dead parameters, mod.cpp:1323 */
-         else if (a == "floating_base") unsupported = "floating_base";
-         else if ((a == "basegoal" || a == "start_tsr" || a == "everyn_tsr" || a == "start_cost") && has1)
+         else if (a == "floating_base") pr.floating_base = 1;
+         else if (a == "basegoal" && has1)
+         {
+            if (!basegoal.empty()) throw module_error("Only one basegoal can be passed!");
+            if (have_starttraj) throw module_error("Cannot pass both basegoal and starttraj!");
+            basegoal = parse_doubles(argv[++i]);
+            if (basegoal.size() != 7) throw module_error("basegoal argument must be length 7!");
+         }
+         else if ((a == "start_tsr" || a == "everyn_tsr" || a == "start_cost") && has1)
          {
             unsupported = argv[i].c_str();
             ++i;
@@ -703,12 +712,16 @@ struct ocb_module
       /* validity checks in the reference's order (mod.cpp:2091-2101) */
       if (robot_name.empty()) throw module_error("Did not pass a robot!");
       if (adofgoal.empty() && !goals_ptr && !have_starttraj) throw module_error("Did not pass either adofgoal or starttraj!");
+      if (pr.floating_base && basegoal.empty() && !have_starttraj) throw module_error("Passed floating_base with no basegoal!");
+      if (pr.floating_base && (have_starttraj || goals_ptr || starts_ptr))
+         throw module_error("floating_base with starttraj or batched end points is not supported by the B200 engine");
       if (sdfs.empty()) throw module_error("No signed distance fields have yet been computed!");
       if (pr.lambda < 0.01) throw module_error("lambda must be >=0.01!");
       if (pr.n_points < 3) throw module_error("n_points must be >=3!");
       Robot &rb = *env->robots[robot_name];
-      const int n = rb.desc.n_dof;
-      if (!goals_ptr && !have_starttraj && (int) adofgoal.size() != n) throw module_error("size of adofgoal does not match active dofs!");
+      const int n_adof = rb.desc.n_dof;
+      const int n = n_adof + (pr.floating_base ? 7 : 0); /* mod.cpp:2128-2131 */
+      if (!goals_ptr && !have_starttraj && (int) adofgoal.size() != n_adof) throw module_error("size of adofgoal does not match active dofs!");
       if (n_runs < 1) throw module_error("n_runs must be >=1!");
       std::vector<double> seed_traj; /* [n_points][n] when starttraj was passed */
       if (have_starttraj)
@@ -722,6 +735,7 @@ struct ocb_module
       r->n_runs = n_runs;
       r->n_points = pr.n_points;
       r->n_dof = n;
+      r->floating = pr.floating_base != 0;
       /* rooted fields: world pose of every grid at this instant (mod.cpp:2347-2369) */
       for (const Field &f : sdfs)
       {
@@ -748,6 +762,13 @@ struct ocb_module
                /* the end rows of the sampled trajectory are the fixed end points (mod.cpp:2578-2580) */
                starts[(size_t) k * n + j] = seed_traj[j];
                goals[(size_t) k * n + j] = seed_traj[(size_t) (pr.n_points - 1) * n + j];
+               continue;
+            }
+            if (pr.floating_base)
+            {
+               /* rows are [base pose, active dofs]: from the robot's transform to basegoal (mod.cpp:2424-2443) */
+               starts[(size_t) k * n + j] = (j < 7) ? rb.desc.base_pose[j] : rb.q[j - 7];
+               goals[(size_t) k * n + j] = (j < 7) ? basegoal[j] : adofgoal[j - 7];
                continue;
             }
             starts[(size_t) k * n + j] = starts_ptr ? starts_ptr[(size_t) k * n + j] : rb.q[j]; /* GetActiveDOFValues, mod.cpp:2447 */
@@ -881,17 +902,27 @@ struct ocb_module
       if (ocb_batch_get_traj(r->batch, traj.data()) != OCB_OK) fail_engine("gettraj");
       const Robot &rb = *env->robots[r->robot_name];
       sout.precision(17);
+      /* joint_values + deltatime, and for a floating base the affine_transform group the reference
+       * merges in (mod.cpp:2912-2956; OpenRAVE order x y z qw qx qy qz) */
+      const int na = r->floating ? n - 7 : n, j0 = r->floating ? 7 : 0;
       for (int k = 0; k < r->n_runs; k++)
       {
          sout << "<trajectory>\n<configuration>\n<group name=\"joint_values " << rb.name;
-         for (int j = 0; j < n; j++) sout << " " << j;
-         sout << "\" offset=\"0\" dof=\"" << n << "\" interpolation=\"linear\"/>\n"
-              << "<group name=\"deltatime\" offset=\"" << n << "\" dof=\"1\" interpolation=\"\"/>\n</configuration>\n"
-              << "<data count=\"" << P << "\">\n";
+         for (int j = 0; j < na; j++) sout << " " << j;
+         sout << "\" offset=\"0\" dof=\"" << na << "\" interpolation=\"linear\"/>\n"
+              << "<group name=\"deltatime\" offset=\"" << na << "\" dof=\"1\" interpolation=\"\"/>\n";
+         if (r->floating)
+            sout << "<group name=\"affine_transform " << rb.name << " 127\" offset=\"" << na + 1
+                 << "\" dof=\"7\" interpolation=\"linear\"/>\n";
+         sout << "</configuration>\n<data count=\"" << P << "\">\n";
          for (int p = 0; p < P; p++)
          {
-            for (int j = 0; j < n; j++) sout << traj[((size_t) k * P + p) * n + j] << " ";
+            const double *row = &traj[((size_t) k * P + p) * n];
+            for (int j = 0; j < na; j++) sout << row[j0 + j] << " ";
             sout << (p == 0 ? 0.0 : 1.0 / (P - 1)) << " ";
+            if (r->floating)
+               sout << row[0] << " " << row[1] << " " << row[2] << " " << row[6] << " " << row[3] << " " << row[4] << " "
+                    << row[5] << " ";
          }
          sout << "\n</data>\n</trajectory>\n";
       }

@@ -154,7 +154,8 @@ class Batch:
         q_start, q_goal = as_f64(q_start), as_f64(q_goal)
         if q_start.ndim == 1:
             q_start, q_goal = q_start[None, :], q_goal[None, :]
-        assert q_start.shape == q_goal.shape and q_start.shape[1] == robot.n_dof
+        # floating base: rows are [x y z qx qy qz qw, active dofs] (mod.cpp:2424-2443)
+        assert q_start.shape == q_goal.shape and q_start.shape[1] == robot.n_dof + (7 if params.floating_base else 0)
         self.R, self.n = q_start.shape
         self.P = params.n_points
         self.m = self.P - 2

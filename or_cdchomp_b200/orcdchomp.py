@@ -314,6 +314,7 @@ def iterate(mod, run=None, n_iter=None, max_time=None, trajs_fileformstr=None, c
 
 _DATA_RE = re.compile(r"<data count=\"(\d+)\">\s*(.*?)\s*</data>", re.S)
 _DOF_RE = re.compile(r"joint_values [^\"]*\" offset=\"0\" dof=\"(\d+)\"")
+_AFFINE_RE = re.compile(r"affine_transform [^\"]*\" offset=\"(\d+)\" dof=\"7\"")
 
 
 def gettraj(mod, run=None, no_collision_check=None, no_collision_exception=None, no_collision_details=None,
@@ -329,10 +330,17 @@ def gettraj(mod, run=None, no_collision_check=None, no_collision_exception=None,
         parts.append("no_collision_details")
     xml = mod.SendCommand(" ".join(parts), releasegil)
     n = int(_DOF_RE.search(xml).group(1))
+    aff = _AFFINE_RE.search(xml)
     trajs = []
     for count, body in _DATA_RE.findall(xml):
-        vals = np.array(body.split(), dtype=np.float64).reshape(int(count), n + 1)
-        trajs.append(vals[:, :n])
+        vals = np.array(body.split(), dtype=np.float64).reshape(int(count), n + 1 + (7 if aff else 0))
+        if aff:
+            # floating base: rows as the engine holds them, [x y z qx qy qz qw, active dofs]
+            o = int(aff.group(1))
+            pose = vals[:, [o, o + 1, o + 2, o + 4, o + 5, o + 6, o + 3]]
+            trajs.append(np.concatenate([pose, vals[:, :n]], axis=1))
+        else:
+            trajs.append(vals[:, :n])
     return trajs[0] if len(trajs) == 1 else np.array(trajs)
 
 

@@ -121,6 +121,7 @@ struct orc_run
    double *sphere_accs;
    double *sphere_jacs;
    double *J2;
+   double *Jadof;      /* scratch 3 x n_dof (floating base) */
    double *link_poses; /* scratch [n_links][7] */
    int n_rsdfs;
    struct orc_rsdf *rsdfs;
@@ -130,15 +131,25 @@ struct orc_run
    struct orc_mt rng;
    struct cd_chomp *c;
    int iter;
+   int floating; /* floating_base: rows are [x y z qx qy qz qw, adofs] (mod.cpp:991-1021) */
 };
 
 /* ------------------------------------------------- kinematics (OpenRAVE side) */
 /* forward kinematics of every link for active-dof vector q; stands in for
  * robot->SetActiveDOFValues (mod.cpp:1026) + Link::GetTransform (1033) */
+static void orc_fk_base(const struct ocb_robot *rb, const double *base_pose, const double *q, double *link_poses);
+
 void orc_fk(const struct ocb_robot *rb, const double *q, double *link_poses)
 {
+   orc_fk_base(rb, rb->base_pose, q, link_poses);
+}
+
+/* the same with the base at `base_pose`: robot->SetTransform(t) before SetActiveDOFValues in the
+ * floating-base branch (mod.cpp:1009-1020) */
+static void orc_fk_base(const struct ocb_robot *rb, const double *base_pose, const double *q, double *link_poses)
+{
    int i;
-   memcpy(link_poses, rb->base_pose, 7 * sizeof(double));
+   memcpy(link_poses, base_pose, 7 * sizeof(double));
    for (i = 1; i < rb->n_links; i++)
    {
       double motion[7], tmp[7];
@@ -198,6 +209,55 @@ void orc_jacobian(const struct ocb_robot *rb, const double *link_poses, int link
    }
 }
 
+/* cd_spatial_pose_jac (src/libcd/spatial.c:295-337): maps the derivatives of a pose
+ * [x y z qx qy qz qw] to the world spatial velocity [omega; v of the point at the origin] */
+static void orc_pose_jac(const double pose[7], double jac[6][7])
+{
+   double x = pose[0], y = pose[1], z = pose[2];
+   double qxt2 = 2.0 * pose[3], qyt2 = 2.0 * pose[4], qzt2 = 2.0 * pose[5], qwt2 = 2.0 * pose[6];
+   int i, j;
+   for (i = 0; i < 6; i++) for (j = 0; j < 7; j++) jac[i][j] = 0.0;
+   jac[3][0] = 1.0; jac[4][1] = 1.0; jac[5][2] = 1.0;
+   jac[0][3] = qwt2;  jac[0][4] = -qzt2; jac[0][5] = qyt2;  jac[0][6] = -qxt2;
+   jac[1][3] = qzt2;  jac[1][4] = qwt2;  jac[1][5] = -qxt2; jac[1][6] = -qyt2;
+   jac[2][3] = -qyt2; jac[2][4] = qxt2;  jac[2][5] = qwt2;  jac[2][6] = -qzt2;
+   jac[3][3] = -z * qzt2 - y * qyt2; jac[3][4] = -z * qwt2 + y * qxt2;
+   jac[3][5] = z * qxt2 + y * qwt2;  jac[3][6] = z * qyt2 - y * qzt2;
+   jac[4][3] = z * qwt2 + x * qyt2;  jac[4][4] = -z * qzt2 - x * qxt2;
+   jac[4][5] = z * qyt2 - x * qwt2;  jac[4][6] = -z * qxt2 + x * qzt2;
+   jac[5][3] = -y * qwt2 + x * qzt2; jac[5][4] = y * qzt2 + x * qwt2;
+   jac[5][5] = -y * qyt2 - x * qxt2; jac[5][6] = y * qxt2 - x * qyt2;
+}
+
+/* the left 3 x 7 block of a sphere's Jacobian in floating-base mode (mod.cpp:1050-1080):
+ * rows 3..5 of the motion transform to the frame at -v (identity rotation, so [rx] I | I with
+ * r = -v, spatial.c:71-102) times Jsp, then the reference's 0.01 scaling.  J has row length n. */
+static void orc_pose_columns(const double Jsp[6][7], const double v[3], double *J, int n)
+{
+   double Xm3[3][6];
+   int i, k, l;
+   for (i = 0; i < 3; i++) for (l = 0; l < 6; l++) Xm3[i][l] = 0.0;
+   Xm3[0][1] = v[2];  Xm3[0][2] = -v[1];
+   Xm3[1][0] = -v[2]; Xm3[1][2] = v[0];
+   Xm3[2][0] = v[1];  Xm3[2][1] = -v[0];
+   Xm3[0][3] = 1.0; Xm3[1][4] = 1.0; Xm3[2][5] = 1.0;
+   for (i = 0; i < 3; i++)
+      for (k = 0; k < 7; k++)
+      {
+         double acc = 0.0;
+         for (l = 0; l < 6; l++) acc += Xm3[i][l] * Jsp[l][k];
+         J[i * n + k] = acc * 0.01;
+      }
+}
+
+/* test hook: the 3 x 7 pose block for a point v of a body at `pose` */
+void orc_pose_block(const double pose[7], const double v[3], double J[21])
+{
+   double Jsp[6][7];
+   orc_pose_jac(pose, Jsp);
+   orc_pose_columns(Jsp, v, J, 7);
+}
+
 /* robot->DoesAffect(adof, linkindex) over all active dofs (mod.cpp:2270-2273) */
 static int link_is_active(const struct ocb_robot *rb, int link)
 {
@@ -223,17 +283,34 @@ static int orc_sphere_cost_pre(void *cptr, struct cd_chomp *c, int m, double **T
    for (ti = 0; ti < r->n_points; ti++)
    {
       int ti_mov = ti - 1; /* c->m == n_points-2 (no start_tsr) */
-      orc_fk(rb, &r->traj[ti * c->n], r->link_poses);
+      double Jsp[6][7];
+      if (r->floating)
+      {
+         orc_pose_jac(&r->traj[ti * c->n], Jsp);
+         orc_fk_base(rb, &r->traj[ti * c->n], &r->traj[ti * c->n + 7], r->link_poses);
+      }
+      else
+         orc_fk(rb, &r->traj[ti * c->n], r->link_poses);
       for (s = 0; s < sa; s++)
       {
          int src = r->sph_src[s];
          int link = rb->sphere_link[src];
          double v[3];
+         double *J;
          cd_kin_pose_compos(&r->link_poses[7 * link], &rb->sphere_pos[3 * src], v);
          for (k = 0; k < 3; k++) r->sphere_poss_all[ti * row + s * 3 + k] = v[k];
          if (ti_mov < 0 || m <= ti_mov) continue;
-         orc_jacobian(rb, r->link_poses, link, v,
-                      &r->sphere_jacs[((size_t) ti_mov * sa + s) * 3 * c->n]);
+         J = &r->sphere_jacs[((size_t) ti_mov * sa + s) * 3 * c->n];
+         if (r->floating)
+         {
+            int i, j, na = rb->n_dof;
+            orc_pose_columns(Jsp, v, J, c->n);
+            orc_jacobian(rb, r->link_poses, link, v, r->Jadof);
+            for (i = 0; i < 3; i++)
+               for (j = 0; j < na; j++) J[i * c->n + 7 + j] = r->Jadof[i * na + j]; /* mod.cpp:1083-1085 */
+         }
+         else
+            orc_jacobian(rb, r->link_poses, link, v, J);
       }
    }
    /* velocities: (p[t+1] - p[t-1]) * (1/(2 dt))   (mod.cpp:1105-1107) */
@@ -415,6 +492,7 @@ void orc_run_destroy(struct orc_run *r)
    free(r->sphere_accs);
    free(r->sphere_jacs);
    free(r->J2);
+   free(r->Jadof);
    free(r->link_poses);
    free(r);
 }
@@ -428,11 +506,13 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
 {
    struct orc_run *r;
    struct cd_chomp *c = 0;
-   int n = rb->n_dof, P = pr->n_points, m = P - 2;
+   int fl = pr->floating_base ? 1 : 0;
+   int n = rb->n_dof + (fl ? 7 : 0), P = pr->n_points, m = P - 2;
    int i, j, s, na = 0, ni = 0;
    if (pr->lambda < 0.01 || P < 3 || n_sdfs < 1) return -2;
    r = (struct orc_run *) calloc(1, sizeof(struct orc_run));
    if (!r) return -1;
+   r->floating = fl;
    r->robot = rb;
    r->n_points = P;
    r->n = n;
@@ -448,14 +528,16 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    /* active spheres first (XML order), then inactive (XML order): SURVEY A.6 */
    r->n_spheres = rb->n_spheres;
    r->sph_src = (int *) malloc(rb->n_spheres * sizeof(int));
+   /* "if we're floating, call all spheres active" (mod.cpp:2274) */
    for (s = 0; s < rb->n_spheres; s++)
-      if (link_is_active(rb, rb->sphere_link[s])) r->sph_src[na++] = s;
+      if (fl || link_is_active(rb, rb->sphere_link[s])) r->sph_src[na++] = s;
    for (s = 0; s < rb->n_spheres; s++)
-      if (!link_is_active(rb, rb->sphere_link[s])) r->sph_src[na + ni++] = s;
+      if (!(fl || link_is_active(rb, rb->sphere_link[s]))) r->sph_src[na + ni++] = s;
    r->n_spheres_active = na;
    if (!na) { orc_run_destroy(r); return -2; }
 
    r->J2 = (double *) malloc(3 * n * sizeof(double));
+   r->Jadof = (double *) malloc(3 * (rb->n_dof ? rb->n_dof : 1) * sizeof(double));
    r->link_poses = (double *) malloc((size_t) rb->n_links * 7 * sizeof(double));
    r->sphere_poss_all = (double *) malloc((size_t) P * na * 3 * sizeof(double));
    r->sphere_poss = r->sphere_poss_all + (size_t) na * 3;
@@ -464,8 +546,8 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    r->sphere_jacs = (double *) malloc((size_t) m * na * 3 * n * sizeof(double));
    r->sphere_poss_inactive = (double *) malloc((size_t) (ni ? ni : 1) * 3 * sizeof(double));
 
-   /* inactive spheres are frozen at the robot's current configuration */
-   orc_fk(rb, q_start, r->link_poses);
+   /* inactive spheres are frozen at the robot's current configuration (none when floating) */
+   if (!fl) orc_fk(rb, q_start, r->link_poses);
    for (s = 0; s < ni; s++)
    {
       int src = r->sph_src[na + s];
@@ -496,6 +578,8 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    for (i = 0; i < P; i++)
       for (j = 0; j < n; j++)
          r->traj[i * n + j] = r->traj[j] + (r->traj[(P - 1) * n + j] - r->traj[j]) * i / (P - 1);
+   if (fl) /* mod.cpp:2461-2464 */
+      for (i = 0; i < P; i++) cd_kin_pose_normalize(&r->traj[i * n]);
 
    if (cd_chomp_create(&c, m, n, pr->derivative, &r->traj[n], n)) { orc_run_destroy(r); return -1; }
    r->c = c;
@@ -509,8 +593,9 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    if (pr->use_momentum) c->use_momentum = 1;
    for (j = 0; j < n; j++)
    {
-      c->jlimit_lower[j] = rb->limit_lower[j];
-      c->jlimit_upper[j] = rb->limit_upper[j];
+      /* mod.cpp:2639-2660: the pose entries are unbounded */
+      c->jlimit_lower[j] = (fl && j < 7) ? -HUGE_VAL : rb->limit_lower[j - (fl ? 7 : 0)];
+      c->jlimit_upper[j] = (fl && j < 7) ? HUGE_VAL : rb->limit_upper[j - (fl ? 7 : 0)];
    }
    if (cd_chomp_init(c)) { orc_run_destroy(r); return -2; }
    *out = r;
@@ -555,6 +640,8 @@ int orc_run_iterate(struct orc_run *r, int n_iter, double *costs, double *trace,
       }
       if (grads) memcpy(&grads[(size_t) r->iter * c->m * c->n], c->G, (size_t) c->m * c->n * sizeof(double));
       if (ret == -1) return -1;
+      if (r->floating) /* mod.cpp:2805-2808 */
+         for (i = 0; i < r->n_points; i++) cd_kin_pose_normalize(&r->traj[i * c->n]);
    }
    cd_chomp_iterate(c, 0, &total, &obs, &smooth);
    if (costs) { costs[0] = total; costs[1] = obs; costs[2] = smooth; }

@@ -85,6 +85,8 @@ def load(flavour="port"):
                                    c_double_p, c_int_p]
     lib.orc_fk.restype = None
     lib.orc_fk.argtypes = [C.POINTER(OcbRobot), c_double_p, c_double_p]
+    lib.orc_pose_block.restype = None
+    lib.orc_pose_block.argtypes = [c_double_p, c_double_p, c_double_p]
     lib.orc_mt_seed.restype = None
     lib.orc_mt_seed.argtypes = [vp, C.c_uint]
     lib.orc_mt_next.restype = C.c_uint
@@ -128,7 +130,7 @@ class Run:
     def __init__(self, robot, params, sdfs, q_start, q_goal, seed=0, flavour="port"):
         self.lib = load(flavour)
         self.robot, self.params, self.sdfs = robot, params, list(sdfs)
-        self.n = robot.n_dof
+        self.n = robot.n_dof + (7 if params.floating_base else 0)
         self.P = params.n_points
         self.m = self.P - 2
         arr = (OcbSdf * len(self.sdfs))(*[s.struct for s in self.sdfs])
@@ -248,6 +250,15 @@ def fk(robot, q, flavour="port"):
     q = as_f64(q)
     out = np.zeros((robot.n_links, 7))
     lib.orc_fk(C.byref(robot.struct), dptr(q), dptr(out))
+    return out
+
+
+def pose_block(pose, v, flavour="port"):
+    """3 x 7 pose block of a sphere Jacobian in floating-base mode (mod.cpp:1050-1080), 0.01 scaling included"""
+    lib = load(flavour)
+    pose, v = as_f64(pose), as_f64(v)
+    out = np.zeros((3, 7))
+    lib.orc_pose_block(dptr(pose), dptr(v), dptr(out))
     return out
 
 

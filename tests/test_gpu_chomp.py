@@ -426,3 +426,82 @@ def test_cd_chomp_facade_matches_reference(oracle, flavour, wam7, table):
     assert np.allclose(cf, tr[-1], rtol=1e-9, atol=0)
     fac.close()
     run.close()
+
+
+def _floating_endpoints(robot, n, seed0):
+    starts, goals = models.random_endpoints(robot, n, seed0=seed0, shrink=0.3)
+    rng = np.random.default_rng(seed0)
+    base0 = np.asarray(robot.base_pose, dtype=float)
+    qs, qg = [], []
+    for r in range(n):
+        move = models.pose_make(rng.uniform(-0.2, 0.2, 3), models.quat_from_axis_angle(rng.normal(size=3), rng.uniform(0.2, 0.6)))
+        qs.append(np.concatenate([base0, starts[r]]))
+        qg.append(np.concatenate([models.pose_compose(base0, move), goals[r]]))
+    return np.array(qs), np.array(qg)
+
+
+def test_floating_base_matches_oracle(engine, oracle, flavour, wam7, table):
+    """floating_base (mod.cpp:991-1021, 1050-1086, 2424-2464, 2805-2808): n = 7 + adof, every sphere
+    active, pose columns of the Jacobian x 0.01, quaternions re-normalised per iteration; plain and
+    momentum runs against the oracle."""
+    sd = table["desc"]
+    sid = engine.upload_sdf(sd)
+    for mom in (0, 1):
+        params = capi.default_params(n_points=50, lambda_=100.0, obs_factor=300.0, floating_base=1, use_momentum=mom)
+        qs, qg = _floating_endpoints(wam7, 4, 70 + mom)
+        b = engine.create_batch(wam7, params, [sid], qs, qg)
+        assert b.get_traj().shape == (4, 50, 14)
+        b.capture_gradient(1)
+        b.iterate(1)
+        g = b.get_gradient()
+        for r in range(4):
+            run = oracle.Run(wam7, params, [sd], qs[r], qg[r], flavour=flavour)
+            _, _, _, gr = run.iterate(1, want_grads=True)
+            assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * np.max(np.abs(gr[0]))
+            assert np.abs(gr[0][:, :7]).max() > 0
+            run.close()
+        b.close()
+        b = engine.create_batch(wam7, params, [sid], qs, qg)
+        costs, status = b.iterate(30)
+        traj = b.get_traj()
+        for r in range(4):
+            run = oracle.Run(wam7, params, [sd], qs[r], qg[r], flavour=flavour)
+            ret, c, _, _ = run.iterate(30)
+            assert ret == 0 and status[r] == 0
+            assert np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL
+            assert np.allclose(np.linalg.norm(traj[r][:, 3:7], axis=1), 1.0, atol=1e-14)
+            assert np.allclose(costs[r], c, rtol=1e-8, atol=0)
+            run.close()
+        b.close()
+    engine.remove_sdf(sid)
+
+
+def test_floating_base_tiled_path(engine, oracle, flavour, table):
+    """the same mode on the tiled two-kernel path (200-sphere arm)."""
+    robot = models.dense_sphere_arm(200, seed=5)
+    sd = table["desc"]
+    sid = engine.upload_sdf(sd)
+    params = capi.default_params(n_points=48, lambda_=200.0, obs_factor=100.0, floating_base=1)
+    qs, qg = _floating_endpoints(robot, 2, 91)
+    b = engine.create_batch(robot, params, [sid], qs, qg)
+    b.capture_gradient(1)
+    b.iterate(1)
+    g = b.get_gradient()
+    for r in range(2):
+        run = oracle.Run(robot, params, [sd], qs[r], qg[r], flavour=flavour)
+        _, _, _, gr = run.iterate(1, want_grads=True)
+        assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * np.max(np.abs(gr[0]))
+        run.close()
+    b.close()
+    b = engine.create_batch(robot, params, [sid], qs, qg)
+    costs, status = b.iterate(6)
+    traj = b.get_traj()
+    for r in range(2):
+        run = oracle.Run(robot, params, [sd], qs[r], qg[r], flavour=flavour)
+        ret, c, _, _ = run.iterate(6)
+        assert ret == 0 and status[r] == 0
+        assert np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL
+        assert np.allclose(costs[r], c, rtol=1e-8, atol=0)
+        run.close()
+    b.close()
+    engine.remove_sdf(sid)

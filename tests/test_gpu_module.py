@@ -112,7 +112,7 @@ def test_addfield_fromobsarray_cache_and_errors(world, oracle, flavour, tmp_path
     with pytest.raises(RuntimeError, match="size of adofgoal does not match"):
         mod.create(robot=robot, adofgoal=[0, 1])
     with pytest.raises(RuntimeError, match="not supported by the B200 engine"):
-        mod.create(robot=robot, adofgoal=goal, floating_base=True)
+        mod.create(robot=robot, adofgoal=goal, start_tsr="x")
     with pytest.raises(RuntimeError, match="you must pass a created run!"):
         mod.iterate(run="0x1234", n_iter=1)
     with pytest.raises(RuntimeError, match="Could not find kinbody"):
@@ -171,4 +171,30 @@ def test_starttraj_seeding(world):
                        "does not match")):
         with pytest.raises(RuntimeError) as ei:
             mod.create(robot=robot, **bad)
+        assert text in str(ei.value)
+
+
+def test_floating_base_through_module(world, oracle, flavour):
+    """create floating_base basegoal '...' (mod.cpp:1912-1923, 2093, 2424-2443): rows are the base
+    pose from the robot's transform to basegoal followed by the active dofs; gettraj carries the
+    affine_transform group (mod.cpp:2912-2956)."""
+    env, mod, table, robot, robot_desc = world
+    mod.computedistancefield(kinbody=table, cube_extent=0.02)
+    base0 = np.asarray(robot_desc.base_pose, dtype=float)
+    base1 = models.pose_compose(base0, models.pose_make((0.1, 0.15, -0.05), models.quat_from_axis_angle((0, 0.3, 1), 0.5)))
+    goal = list(models.WAM7_DEMO_GOAL)
+    traj = mod.runchomp(robot=robot, n_iter=20, lambda_=100.0, obs_factor=300.0, n_points=40, adofgoal=goal,
+                        floating_base=True, basegoal=list(base1), no_collision_check=True)
+    assert traj.shape == (40, 14)
+    sd = oracle_field_for_table(oracle, flavour)
+    params = capi.default_params(n_points=40, lambda_=100.0, obs_factor=300.0, floating_base=1)
+    run = oracle.Run(robot_desc, params, [sd], np.concatenate([base0, models.WAM7_DEMO_START]),
+                     np.concatenate([base1, goal]), flavour=flavour)
+    ret, c, _, _ = run.iterate(20)
+    assert ret == 0 and np.max(np.abs(traj - run.traj())) <= 1e-6
+    run.close()
+    for bad, text in ((dict(floating_base=True), "Passed floating_base with no basegoal!"),
+                      (dict(floating_base=True, basegoal=[0, 0, 0, 1]), "basegoal argument must be length 7!")):
+        with pytest.raises(RuntimeError) as ei:
+            mod.create(robot=robot, adofgoal=goal, **bad)
         assert text in str(ei.value)

@@ -252,3 +252,53 @@ def test_fk_jacobian_finite_difference(oracle):
     g, c = run.obstacle_gradient()
     assert np.isfinite(g).all() and np.abs(g).max() > 0
     run.close()
+
+
+def test_floating_base_oracle(oracle, flavour, wam7, table):
+    """floating_base branch of the restated callbacks (mod.cpp:991-1021, 1050-1086, 2424-2464,
+    2805-2808): the pose block of the sphere Jacobian is 0.01 x the derivative of the sphere
+    centre along translations and unit-quaternion tangents; with the base held where
+    robot.base_pose puts it the active-dof columns equal the fixed-base gradient; rows start as
+    and stay unit quaternions."""
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    pose = np.concatenate([rng.uniform(-1, 1, 3), q])
+    pb = rng.uniform(-0.5, 0.5, 3)
+
+    def world(p7):
+        return models.quat_rotate(p7[3:], pb) + p7[:3]
+    v = world(pose)
+    J = oracle.pose_block(pose, v, flavour=flavour)
+    h = 1e-6
+    for k in range(3):
+        d = np.zeros(7); d[k] = h
+        assert np.allclose((world(pose + d) - world(pose - d)) / (2 * h), J[:, k] / 0.01, atol=1e-8)
+    for _ in range(3):
+        dq = rng.normal(size=4)
+        dq -= q * dq.dot(q)                      # tangent to the unit sphere
+        pp, pm = pose.copy(), pose.copy()
+        pp[3:] = (q + h * dq) / np.linalg.norm(q + h * dq)
+        pm[3:] = (q - h * dq) / np.linalg.norm(q - h * dq)
+        assert np.allclose((world(pp) - world(pm)) / (2 * h), J[:, 3:] @ dq / 0.01, atol=1e-7)
+    # a run: rows start as unit quaternions and stay so; the 0.01-scaled pose columns move the
+    # base far less than the arm.  (The base must travel: the reference divides by the squared
+    # speed of every active sphere unguarded, mod.cpp:1239, and in this mode the spheres of the
+    # base link are active too.)
+    sd = table["desc"]
+    pf = capi.default_params(n_points=30, lambda_=100.0, obs_factor=300.0, floating_base=1)
+    starts, goals = models.random_endpoints(wam7, 1, seed0=11, shrink=0.3)
+    base0 = np.asarray(wam7.base_pose, dtype=float)
+    base1 = models.pose_compose(base0, models.pose_make((0.15, -0.1, 0.05), models.quat_from_axis_angle((0.2, 0.1, 1.0), 0.4)))
+    flt = oracle.Run(wam7, pf, [sd], np.concatenate([base0, starts[0]]), np.concatenate([base1, goals[0]]), flavour=flavour)
+    t0 = flt.traj()
+    assert t0.shape == (30, 14)
+    assert np.allclose(np.linalg.norm(t0[:, 3:7], axis=1), 1.0, atol=1e-15)
+    g1, c1 = flt.obstacle_gradient()
+    assert g1.shape == (28, 14) and np.all(np.isfinite(g1)) and np.abs(g1[:, :7]).max() > 0
+    ret, c, tr, _ = flt.iterate(5, want_trace=True)
+    assert ret == 0 and np.all(np.isfinite(tr))
+    t = flt.traj()
+    assert np.allclose(np.linalg.norm(t[:, 3:7], axis=1), 1.0, atol=1e-15)
+    assert np.max(np.abs(t[:, :7] - t0[:, :7])) < 0.2 * np.max(np.abs(t[:, 7:] - t0[:, 7:]))
+    flt.close()
