@@ -1136,7 +1136,6 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    int rc = compile_robot(robot, params->epsilon_self, floating, C);
    if (rc) return rc;
    const int P = params->n_points, m = P - 2, n = robot->n_dof + (floating ? 7 : 0);
-   if (m <= params->derivative) return fail(OCB_ERR_ARG, "n_points too small for derivative %d", params->derivative);
    Metric M;
    const double dt = 1.0 / (P - 1); /* mod.cpp:2567 */
    rc = build_metric(m, params->derivative, dt, M);

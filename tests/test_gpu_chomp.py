@@ -505,3 +505,25 @@ def test_floating_base_tiled_path(engine, oracle, flavour, table):
         run.close()
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_smallest_trajectories(engine, oracle, flavour, wam7, table):
+    """the shortest problems cd_chomp accepts: one or two moving waypoints, derivative up to 3
+    (fewer moving points than the metric's bandwidth)."""
+    sd = table["desc"]
+    sid = engine.upload_sdf(sd)
+    starts, goals = models.random_endpoints(wam7, 2, seed0=31, shrink=0.3)
+    for P, D in ((3, 1), (4, 1), (3, 2), (4, 2), (5, 3), (4, 3), (33, 1), (34, 2)):
+        params = capi.default_params(n_points=P, lambda_=100.0, obs_factor=300.0, derivative=D)
+        b = engine.create_batch(wam7, params, [sid], starts, goals)
+        costs, status = b.iterate(5)
+        traj = b.get_traj()
+        for r in range(2):
+            run = oracle.Run(wam7, params, [sd], starts[r], goals[r], flavour=flavour)
+            ret, c, _, _ = run.iterate(5)
+            assert ret == 0 and status[r] == 0, (P, D)
+            assert np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL, (P, D)
+            assert np.allclose(costs[r], c, rtol=1e-8, atol=0), (P, D)
+            run.close()
+        b.close()
+    engine.remove_sdf(sid)
