@@ -7,9 +7,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define OCB_MAX_JOINTS 16   /* moving joints carried in kernel-parameter (constant) space */
-#define OCB_MAX_SDFS 16  /* descriptors are staged in shared memory */
-#define OCB_MAX_BW 4        /* half bandwidth of the smoothness metric (= derivative D) */
+#define OCB_MAX_JOINTS 24   /* moving joints carried in kernel-parameter (constant) space */
+#define OCB_MAX_SDFS 64  /* descriptors are staged in shared memory */
+#define OCB_MAX_BW 8        /* half bandwidth of the smoothness metric (= derivative D) */
 
 /* parent-transform source of a joint in the forward sweep */
 #define OCB_LOAD_PREV (-1)

@@ -513,7 +513,7 @@ def test_smallest_trajectories(engine, oracle, flavour, wam7, table):
     sd = table["desc"]
     sid = engine.upload_sdf(sd)
     starts, goals = models.random_endpoints(wam7, 2, seed0=31, shrink=0.3)
-    for P, D in ((3, 1), (4, 1), (3, 2), (4, 2), (5, 3), (4, 3), (33, 1), (34, 2)):
+    for P, D in ((3, 1), (4, 1), (3, 2), (4, 2), (5, 3), (4, 3), (33, 1), (34, 2), (40, 5)):
         params = capi.default_params(n_points=P, lambda_=100.0, obs_factor=300.0, derivative=D)
         b = engine.create_batch(wam7, params, [sid], starts, goals)
         costs, status = b.iterate(5)
@@ -523,7 +523,8 @@ def test_smallest_trajectories(engine, oracle, flavour, wam7, table):
             ret, c, _, _ = run.iterate(5)
             assert ret == 0 and status[r] == 0, (P, D)
             assert np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL, (P, D)
-            assert np.allclose(costs[r], c, rtol=1e-8, atol=0), (P, D)
+            # a 5th-derivative metric has entries ~1e14: the two factorisations agree less tightly
+            assert np.allclose(costs[r], c, rtol=1e-8 if D < 4 else 1e-6, atol=0), (P, D)
             run.close()
         b.close()
     engine.remove_sdf(sid)
