@@ -40,13 +40,13 @@ struct SmemLayout
    int bytes;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(const OcbChompArgs &a)
+__host__ __device__ inline SmemLayout smem_layout(const OcbChompArgs &a, const int Pp, const int n)
 {
    SmemLayout l;
    int d = 0;
-   l.T = d; d += a.n * a.Ppad;
-   l.G = d; d += a.n * a.Ppad;
-   l.AG = d; d += a.use_momentum ? a.n * a.Ppad : 0;
+   l.T = d; d += n * Pp;
+   l.G = d; d += n * Pp;
+   l.AG = d; d += a.use_momentum ? n * Pp : 0;
    l.red = d; d += 36;
    l.ws = d; d += (int) a.ws_stride;
    l.cut2 = d; d += a.nsa * (a.NAp + a.nsi);
@@ -73,11 +73,11 @@ struct Tables
 
 /* forward kinematics of waypoint t: world positions of the active spheres.
  * Replaces SetActiveDOFValues + GetTransform()*pos (mod.cpp:1026-1038). */
-template <bool FLOAT>
+template <bool FLOAT, int PP>
 __device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables &tb,
                                             const double *__restrict__ Ts, double *__restrict__ ws, int t)
 {
-   const int Pp = a.Ppad;
+   const int Pp = PP ? PP : a.Ppad;
    double *slots = ws + 3 * a.nsa * Pp;
    double R[9], tr[3], ax[3], org[3];
 #pragma unroll
@@ -104,12 +104,12 @@ __device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables 
  * the wrench of the joint's subtree:  dC/dq_j = c0 * axis . (M - origin x F)  for a
  * revolute joint, c0 * axis . F for a prismatic one.  This is the product with the
  * CalculateJacobian columns (mod.cpp:1048, 1244, 1314) without storing them. */
-template <bool FLOAT>
+template <bool FLOAT, int PP>
 __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tables &tb,
                                                const double *__restrict__ Ts, double *__restrict__ ws,
                                                double *__restrict__ Gs, int t)
 {
-   const int Pp = a.Ppad;
+   const int Pp = PP ? PP : a.Ppad;
    double *slots = ws + 3 * a.nsa * Pp;
    const double *Wg = ws + (3 * a.nsa + 12 * a.n_slots) * Pp + t;
    double R[9], tr[3], ax[3], org[3];
@@ -163,13 +163,13 @@ __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tabl
  * directed terms x(s,o) and x(o,s) are formed, their difference is the net
  * workspace force on s and its negative the force on o.  Forces are gathered as
  * wrenches per joint frame in ws and mapped to joint space by flush_wrenches. */
-template <bool FLOAT>
+template <bool FLOAT, int PP>
 __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tables &tb,
                                                 const double *__restrict__ Ts,
                                                 double *__restrict__ ws, double *__restrict__ Gs,
                                                 int t, bool want_grad)
 {
-   const int Pp = a.Ppad;
+   const int Pp = PP ? PP : a.Ppad;
    const int nsa = a.nsa;
    const int row = a.NAp + a.nsi;
    double *Wg = ws + (3 * nsa + 12 * a.n_slots) * Pp + t;
@@ -326,11 +326,11 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
       }
    }
-   if (want_grad) flush_wrenches<FLOAT>(a, tb, Ts, ws, Gs, t);
+   if (want_grad) flush_wrenches<FLOAT, PP>(a, tb, Ts, ws, Gs, t);
    return cost;
 }
 
-template <int NT_MAX, bool FLOAT>
+template <int NT_MAX, bool FLOAT, int PP, int NN>
 __global__ void __launch_bounds__(NT_MAX, (NT_MAX == 128 && !FLOAT) ? 3 : 1)
 chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
 {
@@ -338,10 +338,11 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
    const int tid = threadIdx.x;
    const int NT = blockDim.x;
    const int run = blockIdx.x;
-   const int P = a.P, m = a.m, n = a.n, Pp = a.Ppad;
+   const int Pp = PP ? PP : a.Ppad;
+   const int P = PP ? PP : a.P, m = PP ? PP - 2 : a.m, n = NN ? NN : a.n;
 
    /* ---- shared memory carve-up ---- */
-   const SmemLayout lay = smem_layout(a);
+   const SmemLayout lay = smem_layout(a, Pp, n);
    double *sd = reinterpret_cast<double *>(smem_raw);
    double *Ts = sd + lay.T;     /* [n][Pp] */
    double *Gs = sd + lay.G;     /* [n][Pp] */
@@ -442,7 +443,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       }
 
       /* ---- forward kinematics of all P waypoints ---- */
-      for (int t = tid; t < P; t += NT) fk_waypoint<FLOAT>(a, tb, Ts, ws, t);
+      for (int t = tid; t < P; t += NT) fk_waypoint<FLOAT, PP>(a, tb, Ts, ws, t);
       __syncthreads();
 
       /* ---- obstacle + self-collision cost / gradient, then G = G/m + A T + B ---- */
@@ -451,7 +452,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       {
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
-         csum += waypoint_cost<FLOAT>(a, tb, Ts, ws, Gs, t, !final_pass);
+         csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass);
          if (!final_pass)
          {
             const double bi = __ldg(a.bcoef_i + t - 1), bf = __ldg(a.bcoef_f + t - 1);
@@ -460,13 +461,13 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
                const double *Tj = Ts + j * Pp;
                double g = Gs[j * Pp + t] * inv_m;
                if (a.grad_mode == 2) a.grad_out[((size_t) run * m + (t - 1)) * n + j] = g;
-               g += band_AT(a, Tj, t) + (bi * Tj[0] + bf * Tj[P - 1]);
+               g += band_AT(a, Tj, t, m) + (bi * Tj[0] + bf * Tj[P - 1]);
                Gs[j * Pp + t] = g;
                if (a.grad_mode == 1) a.grad_out[((size_t) run * m + (t - 1)) * n + j] = g;
             }
          }
          else
-            ssum += smooth_row(a, Ts, t);
+            ssum += smooth_row(a, Ts, t, Pp, P, n);
       }
       if (final_pass)
       {
@@ -478,7 +479,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       __syncthreads(); /* every row of G is complete */
 
       /* ---- AG = A^-1 G (banded solve, one thread per dof) ---- */
-      if (tid < n) band_solve(a, Gs + tid * Pp + 1);
+      if (tid < n) band_solve(a, Gs + tid * Pp + 1, m);
       __syncthreads();
 
       /* ---- momentum / plain update, T -= AG/lambda (chomp.c:525-548, 604-605); each thread
@@ -504,7 +505,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       const int any_violation = __syncthreads_or(violated);
 
       /* ---- joint-limit projection (chomp.c:608-655) ---- */
-      if (any_violation && !project_joint_limits(a, Ts, Gs, red, ired))
+      if (any_violation && !project_joint_limits(a, Ts, Gs, red, ired, Pp, m, n))
       {
          status = OCB_ERR_JLIMIT; /* chomp.c:651-655 returns -1 before the smoothness cost */
          break;
@@ -512,7 +513,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
 
       /* ---- smoothness cost of the updated trajectory (chomp.c:660-671) ---- */
       ssum = 0.0;
-      for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t);
+      for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t, Pp, P, n);
       block_sum2(csum, ssum, red, red_parity);
       cost_obs = csum * inv_m;
       cost_smooth = ssum + trC;
@@ -611,21 +612,21 @@ __global__ void best_kernel(const double *costs, const int *status, int R, int *
 
 extern "C" size_t ocb_chomp_smem_bytes(const OcbChompArgs *a)
 {
-   return (size_t) smem_layout(*a).bytes;
+   return (size_t) smem_layout(*a, a->Ppad, a->n).bytes;
 }
 
-template <int NT_MAX, bool FLOAT>
+template <int NT_MAX, bool FLOAT, int PP, int NN>
 static cudaError_t launch_variant(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    static size_t configured = 0;
    if (smem_bytes > configured)
    {
-      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel<NT_MAX, FLOAT>,
+      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
       if (e != cudaSuccess) return e;
       configured = smem_bytes;
    }
-   chomp_iterate_kernel<NT_MAX, FLOAT><<<args->R, threads, smem_bytes, st>>>(*args);
+   chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN><<<args->R, threads, smem_bytes, st>>>(*args);
    return cudaGetLastError();
 }
 
@@ -633,10 +634,21 @@ extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_by
 {
    if (threads > 256 || threads % 32) return cudaErrorInvalidValue;
    if (args->floating)
-      return threads <= 128 ? launch_variant<128, true>(args, smem_bytes, threads, st)
-                            : launch_variant<256, true>(args, smem_bytes, threads, st);
-   return threads <= 128 ? launch_variant<128, false>(args, smem_bytes, threads, st)
-                         : launch_variant<256, false>(args, smem_bytes, threads, st);
+      return threads <= 128 ? launch_variant<128, true, 0, 0>(args, smem_bytes, threads, st)
+                            : launch_variant<256, true, 0, 0>(args, smem_bytes, threads, st);
+   /* the common trajectory shapes -- n_points 100 (BASELINE), 101 (the reference's default,
+    * mod.cpp:1840) and 256, seven dofs -- with P and n as compile-time constants: every
+    * [item][waypoint] shared-memory address becomes base + immediate and the dof loops unroll
+    * (+15 % on config 2; one third of the generic kernel's instructions is address arithmetic).
+    * Same source, same floating-point operations, so results do not depend on the variant. */
+   if (args->Ppad == args->P && args->n == 7)
+   {
+      if (args->P == 100 && threads <= 128) return launch_variant<128, false, 100, 7>(args, smem_bytes, threads, st);
+      if (args->P == 101 && threads <= 128) return launch_variant<128, false, 101, 7>(args, smem_bytes, threads, st);
+      if (args->P == 256 && threads == 256) return launch_variant<256, false, 256, 7>(args, smem_bytes, threads, st);
+   }
+   return threads <= 128 ? launch_variant<128, false, 0, 0>(args, smem_bytes, threads, st)
+                         : launch_variant<256, false, 0, 0>(args, smem_bytes, threads, st);
 }
 
 extern "C" cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const double *q_goal,

@@ -463,7 +463,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
    if (final_pass)
    {
       double ssum = 0.0, zero = 0.0;
-      for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t);
+      for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t, Pp, P, n);
       block_sum2(ssum, zero, red, red_parity);
       if (tid == 0)
       {
@@ -526,14 +526,14 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
             const double *Tj = Ts + j * Pp;
             double g = go[(size_t) (t - 1) * n + j] * inv_m;
             if (a.grad_mode == 2) a.grad_out[((size_t) run * m + (t - 1)) * n + j] = g;
-            g += band_AT(a, Tj, t) + (bi * Tj[0] + bf * Tj[P - 1]);
+            g += band_AT(a, Tj, t, m) + (bi * Tj[0] + bf * Tj[P - 1]);
             Gs[j * Pp + t] = g;
             if (a.grad_mode == 1) a.grad_out[((size_t) run * m + (t - 1)) * n + j] = g;
          }
       }
    }
    __syncthreads();
-   if (tid < n) band_solve(a, Gs + tid * Pp + 1);
+   if (tid < n) band_solve(a, Gs + tid * Pp + 1, m);
    __syncthreads();
 
    /* ---- momentum / plain update (chomp.c:525-548, 604-605) ---- */
@@ -555,7 +555,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
          }
    }
    const int any_violation = __syncthreads_or(violated);
-   const bool ok = !any_violation || project_joint_limits(a, Ts, Gs, red, ired);
+   const bool ok = !any_violation || project_joint_limits(a, Ts, Gs, red, ired, Pp, m, n);
 
    /* the reference has already moved the trajectory when it gives up (chomp.c:651-655) */
    __syncthreads();
@@ -574,7 +574,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
 
    /* ---- smoothness cost of the updated trajectory (chomp.c:660-671) ---- */
    double ssum = 0.0, zero = 0.0;
-   for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t);
+   for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t, Pp, P, n);
    block_sum2(ssum, zero, red, red_parity);
    if (a.floating)
    {
