@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--runs", type=int, default=RUNS_PER_GPU, help="runs per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sdf", action="store_true", help="skip the secondary SDF-build measurement")
+    ap.add_argument("--no-jit", action="store_true", help="use the library's own kernel instead of the run-time specialised one")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -297,6 +298,10 @@ def main():
     starts[:], goals[:] = s_all[lo:hi], g_all[lo:hi]
 
     eng = Engine(local_rank)
+    if not args.no_jit:
+        # the engine's run-time specialisation (ocb_engine_enable_jit): the kernel is compiled once for
+        # this batch shape during set-up, outside every timed region, and cached
+        eng.enable_jit(True)
     # a real (non-default) stream shared by torch and the engine, so torch.cuda.Event sees the kernels
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
@@ -306,6 +311,7 @@ def main():
     sd = capi.SdfDesc(sdf, lengths, pose_world)
     sid = eng.upload_sdf(sd)
     batch = eng.create_batch(robot, params, [sid], starts, goals)
+    kernel_kind = "run-time specialised (NVRTC)" if batch.uses_jit() else "library instantiation"
     P, n = params.n_points, robot.n_dof
     d_traj, d_costs = batch.device_ptrs()
 
@@ -366,13 +372,17 @@ def main():
     out_traj = torch.empty((R, P, n), dtype=torch.float64, pin_memory=True).numpy()
     starts_h = torch.from_numpy(np.ascontiguousarray(starts)).pin_memory().numpy()
     goals_h = torch.from_numpy(np.ascontiguousarray(goals)).pin_memory().numpy()
+    def e2e_step():
+        b2 = eng.create_batch(robot, params, [sid], starts_h, goals_h)
+        b2.iterate(N_ITER)
+        b2.get_traj(out_traj)
+        b2.close()
+    e2e_step()  # warm-up (untimed), as for the device-timed steps
+    torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        b2 = eng.create_batch(robot, params, [sid], starts_h, goals_h)
-        c2, s2 = b2.iterate(N_ITER)
-        b2.get_traj(out_traj)
-        b2.close()
+        e2e_step()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device=device)
@@ -425,7 +435,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(world), "clocks": clocks,
+            "config": dict(config_dict(world), kernel=kernel_kind), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "create+iterate+gettraj+destroy through the C ABI, pinned host buffers, wall clock"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

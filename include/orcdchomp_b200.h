@@ -21,7 +21,9 @@
 #ifndef ORCDCHOMP_B200_H
 #define ORCDCHOMP_B200_H
 
+#ifndef __CUDACC_RTC__ /* the kernels are also compiled at run time (NVRTC), without host headers */
 #include <stddef.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -122,6 +124,12 @@ int ocb_engine_destroy(ocb_engine *e);
 /* Make the engine launch on a caller stream (cudaStream_t as void*; NULL = own). */
 int ocb_engine_set_stream(ocb_engine *e, void *cuda_stream);
 int ocb_engine_sync(ocb_engine *e);
+/* Run-time specialisation: batches created while this is on get the persistent kernel compiled
+ * (NVRTC, once per configuration, ~2 s, cached for the life of the process) with their sizes --
+ * waypoints, dofs, spheres, joint frames, fields, mode flags -- as literal constants.  Same
+ * source and arithmetic as the library's own kernel, fewer integer instructions.  Off by
+ * default; if NVRTC is missing the library's kernel is used and ocb_last_error() says why. */
+int ocb_engine_enable_jit(ocb_engine *e, int on);
 
 /* --- SDF residency (replaces mod::sdfs[], mod.cpp:584-586 / 716-718 / 836) --- */
 /* copies the grid to HBM; *id indexes it in later calls */
@@ -248,6 +256,7 @@ int ocb_batch_get_gradient(ocb_batch *b, double *G);
 int ocb_batch_best(ocb_batch *b, int *best_run, double *best_cost);
 int ocb_batch_destroy(ocb_batch *b);
 /* sizes for callers that allocate outputs */
+int ocb_batch_uses_jit(const ocb_batch *b);   /* 1 when this batch runs a run-time specialised kernel */
 int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof);
 /* device pointers (HBM) of the trajectory [R][n_points][n_dof] and costs [R][3],
  * for callers that keep everything resident (bench, NCCL gather)              */

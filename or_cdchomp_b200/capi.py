@@ -245,6 +245,8 @@ EXPORTS = {
     "ocb_engine_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "ocb_engine_destroy": (C.c_int, [C.c_void_p]),
     "ocb_engine_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocb_engine_enable_jit": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocb_batch_uses_jit": (C.c_int, [C.c_void_p]),
     "ocb_engine_sync": (C.c_int, [C.c_void_p]),
     "ocb_sdf_upload": (C.c_int, [C.c_void_p, C.POINTER(OcbSdf), c_int_p]),
     "ocb_sdf_adopt_device": (C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p, C.c_void_p, c_int_p]),

@@ -28,6 +28,16 @@
  */
 #include "chomp_device.cuh"
 
+/* Sizes of the compiled robot and the mode flags: kernel arguments in the library's own
+ * instantiations, literal constants when the kernel is compiled at run time for one batch
+ * (ocb_jit.cpp passes -DOCB_JIT -DOCB_JIT_nsa=15 ...): loop bounds, table strides and the
+ * workspace carve-up then fold into immediates. */
+#ifdef OCB_JIT
+#define DIM(a, f) (OCB_JIT_##f)
+#else
+#define DIM(a, f) ((a).f)
+#endif
+
 namespace
 {
 
@@ -46,16 +56,16 @@ __host__ __device__ inline SmemLayout smem_layout(const OcbChompArgs &a, const i
    int d = 0;
    l.T = d; d += n * Pp;
    l.G = d; d += n * Pp;
-   l.AG = d; d += a.use_momentum ? n * Pp : 0;
+   l.AG = d; d += DIM(a, use_momentum) ? n * Pp : 0;
    l.red = d; d += 36;
    l.ws = d; d += (int) a.ws_stride;
-   l.cut2 = d; d += a.nsa * (a.NAp + a.nsi);
-   l.radius = d; d += a.nsa + a.nsi;
+   l.cut2 = d; d += DIM(a, nsa) * (DIM(a, NAp) + DIM(a, nsi));
+   l.radius = d; d += DIM(a, nsa) + DIM(a, nsi);
    int b = d * 8;
-   l.sdf = b; b += a.nsdf * (int) sizeof(OcbSdfDev);
-   l.sph = b; b += a.nsa * (int) sizeof(OcbSphereDev);
-   l.desc = b; b += a.n_desc * 4;
-   l.mt = b; b += a.use_hmc ? (626 + 626 + 16) * 4 : 0; /* state, saved copy (serial fallback), scratch */
+   l.sdf = b; b += DIM(a, nsdf) * (int) sizeof(OcbSdfDev);
+   l.sph = b; b += DIM(a, nsa) * (int) sizeof(OcbSphereDev);
+   l.desc = b; b += DIM(a, n_desc) * 4;
+   l.mt = b; b += DIM(a, use_hmc) ? (626 + 626 + 16) * 4 : 0; /* state, saved copy (serial fallback), scratch */
    l.ired = b; b += 40 * 4;
    l.bytes = b;
    return l;
@@ -78,12 +88,12 @@ __device__ __forceinline__ void fk_waypoint(const OcbChompArgs &a, const Tables 
                                             const double *__restrict__ Ts, double *__restrict__ ws, int t)
 {
    const int Pp = PP ? PP : a.Ppad;
-   double *slots = ws + 3 * a.nsa * Pp;
+   double *slots = ws + 3 * DIM(a, nsa) * Pp;
    double R[9], tr[3], ax[3], org[3];
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
-   for (int j = 0; j < a.nj; j++)
+   for (int j = 0; j < DIM(a, nj); j++)
    {
       const OcbJointDev &J = a.joints[j];
       fk_step<true, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
@@ -110,13 +120,13 @@ __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tabl
                                                double *__restrict__ Gs, int t)
 {
    const int Pp = PP ? PP : a.Ppad;
-   double *slots = ws + 3 * a.nsa * Pp;
-   const double *Wg = ws + (3 * a.nsa + 12 * a.n_slots) * Pp + t;
+   double *slots = ws + 3 * DIM(a, nsa) * Pp;
+   const double *Wg = ws + (3 * DIM(a, nsa) + 12 * DIM(a, n_slots)) * Pp + t;
    double R[9], tr[3], ax[3], org[3];
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
-   for (int j = 0; j < a.nj; j++)
+   for (int j = 0; j < DIM(a, nj); j++)
    {
       const OcbJointDev &J = a.joints[j];
       fk_step<false, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
@@ -143,7 +153,7 @@ __device__ __forceinline__ void flush_wrenches(const OcbChompArgs &a, const Tabl
    {
       /* the base pose sees the total wrench of the waypoint */
       double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
-      for (int g = 0; g < a.ng; g++)
+      for (int g = 0; g < DIM(a, ng); g++)
       {
          const double *Wo = Wg + 6 * g * Pp;
          F[0] += Wo[0]; F[1] += Wo[Pp]; F[2] += Wo[2 * Pp];
@@ -170,18 +180,18 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
                                                 int t, bool want_grad)
 {
    const int Pp = PP ? PP : a.Ppad;
-   const int nsa = a.nsa;
-   const int row = a.NAp + a.nsi;
-   double *Wg = ws + (3 * nsa + 12 * a.n_slots) * Pp + t;
+   const int nsa = DIM(a, nsa);
+   const int row = DIM(a, NAp) + DIM(a, nsi);
+   double *Wg = ws + (3 * nsa + 12 * DIM(a, n_slots)) * Pp + t;
    const double inv2dt = 1.0 / (2.0 * a.dt);
    const double invdt2 = 1.0 / (a.dt * a.dt);
    const double es = a.eps_self, inv_es = 1.0 / es, half_inv_es = 0.5 / es;
    double cost = 0.0;
 
    if (want_grad)
-      for (int k = 0; k < 6 * a.ng; k++) Wg[k * Pp] = 0.0;
+      for (int k = 0; k < 6 * DIM(a, ng); k++) Wg[k * Pp] = 0.0;
 
-   for (int j = 0; j < a.nj; j++)
+   for (int j = 0; j < DIM(a, nj); j++)
    {
       const OcbJointDev &J = a.joints[j];
       if (J.sph_begin == J.sph_end) continue;
@@ -303,12 +313,12 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
             }
          }
          /* inactive partners are frozen in the world (mod.cpp:2332-2345) */
-         for (int i = 0; i < a.nsi; i++)
+         for (int i = 0; i < DIM(a, nsi); i++)
          {
             const double q[3] = {__ldg(a.inactive_pos + 3 * i), __ldg(a.inactive_pos + 3 * i + 1),
                                  __ldg(a.inactive_pos + 3 * i + 2)};
             const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
-            if (dx * dx + dy * dy + dz * dz <= crow[a.NAp + i]) in_range(q, nullptr, nsa + i);
+            if (dx * dx + dy * dy + dz * dz <= crow[DIM(a, NAp) + i]) in_range(q, nullptr, nsa + i);
          }
          cost += cost_s;
          if (want_grad)
@@ -330,9 +340,8 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
    return cost;
 }
 
-template <int NT_MAX, bool FLOAT, int PP, int NN>
-__global__ void __launch_bounds__(NT_MAX, (NT_MAX == 128 && !FLOAT) ? 3 : 1)
-chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
+template <bool FLOAT, int PP, int NN>
+__device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
    const int tid = threadIdx.x;
@@ -358,36 +367,36 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       double *c2 = sd + lay.cut2, *rad = sd + lay.radius;
       OcbSphereDev *sph = reinterpret_cast<OcbSphereDev *>(smem_raw + lay.sph);
       int *dsc = reinterpret_cast<int *>(smem_raw + lay.desc);
-      for (int e = tid; e < a.nsa * (a.NAp + a.nsi); e += NT) c2[e] = __ldg(a.cut2 + e);
-      for (int e = tid; e < a.nsa + a.nsi; e += NT) rad[e] = __ldg(a.radius + e);
+      for (int e = tid; e < DIM(a, nsa) * (DIM(a, NAp) + DIM(a, nsi)); e += NT) c2[e] = __ldg(a.cut2 + e);
+      for (int e = tid; e < DIM(a, nsa) + DIM(a, nsi); e += NT) rad[e] = __ldg(a.radius + e);
       {
-         const int words = a.nsa * (int) (sizeof(OcbSphereDev) / 4);
+         const int words = DIM(a, nsa) * (int) (sizeof(OcbSphereDev) / 4);
          const uint32_t *src = reinterpret_cast<const uint32_t *>(a.spheres);
          uint32_t *dst = reinterpret_cast<uint32_t *>(sph);
          for (int e = tid; e < words; e += NT) dst[e] = __ldg(src + e);
       }
-      for (int e = tid; e < a.n_desc; e += NT) dsc[e] = __ldg(a.desc + e);
+      for (int e = tid; e < DIM(a, n_desc); e += NT) dsc[e] = __ldg(a.desc + e);
       tb.sph = sph; tb.desc = dsc; tb.cut2 = c2; tb.radius = rad;
    }
 
    /* ---- stage per-run state and shared constants ---- */
    double *traj = a.traj + (size_t) run * P * n;
    for (int e = tid; e < P * n; e += NT) Ts[(e % n) * Pp + (e / n)] = traj[e];
-   if (a.use_momentum)
+   if (DIM(a, use_momentum))
    {
       const double *ag = a.AG + (size_t) run * m * n;
       for (int e = tid; e < m * n; e += NT) AGs[(e % n) * Pp + (e / n) + 1] = ag[e];
    }
    {
-      const int words = (int) (sizeof(OcbSdfDev) / 4) * a.nsdf;
+      const int words = (int) (sizeof(OcbSdfDev) / 4) * DIM(a, nsdf);
       const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sdfs);
       uint32_t *dst = reinterpret_cast<uint32_t *>(sdfs);
       for (int e = tid; e < words; e += NT) dst[e] = src[e];
    }
-   if (a.use_hmc)
+   if (DIM(a, use_hmc))
       for (int e = tid; e < 625; e += NT) mts[e] = a.mt_state[(size_t) run * 625 + e];
-   int leapfrog_first = a.use_momentum ? a.leapfrog_first[run] : 0;
-   int hmc_next = a.use_hmc ? a.hmc_next[run] : -1;
+   int leapfrog_first = DIM(a, use_momentum) ? a.leapfrog_first[run] : 0;
+   int hmc_next = DIM(a, use_hmc) ? a.hmc_next[run] : -1;
    int status = 0;
    const double inv_m = 1.0 / m;
    const double inv_lambda = 1.0 / a.lambda;
@@ -412,7 +421,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
       const bool final_pass = (iter == a.n_iter);
 
       /* ---- HMC momentum resample (mod.cpp:2755-2768) ---- */
-      if (a.use_hmc && !final_pass && iter == hmc_next)
+      if (DIM(a, use_hmc) && !final_pass && iter == hmc_next)
       {
          const double alpha = 100.0 * exp(0.02 * iter);
          const double sigma = 1.0 / sqrt(alpha);
@@ -421,7 +430,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
          for (int e = tid; e < 625; e += NT) saved[e] = mts[e];
          __syncthreads();
          double u = 0.0;
-         if (a.use_hmc == 2 || !hmc_resample_parallel(mts, scratch, AGs, Pp, m, n, sigma, &u))
+         if (DIM(a, use_hmc) == 2 || !hmc_resample_parallel(mts, scratch, AGs, Pp, m, n, sigma, &u))
          {
             /* a zero word was drawn (or use_hmc == 2, the test hook that forces this path): redo this
              * resample serially, with the exact gsl_rng_uniform_pos semantics */
@@ -491,7 +500,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
             for (int j = 0; j < n; j++)
             {
                double step = Gs[j * Pp + t];
-               if (a.use_momentum)
+               if (DIM(a, use_momentum))
                {
                   step = fma(coef, step, AGs[j * Pp + t]);
                   AGs[j * Pp + t] = step;
@@ -500,7 +509,7 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
                Ts[j * Pp + t] = q;
                violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
             }
-         if (a.use_momentum) leapfrog_first = 0;
+         if (DIM(a, use_momentum)) leapfrog_first = 0;
       }
       const int any_violation = __syncthreads_or(violated);
 
@@ -536,23 +545,32 @@ chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
    /* ---- write the run back ---- */
    __syncthreads();
    for (int e = tid; e < P * n; e += NT) traj[e] = Ts[(e % n) * Pp + (e / n)];
-   if (a.use_momentum)
+   if (DIM(a, use_momentum))
    {
       double *ag = a.AG + (size_t) run * m * n;
       for (int e = tid; e < m * n; e += NT) ag[e] = AGs[(e % n) * Pp + (e / n) + 1];
    }
-   if (a.use_hmc)
+   if (DIM(a, use_hmc))
       for (int e = tid; e < 625; e += NT) a.mt_state[(size_t) run * 625 + e] = mts[e];
    if (tid == 0)
    {
-      if (a.use_momentum) a.leapfrog_first[run] = leapfrog_first;
-      if (a.use_hmc) a.hmc_next[run] = hmc_next;
+      if (DIM(a, use_momentum)) a.leapfrog_first[run] = leapfrog_first;
+      if (DIM(a, use_hmc)) a.hmc_next[run] = hmc_next;
       a.costs[(size_t) run * 3 + 0] = cost_obs + cost_smooth;
       a.costs[(size_t) run * 3 + 1] = cost_obs;
       a.costs[(size_t) run * 3 + 2] = cost_smooth;
       a.status[run] = status;
    }
 }
+
+#ifndef OCB_JIT
+template <int NT_MAX, bool FLOAT, int PP, int NN>
+__global__ void __launch_bounds__(NT_MAX, (NT_MAX == 128 && !FLOAT) ? 3 : 1)
+chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
+{
+   chomp_iterate_body<FLOAT, PP, NN>(a);
+}
+#endif
 
 /* straight-line initial trajectory, evaluated exactly as mod.cpp:2456-2458:
  * traj[i] = q_s + ((q_g - q_s) * i) / (P-1), every operation rounded on its own */
@@ -609,6 +627,16 @@ __global__ void best_kernel(const double *costs, const int *status, int R, int *
 }
 
 } /* namespace */
+
+#ifdef OCB_JIT
+/* the one entry point of a run-time compiled instance */
+extern "C" __global__ void __launch_bounds__(OCB_JIT_NT, OCB_JIT_MINBLOCKS)
+chomp_iterate_jit(const __grid_constant__ OcbChompArgs a)
+{
+   chomp_iterate_body<OCB_JIT_FLOAT != 0, OCB_JIT_PP, OCB_JIT_NN>(a);
+}
+#else
+
 
 extern "C" size_t ocb_chomp_smem_bytes(const OcbChompArgs *a)
 {
@@ -675,3 +703,5 @@ extern "C" cudaError_t ocb_launch_best(const double *costs, const int *status, i
    best_kernel<<<1, 1024, 0, st>>>(costs, status, R, best_run, best_cost);
    return cudaGetLastError();
 }
+
+#endif /* !OCB_JIT */

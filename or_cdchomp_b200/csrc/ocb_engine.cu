@@ -203,8 +203,10 @@ struct ocb_engine
    size_t scratch_bytes = 0;
    long launches = 0;
    int smem_optin = 0;
+   int smem_per_sm = 0;
    int sm_count = 0;
    int force_general_sdf = 0; /* test hook: always take the general fp64 distance transform */
+   int jit = 0;               /* compile the persistent kernel per batch configuration (ocb_jit.cpp) */
    /* every device buffer of batches, resident SDFs and host-call temporaries comes from this
     * stream-ordered pool, which keeps what it is given back: create / destroy of a batch costs
     * microseconds and never synchronises the device (cudaMalloc / cudaFree took 1 - 300 ms per
@@ -261,6 +263,7 @@ extern "C" int ocb_engine_create(int device, ocb_engine **out)
    if (!e) return fail(OCB_ERR_ALLOC, "out of host memory");
    e->device = device;
    e->smem_optin = (int) prop.sharedMemPerBlockOptin;
+   e->smem_per_sm = (int) prop.sharedMemPerMultiprocessor;
    e->sm_count = prop.multiProcessorCount;
    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess)
    {
@@ -318,6 +321,13 @@ extern "C" int ocb_engine_sync(ocb_engine *e)
 }
 
 extern "C" long ocb_engine_launch_count(const ocb_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int ocb_engine_enable_jit(ocb_engine *e, int on)
+{
+   if (!e) return fail(OCB_ERR_ARG, "null engine");
+   e->jit = on ? 1 : 0;
+   return OCB_OK;
+}
 
 extern "C" int ocb_engine_force_general_sdf(ocb_engine *e, int on)
 {
@@ -718,6 +728,7 @@ struct ocb_batch
    int threads = 128;
    size_t smem = 0;
    size_t tile_smem = 0, run_smem = 0; /* tiled path (args.tiled) */
+   void *jit_kernel = nullptr;         /* run-time specialised persistent kernel, when the engine asks for it */
    int trace_cap = 0; /* iterations the trace buffer can hold */
    int last_n_iter = 0;
    std::vector<void *> owned; /* device allocations to free */
@@ -1282,6 +1293,18 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       TRY(batch_alloc(b, &a.tile_cost, R * a.n_tiles));
    }
    b->threads = std::min(256, ((P + 31) / 32) * 32);
+   if (e->jit && !a.tiled)
+   {
+      /* blocks per SM the shared memory allows, not more than ~160 registers per thread can feed */
+      int min_blocks = (int) ((size_t) e->smem_per_sm / (b->smem + 1024));
+      min_blocks = std::max(1, std::min(min_blocks, 65536 / (b->threads * 160)));
+      char why[512] = "";
+      if (ocb_jit_chomp_kernel(&a, e->device, b->threads, min_blocks, b->smem, &b->jit_kernel, why, sizeof(why)) != 0)
+      {
+         b->jit_kernel = nullptr; /* the library's own kernel runs instead */
+         fail(OCB_ERR_CUDA, "run-time specialisation unavailable: %s", why);
+      }
+   }
    err = cudaStreamSynchronize(e->stream);
    if (err != cudaSuccess)
    {
@@ -1292,6 +1315,8 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    *out = b;
    return OCB_OK;
 }
+
+extern "C" int ocb_batch_uses_jit(const ocb_batch *b) { return (b && b->jit_kernel) ? 1 : 0; }
 
 extern "C" int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof)
 {
@@ -1422,7 +1447,10 @@ extern "C" int ocb_batch_iterate_async(ocb_batch *b, int n_iter)
       CU(ocb_launch_chomp_tiled(&a, b->tile_smem, b->run_smem, 256, b->e->stream, &b->e->launches));
       return OCB_OK;
    }
-   CU(ocb_launch_chomp(&a, b->smem, b->threads, b->e->stream));
+   if (b->jit_kernel)
+      CU(ocb_jit_launch(b->jit_kernel, &a, b->threads, b->smem, b->e->stream));
+   else
+      CU(ocb_launch_chomp(&a, b->smem, b->threads, b->e->stream));
    b->e->launches++;
    return OCB_OK;
 }

@@ -3,9 +3,15 @@
 #ifndef OCB_INTERNAL_H
 #define OCB_INTERNAL_H
 
+#ifdef __CUDACC_RTC__
+/* run-time compilation of the CHOMP kernel (ocb_jit.cpp): no host headers */
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #define OCB_MAX_JOINTS 24   /* moving joints carried in kernel-parameter (constant) space */
 #define OCB_MAX_SDFS 64  /* descriptors are staged in shared memory */
@@ -103,12 +109,17 @@ struct OcbChompArgs
    size_t ws_stride;      /* doubles of per-run workspace in shared memory (persistent kernel) */
 };
 
+#ifndef __CUDACC_RTC__
 #ifdef __cplusplus
 extern "C" {
 #endif
 /* kernels' host launchers (defined in the .cu files) */
 cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st);
 size_t ocb_chomp_smem_bytes(const OcbChompArgs *args);
+/* ocb_jit.cpp: the persistent kernel compiled at run time for one batch's sizes */
+int ocb_jit_chomp_kernel(const OcbChompArgs *args, int device, int threads, int min_blocks, size_t smem,
+                         void **kernel_out, char *err, size_t err_cap);
+cudaError_t ocb_jit_launch(void *kernel, const OcbChompArgs *args, int threads, size_t smem, cudaStream_t st);
 /* chomp_tiled.cu */
 size_t ocb_tile_smem_bytes(const OcbChompArgs *args, int tile_w);
 size_t ocb_run_update_smem_bytes(const OcbChompArgs *args);
@@ -144,5 +155,6 @@ size_t ocb_flood_scratch_bytes(const int sizes[3]);
 #ifdef __cplusplus
 }
 #endif
+#endif /* !__CUDACC_RTC__ */
 
 #endif

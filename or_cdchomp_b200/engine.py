@@ -31,6 +31,10 @@ class Engine:
         self.h = h
         self.device = device
 
+    def enable_jit(self, on=True):
+        """compile the persistent kernel per batch configuration (ocb_engine_enable_jit)"""
+        check(self.lib, self.lib.ocb_engine_enable_jit(self.h, 1 if on else 0), "ocb_engine_enable_jit")
+
     # -- SDF residency -----------------------------------------------------
     def upload_sdf(self, sdf_desc):
         sid = C.c_int()
@@ -170,6 +174,9 @@ class Batch:
                                                  ids.ctypes.data_as(c_int_p), self.R, dptr(q_start), dptr(q_goal),
                                                  sp, C.byref(h)), "ocb_batch_create")
         self.h = h
+
+    def uses_jit(self):
+        return bool(self.lib.ocb_batch_uses_jit(self.h))
 
     def reset(self, q_start=None, q_goal=None, seeds=None):
         """Re-arm the batch (straight lines, zero momentum, fresh rng); async."""

@@ -10,14 +10,16 @@ obs, sdf = eng.computedistancefield(gprims, sizes, lengths, 0.02)
 sid = eng.upload_sdf(capi.SdfDesc(sdf, lengths, pose_world))
 R, P, n = 4096, 100, 7
 starts, goals = models.random_endpoints(robot, R)
-def leg(out, s, g, tag):
-    for rep in range(3):
-        t0 = time.perf_counter(); b = eng.create_batch(robot, params, [sid], s, g); t1 = time.perf_counter()
+out = torch.empty((R, P, n), dtype=torch.float64, pin_memory=True).numpy()
+def leg(tag):
+    for rep in range(4):
+        t0 = time.perf_counter(); b = eng.create_batch(robot, params, [sid], starts, goals); t1 = time.perf_counter()
         b.iterate(100); t2 = time.perf_counter()
         b.get_traj(out); t3 = time.perf_counter()
         b.close(); t4 = time.perf_counter()
-        print("%s: create %.2f iterate %.2f gettraj %.2f destroy %.2f total %.2f ms" % ((tag,) + tuple(1e3 * x for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0))))
-leg(np.empty((R, P, n)), starts, goals, "pageable")
-out = torch.empty((R, P, n), dtype=torch.float64, pin_memory=True).numpy()
-leg(out, torch.from_numpy(starts.copy()).pin_memory().numpy(), torch.from_numpy(goals.copy()).pin_memory().numpy(), "pinned  ")
-leg(np.empty((R, P, n)), starts, goals, "pageable")
+        print("%s: create %.2f iterate %.2f gettraj %.2f destroy %.2f total %.2f ms (jit %s)" % ((tag,) + tuple(1e3 * x for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0)) + (b.uses_jit(),)))
+leg("static")
+eng.enable_jit(True)
+leg("jit   ")
+eng.enable_jit(False)
+leg("static")

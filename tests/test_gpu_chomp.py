@@ -528,3 +528,36 @@ def test_smallest_trajectories(engine, oracle, flavour, wam7, table):
             run.close()
         b.close()
     engine.remove_sdf(sid)
+
+
+def test_runtime_specialised_kernel_is_bit_identical(oracle, flavour, wam7, table):
+    """ocb_engine_enable_jit: the persistent kernel compiled by NVRTC with the batch's sizes as
+    constants gives bit-identical trajectories, costs and momentum to the library's own kernel
+    (same source, same floating-point operations), for plain, momentum + HMC, odd sizes and a
+    floating base."""
+    from or_cdchomp_b200.engine import Engine
+    eng = Engine(0)
+    sid = eng.upload_sdf(table["desc"])
+    cases = [(dict(n_points=100, lambda_=100.0, obs_factor=500.0), 6, False),
+             (dict(n_points=37, lambda_=100.0, obs_factor=300.0, use_momentum=1, use_hmc=1, hmc_resample_lambda=0.2), 5, False),
+             (dict(n_points=50, lambda_=100.0, obs_factor=300.0, floating_base=1), 3, True)]
+    for kw, R, floating in cases:
+        params = capi.default_params(**kw)
+        if floating:
+            qs, qg = _floating_endpoints(wam7, R, 3)
+        else:
+            qs, qg = models.random_endpoints(wam7, R, seed0=123, shrink=0.3)
+        seeds = np.arange(1, R + 1)
+        out = []
+        for jit in (False, True):
+            eng.enable_jit(jit)
+            b = eng.create_batch(wam7, params, [sid], qs, qg, seeds=seeds)
+            assert b.uses_jit() == jit, eng.lib.ocb_last_error()
+            costs, status = b.iterate(25)
+            out.append((b.get_traj(), costs, status))
+            b.close()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        assert np.array_equal(out[0][2], out[1][2])
+    eng.enable_jit(False)
+    eng.remove_sdf(sid)
+    eng.close()
