@@ -668,7 +668,7 @@ extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_by
     * mod.cpp:1840) and 256, seven dofs -- with P and n as compile-time constants: every
     * [item][waypoint] shared-memory address becomes base + immediate and the dof loops unroll
     * (+15 % on config 2; one third of the generic kernel's instructions is address arithmetic).
-    * Same source, same floating-point operations, so results do not depend on the variant. */
+    * Same source and arithmetic; variants agree up to the compiler's choice of fused multiply-adds. */
    if (args->Ppad == args->P && args->n == 7)
    {
       if (args->P == 100 && threads <= 128) return launch_variant<128, false, 100, 7>(args, smem_bytes, threads, st);

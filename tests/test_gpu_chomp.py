@@ -530,11 +530,11 @@ def test_smallest_trajectories(engine, oracle, flavour, wam7, table):
     engine.remove_sdf(sid)
 
 
-def test_runtime_specialised_kernel_is_bit_identical(oracle, flavour, wam7, table):
+def test_runtime_specialised_kernel_agrees_with_library_kernel(oracle, flavour, wam7, table):
     """ocb_engine_enable_jit: the persistent kernel compiled by NVRTC with the batch's sizes as
-    constants gives bit-identical trajectories, costs and momentum to the library's own kernel
-    (same source, same floating-point operations), for plain, momentum + HMC, odd sizes and a
-    floating base."""
+    constants computes the same thing as the library's own kernel -- same source, so the only
+    differences are the compiler's choices of fused multiply-adds (observed: <= 4e-15 rad) --
+    and is itself reproducible run to run; plain, momentum + HMC with odd sizes, floating base."""
     from or_cdchomp_b200.engine import Engine
     eng = Engine(0)
     sid = eng.upload_sdf(table["desc"])
@@ -549,15 +549,17 @@ def test_runtime_specialised_kernel_is_bit_identical(oracle, flavour, wam7, tabl
             qs, qg = models.random_endpoints(wam7, R, seed0=123, shrink=0.3)
         seeds = np.arange(1, R + 1)
         out = []
-        for jit in (False, True):
+        for jit in (False, True, True):
             eng.enable_jit(jit)
             b = eng.create_batch(wam7, params, [sid], qs, qg, seeds=seeds)
             assert b.uses_jit() == jit, eng.lib.ocb_last_error()
             costs, status = b.iterate(25)
             out.append((b.get_traj(), costs, status))
             b.close()
-        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
         assert np.array_equal(out[0][2], out[1][2])
+        assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-11, kw
+        assert np.allclose(out[0][1], out[1][1], rtol=1e-11, atol=0), kw
+        assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1], out[2][1]), kw
     eng.enable_jit(False)
     eng.remove_sdf(sid)
     eng.close()
