@@ -129,7 +129,8 @@ int ocb_engine_sync(ocb_engine *e);
  * waypoints, dofs, spheres, joint frames, fields, mode flags -- as literal constants.  Same
  * source and arithmetic as the library's own kernel (results agree to ~1e-15), fewer integer
  * instructions.  Off by
- * default; if NVRTC is missing the library's kernel is used and ocb_last_error() says why. */
+ * default (environment variable OCB_JIT=1 turns it on for every engine); if NVRTC is missing
+ * the library's kernel is used and ocb_last_error() says why. */
 int ocb_engine_enable_jit(ocb_engine *e, int on);
 
 /* --- SDF residency (replaces mod::sdfs[], mod.cpp:584-586 / 716-718 / 836) --- */

@@ -283,6 +283,10 @@ extern "C" int ocb_engine_create(int device, ocb_engine **out)
       delete e;
       return fail(OCB_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
    }
+   {
+      const char *env = getenv("OCB_JIT"); /* OCB_JIT=1: run-time specialisation on for every engine */
+      e->jit = (env && env[0] && env[0] != '0') ? 1 : 0;
+   }
    unsigned long long keep = ~0ull; /* never hand memory back to the driver between batches */
    cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep);
    *out = e;
