@@ -365,6 +365,12 @@ def main():
     step_ms, kern_ms = float(t[0]), float(t[1])
     costs, status = batch.get_costs()
     n_failed = int((status != 0).sum())
+    # run-iterations actually performed per step: a run that leaves the joint limits stops there, as in
+    # the reference (mod.cpp:2799-2803); the CPU arms count the same way
+    done = torch.tensor([int(batch.get_iterations().sum())], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(done, op=dist.ReduceOp.SUM)
+    run_iters_done = float(done[0])
 
     # ---- end to end through the C ABI with host buffers ----
     e2e_steps = max(2, min(args.steps, 3))
@@ -389,7 +395,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te[0])
-    e2e_value = total_runs * N_ITER * e2e_steps / t_e2e
+    e2e_value = run_iters_done * e2e_steps / t_e2e
     h2d = 2 * R * n * 8
     d2h = R * P * n * 8 + R * 3 * 8 + R * 4
 
@@ -398,7 +404,7 @@ def main():
     if rank == 0 and not args.no_sdf:
         sdf_build = measure_sdf_build(eng, stream, device)
 
-    run_iters_per_step = total_runs * N_ITER
+    run_iters_per_step = run_iters_done
     value = run_iters_per_step * args.steps / (step_ms * 1e-3)
 
     if rank == 0:
@@ -411,7 +417,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         abytes = algorithmic_bytes_per_run_iter(P, n, robot.n_spheres_active, 1, False)
         launch_s = (kern_ms * 1e-3) / args.steps
-        achieved = abytes * R * N_ITER / launch_s / 1e9
+        achieved = abytes * (run_iters_done / world) / launch_s / 1e9  # units one launch processed (this GPU's share)
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -439,7 +445,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "create+iterate+gettraj+destroy through the C ABI, pinned host buffers, wall clock"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "runs_failed_joint_limits": n_failed, "wall_s_timed_region": t_wall,
+            "runs_failed_joint_limits": n_failed, "run_iterations_per_step": run_iters_done, "wall_s_timed_region": t_wall,
             "kernel_ms_per_step": kern_ms / args.steps, "sdf_build": sdf_build,
         }
         print(json.dumps(line))

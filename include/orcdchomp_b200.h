@@ -242,6 +242,9 @@ int ocb_batch_get_costs(ocb_batch *b, double *cost_total, double *cost_obs,
 int ocb_batch_set_momentum(ocb_batch *b, const double *AG, const int *leapfrog_first);
 int ocb_batch_get_momentum(ocb_batch *b, double *AG, int *leapfrog_first);
 int ocb_batch_set_lambda(ocb_batch *b, double lambda);
+/* iterations each run completed in the last iterate call: n_iter, or fewer for a run that left
+ * the joint limits (the reference's r->iter when the exception is thrown, mod.cpp:2799-2803) */
+int ocb_batch_get_iterations(ocb_batch *b, int *iterations);
 /* per-iteration cost log of the last iterate call: [R][n_iter][3] (total, obs,
  * smooth) as RAVELOG_INFO prints them (mod.cpp:2798).  Enable before iterate. */
 int ocb_batch_enable_trace(ocb_batch *b, int enable);

@@ -416,6 +416,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 
    double cost_obs = 0.0, cost_smooth = 0.0;
    int red_parity = 0;
+   int iters_done = 0; /* iterations completed (the reference's r->iter when iterate returns or throws) */
    for (int iter = 0; iter <= a.n_iter; iter++)
    {
       const bool final_pass = (iter == a.n_iter);
@@ -533,6 +534,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          tr[1] = cost_obs;
          tr[2] = cost_smooth;
       }
+      iters_done = iter + 1;
       if (FLOAT)
       {
          /* base quaternions back to unit length (mod.cpp:2805-2808); the end rows are unit already */
@@ -560,6 +562,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       a.costs[(size_t) run * 3 + 1] = cost_obs;
       a.costs[(size_t) run * 3 + 2] = cost_smooth;
       a.status[run] = status;
+      a.iters_done[run] = iters_done;
    }
 }
 

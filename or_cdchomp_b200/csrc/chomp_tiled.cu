@@ -591,6 +591,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
       a.costs[(size_t) run * 3 + 0] = cost_obs + cost_smooth;
       a.costs[(size_t) run * 3 + 1] = cost_obs;
       a.costs[(size_t) run * 3 + 2] = cost_smooth;
+      a.iters_done[run] = iter + 1;
       if (a.trace_on)
       {
          double *tr = a.trace + ((size_t) run * a.n_iter + iter) * 3;

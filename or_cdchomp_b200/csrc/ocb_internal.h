@@ -102,6 +102,7 @@ struct OcbChompArgs
    uint32_t *mt_state;    /* [R][625] */
    double *costs;         /* [R][3] */
    int *status;           /* [R] */
+   int *iters_done;       /* [R] iterations completed by the last iterate call */
    double *trace;         /* [R][n_iter][3] */
    double *grad_out;      /* [R][m][n] */
    double *G_obs;         /* [R][m][n] obstacle + self-collision gradient, unscaled (tiled path) */

@@ -224,6 +224,12 @@ class Batch:
         check(self.lib, self.lib.ocb_batch_get_trace(self.h, dptr(out), int(n_iter)), "ocb_batch_get_trace")
         return out
 
+    def get_iterations(self):
+        """iterations each run completed in the last iterate call"""
+        out = np.zeros(self.R, dtype=np.int32)
+        check(self.lib, self.lib.ocb_batch_get_iterations(self.h, out.ctypes.data_as(c_int_p)), "ocb_batch_get_iterations")
+        return out
+
     def get_traj(self, out=None):
         if out is None:
             out = np.empty((self.R, self.P, self.n))

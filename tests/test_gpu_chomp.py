@@ -563,3 +563,25 @@ def test_runtime_specialised_kernel_agrees_with_library_kernel(oracle, flavour, 
     eng.enable_jit(False)
     eng.remove_sdf(sid)
     eng.close()
+
+
+def test_completed_iterations_are_reported(engine, oracle, flavour, wam7, table):
+    """ocb_batch_get_iterations: n_iter for a run that finished, the index of the failing iteration
+    for one that left the joint limits (the reference's r->iter when it throws, mod.cpp:2799-2803)."""
+    sid = engine.upload_sdf(table["desc"])
+    params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
+    starts, goals = models.random_endpoints(wam7, 256, shrink=0.0)   # some runs start at a limit
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(40)
+    its = b.get_iterations()
+    assert np.all(its[status == 0] == 40) and np.all(its[status != 0] < 40)
+    assert (status != 0).any()
+    r = int(np.where(status != 0)[0][0])
+    oracle.debug_limit_rounds(reset=True)
+    run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
+    ret, c, tr, _ = run.iterate(40, want_trace=True)
+    if ret == -1 and oracle.debug_limit_rounds() > 900:   # a genuine 1000-round failure on the CPU as well
+        assert its[r] == int(np.count_nonzero(tr[:, 0])) - 1 or its[r] == int(np.count_nonzero(tr[:, 0]))
+    run.close()
+    b.close()
+    engine.remove_sdf(sid)
