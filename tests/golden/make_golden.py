@@ -136,6 +136,55 @@ def chomp():
     np.savez_compressed(os.path.join(OUT, "chomp.npz"), **out)
 
 
+def modes():
+    """floating base (mod.cpp:991-1021, 1050-1086, 2424-2464, 2805-2808) and a 200-sphere arm
+    (BASELINE configs[4] shape, small), from the reference build"""
+    robot = models.wam7_robot()
+    kin_pose, prims, apos, aext = models.table_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.02, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    obs, sdf = po.computedistancefield(capi.make_prims(gp), len(gp), sizes, lengths, 0.02, flavour=FL)
+    sd = capi.SdfDesc(sdf, lengths, models.pose_compose(kin_pose, gpose))
+    out = {}
+    # floating base, plain and momentum
+    rng = np.random.default_rng(404)
+    starts, goals = models.random_endpoints(robot, 2, seed0=404, shrink=0.3)
+    base0 = np.asarray(robot.base_pose, dtype=float)
+    qs, qg = [], []
+    for r in range(2):
+        move = models.pose_make(rng.uniform(-0.2, 0.2, 3), models.quat_from_axis_angle(rng.normal(size=3), rng.uniform(0.2, 0.6)))
+        qs.append(np.concatenate([base0, starts[r]]))
+        qg.append(np.concatenate([models.pose_compose(base0, move), goals[r]]))
+    qs, qg = np.array(qs), np.array(qg)
+    for mom in (0, 1):
+        params = capi.default_params(n_points=50, lambda_=100.0, obs_factor=300.0, floating_base=1, use_momentum=mom)
+        trajs, costs, g0 = [], [], []
+        for r in range(2):
+            run = po.Run(robot, params, [sd], qs[r], qg[r], flavour=FL)
+            ret, c, _, gr = run.iterate(30, want_grads=True)
+            assert ret == 0
+            trajs.append(run.traj()); costs.append(c); g0.append(gr[0])
+            run.close()
+        out.update({"float%d_traj" % mom: np.array(trajs), "float%d_costs" % mom: np.array(costs),
+                    "float%d_grad0" % mom: np.array(g0)})
+    out.update(float_starts=qs, float_goals=qg)
+    # dense-sphere arm, fixed base
+    robot5 = models.dense_sphere_arm(200, seed=5)
+    params = capi.default_params(n_points=48, lambda_=200.0, obs_factor=100.0, epsilon=0.2)
+    starts, goals = models.random_endpoints(robot5, 2, seed0=405, shrink=0.4)
+    trajs, costs, g0 = [], [], []
+    for r in range(2):
+        run = po.Run(robot5, params, [sd], starts[r], goals[r], flavour=FL)
+        ret, c, _, gr = run.iterate(6, want_grads=True)
+        assert ret == 0
+        trajs.append(run.traj()); costs.append(c); g0.append(gr[0])
+        run.close()
+    out.update(dense_starts=starts, dense_goals=goals, dense_traj=np.array(trajs), dense_costs=np.array(costs),
+               dense_grad0=np.array(g0), table_sdf=sdf, table_lengths=np.array(lengths),
+               table_pose=models.pose_compose(kin_pose, gpose))
+    np.savez_compressed(os.path.join(OUT, "modes.npz"), **out)
+
+
 def mt():
     g = po.MT(0, flavour=FL)
     raw0 = np.array([g.next() for _ in range(1300)], dtype=np.uint64)
@@ -146,5 +195,5 @@ def mt():
 
 if __name__ == "__main__":
     assert po.available("reference"), "build oracle/_ref first (needs /root/reference)"
-    sdf_kat(); sdf_build(); occupancy(); mesh(); chomp(); mt()
+    sdf_kat(); sdf_build(); occupancy(); mesh(); chomp(); modes(); mt()
     print("golden fixtures written to", OUT)

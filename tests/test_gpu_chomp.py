@@ -585,3 +585,39 @@ def test_completed_iterations_are_reported(engine, oracle, flavour, wam7, table)
     run.close()
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_golden_modes(engine):
+    """floating base and the 200-sphere arm (tiled path) against outputs of the reference's own
+    libcd build (tests/golden/modes.npz)."""
+    gold = np.load(golden_path("modes.npz"))
+    robot = models.wam7_robot()
+    sid = engine.upload_sdf(capi.SdfDesc(gold["table_sdf"], gold["table_lengths"], gold["table_pose"]))
+    for mom in (0, 1):
+        params = capi.default_params(n_points=50, lambda_=100.0, obs_factor=300.0, floating_base=1, use_momentum=mom)
+        b = engine.create_batch(robot, params, [sid], gold["float_starts"], gold["float_goals"])
+        b.capture_gradient(1)
+        b.iterate(1)
+        g = b.get_gradient()
+        ref = gold["float%d_grad0" % mom]
+        assert np.max(np.abs(g - ref)) <= GRAD_RTOL * np.max(np.abs(ref))
+        b.close()
+        b = engine.create_batch(robot, params, [sid], gold["float_starts"], gold["float_goals"])
+        costs, status = b.iterate(30)
+        assert (status == 0).all()
+        assert np.max(np.abs(b.get_traj() - gold["float%d_traj" % mom])) <= TRAJ_ATOL
+        assert np.allclose(costs, gold["float%d_costs" % mom], rtol=COST_RTOL, atol=0)
+        b.close()
+    robot5 = models.dense_sphere_arm(200, seed=5)
+    params = capi.default_params(n_points=48, lambda_=200.0, obs_factor=100.0, epsilon=0.2)
+    b = engine.create_batch(robot5, params, [sid], gold["dense_starts"], gold["dense_goals"])
+    b.capture_gradient(1)
+    b.iterate(1)
+    assert np.max(np.abs(b.get_gradient() - gold["dense_grad0"])) <= GRAD_RTOL * np.max(np.abs(gold["dense_grad0"]))
+    b.close()
+    b = engine.create_batch(robot5, params, [sid], gold["dense_starts"], gold["dense_goals"])
+    costs, status = b.iterate(6)
+    assert (status == 0).all() and np.max(np.abs(b.get_traj() - gold["dense_traj"])) <= TRAJ_ATOL
+    assert np.allclose(costs, gold["dense_costs"], rtol=COST_RTOL, atol=0)
+    b.close()
+    engine.remove_sdf(sid)

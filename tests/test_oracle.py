@@ -302,3 +302,25 @@ def test_floating_base_oracle(oracle, flavour, wam7, table):
     assert np.allclose(np.linalg.norm(t[:, 3:7], axis=1), 1.0, atol=1e-15)
     assert np.max(np.abs(t[:, :7] - t0[:, :7])) < 0.2 * np.max(np.abs(t[:, 7:] - t0[:, 7:]))
     flt.close()
+
+
+def test_port_matches_golden_modes(oracle):
+    """the self-contained port against fixtures made by the reference build (tests/golden/modes.npz):
+    floating base (plain, momentum) and the 200-sphere arm."""
+    gold = np.load(golden_path("modes.npz"))
+    robot = models.wam7_robot()
+    sd = capi.SdfDesc(gold["table_sdf"], gold["table_lengths"], gold["table_pose"])
+    for mom in (0, 1):
+        params = capi.default_params(n_points=50, lambda_=100.0, obs_factor=300.0, floating_base=1, use_momentum=mom)
+        run = oracle.Run(robot, params, [sd], gold["float_starts"][0], gold["float_goals"][0], flavour="port")
+        ret, c, _, gr = run.iterate(30, want_grads=True)
+        assert ret == 0
+        assert np.max(np.abs(gr[0] - gold["float%d_grad0" % mom][0])) <= 1e-9 * np.max(np.abs(gr[0]))
+        assert np.max(np.abs(run.traj() - gold["float%d_traj" % mom][0])) <= 1e-9
+        run.close()
+    robot5 = models.dense_sphere_arm(200, seed=5)
+    params = capi.default_params(n_points=48, lambda_=200.0, obs_factor=100.0, epsilon=0.2)
+    run = oracle.Run(robot5, params, [sd], gold["dense_starts"][0], gold["dense_goals"][0], flavour="port")
+    ret, c, _, gr = run.iterate(6, want_grads=True)
+    assert ret == 0 and np.max(np.abs(run.traj() - gold["dense_traj"][0])) <= 1e-9
+    run.close()
