@@ -35,7 +35,7 @@ constexpr int TILE_THREADS = 256;
 
 struct TileLayout
 {
-   int pos, jfr, slots, Gp, cp, rad; /* offsets in doubles */
+   int pos, jfr, slots, Gp, cp, rad, gb; /* offsets in doubles */
    int sdf, link;                    /* offsets in bytes   */
    int bytes;
 };
@@ -51,6 +51,7 @@ __host__ __device__ inline TileLayout tile_layout(const OcbChompArgs &a, int TW)
    l.Gp = d; d += NW * a.n * TW;        /* per-worker gradient rows, [NW][n][TW] */
    l.cp = d; d += TILE_THREADS;         /* per-thread cost */
    l.rad = d; d += a.nsa;
+   l.gb = d; d += 3 * a.nj * CS;        /* world centres of the joint frames' bounding spheres, [3 nj][CS] */
    int b = d * 8;
    l.sdf = b; b += a.nsdf * (int) sizeof(OcbSdfDev);
    l.link = b; b += a.nsa * 4;
@@ -164,7 +165,7 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
    const TileLayout lay = tile_layout(a, TW);
    double *sd = reinterpret_cast<double *>(smem_raw);
    double *pos = sd + lay.pos, *jfr = sd + lay.jfr, *slots = sd + lay.slots;
-   double *Gp = sd + lay.Gp, *cp = sd + lay.cp, *rad = sd + lay.rad;
+   double *Gp = sd + lay.Gp, *cp = sd + lay.cp, *rad = sd + lay.rad, *gb = sd + lay.gb;
    OcbSdfDev *sdfs = reinterpret_cast<OcbSdfDev *>(smem_raw + lay.sdf);
    int *link = reinterpret_cast<int *>(smem_raw + lay.link);
    const int t_first = 1 + tile * TW;
@@ -202,6 +203,13 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
             double *fr = jfr + 6 * j * TW + (c - 1);
 #pragma unroll
             for (int k = 0; k < 3; k++) { fr[k * TW] = ax[k]; fr[(3 + k) * TW] = org[k]; }
+         }
+         {
+            const double bx = __ldg(a.gbound + 4 * j), by = __ldg(a.gbound + 4 * j + 1), bz = __ldg(a.gbound + 4 * j + 2);
+            double *o = gb + 3 * j * CS + c;
+            o[0] = R[0] * bx + R[1] * by + R[2] * bz + tr[0];
+            o[CS] = R[3] * bx + R[4] * by + R[5] * bz + tr[1];
+            o[2 * CS] = R[6] * bx + R[7] * by + R[8] * bz + tr[2];
          }
          for (int s = J.sph_begin; s < J.sph_end; s++)
          {
@@ -288,6 +296,22 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
          const int ge = a.joints[j].sph_end;
          const int o_lo = max(a.joints[j].sph_begin, s0 + 1);
          if (o_lo >= ge) continue;
+         {
+            /* none of the four own spheres can reach anything this frame carries: skip its sweep
+             * (decided by the lanes that are here together; a lane that could reach keeps them all) */
+            const double Rj = __ldg(a.gbound + 4 * j + 3);
+            const double *gc = gb + 3 * j * CS + c;
+            const double g0 = gc[0], g1 = gc[CS], g2 = gc[2 * CS];
+            bool near = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+               const double dx = p[k][0] - g0, dy = p[k][1] - g1, dz = p[k][2] - g2;
+               const double lim = rk[k] + Rj;
+               near |= (dx * dx + dy * dy + dz * dz <= lim * lim);
+            }
+            if (!__any_sync(__activemask(), near)) continue;
+         }
          double Rf[3] = {0.0, 0.0, 0.0}, Rm[3] = {0.0, 0.0, 0.0}; /* reaction on this frame */
          bool any = false;
          for (int ob = o_lo; ob < ge; ob += 32)

@@ -880,6 +880,7 @@ struct CompiledRobot
    int n_groups = 0;
    std::vector<int> desc;
    std::vector<int> ganc; /* [n_groups + 1] offsets, then joints above each group (see OcbChompArgs) */
+   std::vector<double> gbound; /* [nj][4] bounding sphere of each joint frame's spheres (see OcbChompArgs) */
    std::vector<double> inactive_pos;
    std::vector<double> inactive_radius;
    std::vector<int> inactive_link;
@@ -1066,6 +1067,30 @@ int compile_robot(const ocb_robot *rb, double eps_self, bool floating, CompiledR
       }
       C.joints[k].desc_end = (int) C.desc.size();
    }
+   /* bounding sphere of the spheres each joint frame carries (centre of their box, slightly inflated) */
+   C.gbound.assign((size_t) nj * 4, -1.0);
+   for (int k = 0; k < nj; k++)
+   {
+      const int sb = C.joints[k].sph_begin, se = C.joints[k].sph_end;
+      if (se <= sb) continue;
+      double lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
+      for (int s = sb; s < se; s++)
+         for (int c = 0; c < 3; c++)
+         {
+            lo[c] = std::min(lo[c], C.spheres[s].pos[c]);
+            hi[c] = std::max(hi[c], C.spheres[s].pos[c]);
+         }
+      double bc[3], br = 0.0;
+      for (int c = 0; c < 3; c++) bc[c] = 0.5 * (lo[c] + hi[c]);
+      for (int s = sb; s < se; s++)
+      {
+         double d2 = 0.0;
+         for (int c = 0; c < 3; c++) d2 += (C.spheres[s].pos[c] - bc[c]) * (C.spheres[s].pos[c] - bc[c]);
+         br = std::max(br, sqrt(d2) + C.spheres[s].radius);
+      }
+      for (int c = 0; c < 3; c++) C.gbound[4 * k + c] = bc[c];
+      C.gbound[4 * k + 3] = br * (1.0 + 1e-9) + 1e-9; /* the frames are orthonormal only up to rounding */
+   }
    /* the same relation by group: the joints whose subtree carries it */
    C.ganc.assign(C.n_groups + 1, 0);
    for (int g = 0; g < C.n_groups; g++)
@@ -1217,6 +1242,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    TRY(batch_upload(b, &a.radius, C.radius));
    TRY(batch_upload(b, &a.desc, C.desc));
    TRY(batch_upload(b, &a.ganc, C.ganc));
+   TRY(batch_upload(b, &a.gbound, C.gbound));
    TRY(batch_upload(b, &a.inactive_pos, C.inactive_pos));
    TRY(batch_upload(b, &a.sdfs, sd));
    TRY(batch_upload(b, &a.Aband, M.Aband));

@@ -75,6 +75,8 @@ struct OcbChompArgs
    const int *desc;        /* [n_desc] group indices, see OcbJointDev::desc_begin */
    const int *ganc;        /* inverse of desc: [ng + 1] offsets into this same array, then the joints
                               whose subtree carries group g (tiled path) */
+   const double *gbound;   /* [nj][4]: bounding sphere (centre in the joint frame, radius) of the spheres a joint
+                              frame carries, radius < 0 when it carries none (tiled path: partner culling) */
    const double *inactive_pos;
    /* self-collision tables over NS = nsa + nsi spheres (active first):
     * cut2[s][o] = (r_s + r_o + epsilon_self)^2, or -1 when s and o sit on the same link
