@@ -135,3 +135,38 @@ def test_libcd_struct_layouts_match_reference_headers():
             subprocess.check_call(["gcc"] + flags + [c, "-o", os.path.join(d, name)])
             outs.append(subprocess.check_output([os.path.join(d, name)]))
     assert outs[0] == outs[1]
+
+
+def test_kernel_sources_compile_under_nvrtc():
+    """the persistent kernel must stay compilable without host headers: the engine compiles these
+    very sources at run time (csrc/ocb_jit.cpp).  NVRTC needs no GPU, so this runs everywhere."""
+    try:
+        from cuda.bindings import nvrtc
+    except Exception:
+        pytest.skip("cuda-python (nvrtc bindings) not importable")
+    csrc = os.path.join(ROOT, "or_cdchomp_b200", "csrc")
+    src = open(os.path.join(csrc, "chomp_kernel.cu")).read()
+    hdrs = {"ocb_internal.h": open(os.path.join(csrc, "ocb_internal.h")).read(),
+            "chomp_device.cuh": open(os.path.join(csrc, "chomp_device.cuh")).read()}
+    for defs in (dict(NT=128, MINBLOCKS=3, FLOAT=0, PP=100, NN=7, nsa=15, nsi=1, NAp=18, n_slots=0, ng=6, nj=7, nsdf=1,
+                      n_desc=21, use_momentum=0, use_hmc=0),
+                 dict(NT=64, MINBLOCKS=1, FLOAT=1, PP=0, NN=11, nsa=9, nsi=0, NAp=12, n_slots=2, ng=5, nj=6, nsdf=3,
+                      n_desc=14, use_momentum=1, use_hmc=1)):
+        err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"chomp_kernel.cu", len(hdrs),
+                                             [v.encode() for v in hdrs.values()], [k.encode() for k in hdrs])
+        assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS
+        opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-DOCB_JIT=1"]
+        opts += [("-DOCB_JIT_%s=%d" % kv).encode() for kv in defs.items()]
+        err, = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+        _, n = nvrtc.nvrtcGetProgramLogSize(prog)
+        log = b" " * n
+        nvrtc.nvrtcGetProgramLog(prog, log)
+        assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS, log.decode(errors="replace")[:2000]
+        _, nb = nvrtc.nvrtcGetCUBINSize(prog)
+        assert nb > 10000
+        nvrtc.nvrtcDestroyProgram(prog)
+    # every -D the kernel reads is one ocb_jit.cpp passes
+    import re as _re
+    used = set(_re.findall(r"OCB_JIT_([A-Za-z_]+)", src)) | set(_re.findall(r"DIM\(a, ([A-Za-z_]+)\)", src))
+    passed = set(_re.findall(r'\{"([A-Za-z_]+)", ', open(os.path.join(csrc, "ocb_jit.cpp")).read()))
+    assert used - {"f"} <= passed, used - passed
