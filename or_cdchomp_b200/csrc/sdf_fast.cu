@@ -22,7 +22,8 @@
  *     HBM scratch with its two top entries in registers.  (Two shared-memory-stack
  *     variants were measured first -- a stack tile per warp, and a stack-free divide and
  *     conquer on the monotone arg-min; both lose to this one because the scan is latency
- *     bound and only massive thread-level parallelism hides that: 8.8 / 5.1 / 2.7 ms at 400^3.)
+ *     bound and only massive thread-level parallelism hides that: 8.8 / 5.1 / 2.7 ms at 400^3;
+ *     1.9 ms since the free-cell field became sparse, see envelope_pass.)
  * HBM traffic per cell: 8 (input) + 4 + 4 + 4 (intermediate write / read / sign re-read)
  * + 8 (output) + envelope stack (<= 8 per pass) + ~0.4 (mask), against 16 B algorithmic.
  *
