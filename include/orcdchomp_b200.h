@@ -124,6 +124,9 @@ int ocb_engine_destroy(ocb_engine *e);
 /* Make the engine launch on a caller stream (cudaStream_t as void*; NULL = own). */
 int ocb_engine_set_stream(ocb_engine *e, void *cuda_stream);
 int ocb_engine_sync(ocb_engine *e);
+/* The engine keeps the device memory of destroyed batches and removed fields in its own pool so
+ * that the next create costs microseconds; this hands the unused part back to the driver. */
+int ocb_engine_trim(ocb_engine *e);
 /* Run-time specialisation: batches created while this is on get the persistent kernel compiled
  * (NVRTC, once per configuration, ~2 s, cached for the life of the process) with their sizes --
  * waypoints, dofs, spheres, joint frames, fields, mode flags -- as literal constants.  Same

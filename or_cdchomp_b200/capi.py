@@ -245,6 +245,7 @@ EXPORTS = {
     "ocb_engine_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "ocb_engine_destroy": (C.c_int, [C.c_void_p]),
     "ocb_engine_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ocb_engine_trim": (C.c_int, [C.c_void_p]),
     "ocb_engine_enable_jit": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_batch_uses_jit": (C.c_int, [C.c_void_p]),
     "ocb_engine_sync": (C.c_int, [C.c_void_p]),

@@ -326,6 +326,15 @@ extern "C" int ocb_engine_sync(ocb_engine *e)
 
 extern "C" long ocb_engine_launch_count(const ocb_engine *e) { return e ? e->launches : 0; }
 
+extern "C" int ocb_engine_trim(ocb_engine *e)
+{
+   if (!e) return fail(OCB_ERR_ARG, "null engine");
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->stream));
+   CU(cudaMemPoolTrimTo(e->pool, 0));
+   return OCB_OK;
+}
+
 extern "C" int ocb_engine_enable_jit(ocb_engine *e, int on)
 {
    if (!e) return fail(OCB_ERR_ARG, "null engine");

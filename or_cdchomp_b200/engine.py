@@ -31,6 +31,10 @@ class Engine:
         self.h = h
         self.device = device
 
+    def trim(self):
+        """hand the pool's unused device memory back to the driver"""
+        check(self.lib, self.lib.ocb_engine_trim(self.h), "ocb_engine_trim")
+
     def enable_jit(self, on=True):
         """compile the persistent kernel per batch configuration (ocb_engine_enable_jit)"""
         check(self.lib, self.lib.ocb_engine_enable_jit(self.h, 1 if on else 0), "ocb_engine_enable_jit")

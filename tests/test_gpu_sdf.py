@@ -285,3 +285,7 @@ def test_resident_fields_and_pose_aliases(engine, wam7, table):
     assert np.array_equal(res[0], res[1])
     for s in (alias, up, sid2, sid):
         engine.remove_sdf(s)
+    engine.trim()  # the pool hands its unused memory back; the engine stays usable
+    again = engine.computedistancefield_resident(gprims, sizes, lengths, 0.02, table["pose_world"])
+    assert np.array_equal(engine.download_sdf(again, sizes), sdf)
+    engine.remove_sdf(again)
