@@ -14,6 +14,7 @@
 #include <time.h>
 
 #include <map>
+#include <mutex>
 #include <memory>
 #include <set>
 #include <sstream>
@@ -205,6 +206,9 @@ struct ocb_env
 {
    std::map<std::string, Kinbody> kinbodies;
    std::map<std::string, std::unique_ptr<Robot>> robots;
+   /* the reference holds the environment's recursive mutex for the whole of every command
+    * (EnvironmentMutex::scoped_lock, mod.cpp:179, 323, 612, 806, 1829, 2745, 2894) */
+   std::recursive_mutex mutex;
 };
 
 namespace
@@ -992,6 +996,8 @@ extern "C" int ocb_env_destroy(ocb_env *env)
 
 extern "C" int ocb_env_add_kinbody(ocb_env *env, const char *name, const double pose[7], const ocb_prim *prims, int n_prims)
 {
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
    if (!env || !name || !pose || env->kinbodies.count(name)) return OCB_ERR_ARG;
    Kinbody kb;
    kb.name = name;
@@ -1003,6 +1009,8 @@ extern "C" int ocb_env_add_kinbody(ocb_env *env, const char *name, const double 
 
 extern "C" int ocb_env_set_kinbody_pose(ocb_env *env, const char *name, const double pose[7])
 {
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
    if (!env || !name || !env->kinbodies.count(name)) return OCB_ERR_ARG;
    memcpy(env->kinbodies[name].pose, pose, 7 * sizeof(double));
    return OCB_OK;
@@ -1010,6 +1018,8 @@ extern "C" int ocb_env_set_kinbody_pose(ocb_env *env, const char *name, const do
 
 extern "C" int ocb_env_enable_kinbody(ocb_env *env, const char *name, int enabled)
 {
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
    if (!env || !name || !env->kinbodies.count(name)) return OCB_ERR_ARG;
    env->kinbodies[name].enabled = enabled != 0;
    return OCB_OK;
@@ -1017,6 +1027,8 @@ extern "C" int ocb_env_enable_kinbody(ocb_env *env, const char *name, int enable
 
 extern "C" int ocb_env_add_robot(ocb_env *env, const char *name, const ocb_robot *robot, const double *values)
 {
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
    if (!env || !name || !robot || !values || env->robots.count(name) || env->kinbodies.count(name)) return OCB_ERR_ARG;
    std::unique_ptr<Robot> r(new Robot());
    r->name = name;
@@ -1031,6 +1043,8 @@ extern "C" int ocb_env_add_robot(ocb_env *env, const char *name, const ocb_robot
 
 extern "C" int ocb_env_set_active_dof_values(ocb_env *env, const char *name, const double *values)
 {
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
    if (!env || !name || !values || !env->robots.count(name)) return OCB_ERR_ARG;
    Robot &r = *env->robots[name];
    r.q.assign(values, values + r.desc.n_dof);
@@ -1066,6 +1080,7 @@ extern "C" int ocb_module_send_command(ocb_module *m, const char *cmd, char *out
    int ret;
    try
    {
+      std::lock_guard<std::recursive_mutex> guard(m->env->mutex);
       ret = m->dispatch(cmd, sout);
    }
    catch (const std::exception &ex)
