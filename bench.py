@@ -173,8 +173,19 @@ def _cpu_baseline(flavour, robot, params, sd, n_runs, n_iter, threads=1):
 
     t0 = time.perf_counter()
     if threads <= 1:
-        for r in range(n_runs):
-            work(r)
+        # one core, pinned (`taskset -c`), affinity restored afterwards
+        saved = None
+        try:
+            saved = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, {sorted(saved)[0]})
+        except (AttributeError, OSError):
+            saved = None
+        try:
+            for r in range(n_runs):
+                work(r)
+        finally:
+            if saved is not None:
+                os.sched_setaffinity(0, saved)
     else:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=threads) as ex:
