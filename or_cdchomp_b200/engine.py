@@ -86,6 +86,14 @@ class Engine:
         check(self.lib, self.lib.ocb_flood_relabel_device(self.h, C.c_void_p(int(d_grid)), _i3(sizes),
                                                          int(index_start)), "ocb_flood_relabel_device")
 
+    def flood_relabel(self, grid, index_start=0):
+        """cd_grid_flood_fill(1.0 -> 0.0 from index_start) + relabel of the remaining 1.0 on a host
+        array (returns a new array)"""
+        g = np.array(grid, dtype=np.float64, order="C", copy=True)
+        check(self.lib, self.lib.ocb_flood_relabel_host(self.h, dptr(g), _i3(g.shape), int(index_start)),
+              "ocb_flood_relabel_host")
+        return g
+
     def computedistancefield(self, prims, sizes, lengths, cube_extent, want_sdf=True):
         """occupancy -> flood fill + relabel -> SDF with host outputs
         (src/orcdchomp_mod.cpp:498-560 in the reference)."""

@@ -289,3 +289,34 @@ def test_resident_fields_and_pose_aliases(engine, wam7, table):
     again = engine.computedistancefield_resident(gprims, sizes, lengths, 0.02, table["pose_world"])
     assert np.array_equal(engine.download_sdf(again, sizes), sdf)
     engine.remove_sdf(again)
+
+
+def test_flood_fill_random_grids(engine):
+    """the bit-mask flood fill against 6-connected component labelling (scipy) on random grids:
+    axes that are not multiples of 32, a single z word, thin grids, winding corridors, start cells
+    anywhere, a start cell that is not fillable (grid_flood.c:30-111, mod.cpp:543-548)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(77)
+    six = ndimage.generate_binary_structure(3, 1)
+    shapes = [(5, 7, 3), (9, 4, 31), (6, 5, 32), (4, 6, 33), (12, 10, 70), (3, 3, 129), (40, 37, 45), (1, 1, 50), (2, 64, 2)]
+    for shape in shapes:
+        for frac in (0.25, 0.45, 0.62):   # around the site-percolation threshold: long winding paths
+            open_cells = rng.uniform(size=shape) > frac
+            grid = np.where(open_cells, 1.0, np.inf)
+            grid[rng.uniform(size=shape) < 0.02] = 0.37            # other values conduct nothing and stay
+            open_cells = grid == 1.0
+            labels, _ = ndimage.label(open_cells, structure=six)
+            flat_open = np.flatnonzero(open_cells.ravel())
+            starts = [0, int(np.prod(shape)) - 1]
+            if len(flat_open):
+                starts += [int(rng.choice(flat_open)) for _ in range(2)]
+            for start in starts:
+                got = engine.flood_relabel(grid, start)
+                want = grid.copy()
+                lab = labels.ravel()[start]
+                if lab > 0:
+                    want[labels == lab] = 0.0
+                    want[open_cells & (labels != lab)] = np.inf
+                else:                                              # start cell not fillable: nothing is reached
+                    want[open_cells] = np.inf
+                assert np.array_equal(got, want), (shape, frac, start)
