@@ -320,3 +320,32 @@ def test_flood_fill_random_grids(engine):
                 else:                                              # start cell not fillable: nothing is reached
                     want[open_cells] = np.inf
                 assert np.array_equal(got, want), (shape, frac, start)
+
+
+def test_fast_path_solid_obstacles(engine):
+    """the sparse free-cell field of the integer path (only zero-height samples at the ends of a
+    run are kept, results only between the first and last obstacle cell of a line) on thick solid
+    obstacles with cavities, thin walls, slabs touching the grid faces and lines that are entirely
+    obstacle -- against the general fp64 path, which follows grid.c:462-569 operation for operation."""
+    rng = np.random.default_rng(91)
+    for shape in ((70, 65, 90), (33, 100, 47), (64, 64, 64)):
+        obs = np.zeros(shape)
+        for _ in range(6):                                  # solid boxes, some touching the faces
+            lo = [rng.integers(0, s - 2) for s in shape]
+            hi = [min(s, l + rng.integers(2, max(3, s // 2))) for s, l in zip(shape, lo)]
+            obs[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = np.inf
+        for _ in range(3):                                  # cavities inside them
+            c = [rng.integers(2, s - 2) for s in shape]
+            obs[c[0] - 1:c[0] + 2, c[1] - 1:c[1] + 2, c[2] - 1:c[2] + 2] = 0.0
+        obs[:, shape[1] // 3, :] = np.inf                   # a full wall: whole lines of obstacle
+        obs[shape[0] // 2, :, shape[2] // 2] = np.inf       # a rod
+        obs[rng.uniform(size=shape) < 0.002] = np.inf       # specks
+        pitch = 0.01
+        lens = [pitch * k for k in shape]
+        engine.force_general_sdf(False)
+        fast = engine.sdf_build(obs, lens)
+        engine.force_general_sdf(True)
+        gen = engine.sdf_build(obs, lens)
+        engine.force_general_sdf(False)
+        assert np.all(np.isfinite(gen)) and np.all((fast < 0) == (obs != 0))
+        assert np.max(np.abs(fast - gen)) <= SDF_ATOL, shape
