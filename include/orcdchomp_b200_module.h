@@ -37,8 +37,10 @@
  *     groups) and sampled as mod.cpp:2375-2415 does;
  *   - floating_base + basegoal are supported for single runs with adofgoal (gettraj then
  *     carries an affine_transform group, x y z qw qx qy qz, as mod.cpp:2912-2956);
- *   - con_tsr, start_tsr, everyn_tsr,
- *     start_cost and trajs_fileformstr are recognised and rejected with an error
+ *   - trajs_fileformstr writes the waypoints before every iteration in the same XML layout
+ *     (joint_values group only, full precision, mod.cpp:2769-2795), one launch per iteration;
+ *   - con_tsr, start_tsr, everyn_tsr and
+ *     start_cost are recognised and rejected with an error
  *     (out of scope for the hot path); ee_force,
  *     ee_force_at and ee_torque_weights are accepted and ignored, as in the
  *     reference (mod.cpp:1323).

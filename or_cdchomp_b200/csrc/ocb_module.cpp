@@ -822,6 +822,7 @@ struct ocb_module
       Run *r = nullptr;
       int n_iter = 1;
       double max_time = HUGE_VAL;
+      std::string trajs_fileformstr;
       size_t i = 1;
       for (; i < argv.size(); i++)
       {
@@ -832,19 +833,53 @@ struct ocb_module
          }
          else if (argv[i] == "n_iter" && i + 1 < argv.size()) n_iter = atoi(argv[++i].c_str());
          else if (argv[i] == "max_time" && i + 1 < argv.size()) max_time = atof(argv[++i].c_str());
-         else if (argv[i] == "trajs_fileformstr" && i + 1 < argv.size())
-            throw module_error("'trajs_fileformstr' is not supported by the B200 engine (see orcdchomp_b200_module.h)");
+         else if (argv[i] == "trajs_fileformstr" && i + 1 < argv.size()) trajs_fileformstr = argv[++i];
          else break;
       }
       if (i < argv.size()) bad_args(argv, i);
       if (!r) throw module_error("you must pass a created run!");
       if (n_iter < 0) throw module_error("n_iter must be >=0!");
+      if (!trajs_fileformstr.empty() && r->floating)
+         throw module_error("Error: trajs_fileformstr and floating_base combined is not yet implemented!"); /* mod.cpp:2772-2776 */
       std::vector<double> total(r->n_runs);
       std::vector<int> status(r->n_runs);
       struct timespec t0, t1;
       clock_gettime(CLOCK_MONOTONIC, &t0);
       int done = 0;
-      if (max_time == HUGE_VAL)
+      if (!trajs_fileformstr.empty())
+      {
+         /* the trajectory as it stands before every iteration goes to sprintf(fmt, iter)
+          * (mod.cpp:2769-2795): one launch per iteration on this path */
+         const int P = r->n_points, n = r->n_dof;
+         std::vector<double> traj((size_t) r->n_runs * P * n);
+         const Robot &rb = *env->robots[r->robot_name];
+         for (; done < n_iter;)
+         {
+            if (ocb_batch_get_traj(r->batch, traj.data()) != OCB_OK) fail_engine("iterate");
+            char fname[4096];
+            snprintf(fname, sizeof(fname), trajs_fileformstr.c_str(), done);
+            FILE *fp = fopen(fname, "w");
+            if (fp)
+            {
+               fprintf(fp, "<trajectory>\n<configuration>\n<group name=\"joint_values %s", rb.name.c_str());
+               for (int j = 0; j < n; j++) fprintf(fp, " %d", j);
+               fprintf(fp, "\" offset=\"0\" dof=\"%d\" interpolation=\"linear\"/>\n</configuration>\n<data count=\"%d\">\n", n, P);
+               for (int q = 0; q < P * n; q++) fprintf(fp, "%.17g ", traj[q]); /* run 0; full precision, mod.cpp:2790 */
+               fprintf(fp, "\n</data>\n</trajectory>\n");
+               fclose(fp);
+            }
+            if (ocb_batch_iterate(r->batch, 1, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
+            done++;
+            if (status[0] == OCB_ERR_JLIMIT) break;
+            if (max_time != HUGE_VAL)
+            {
+               clock_gettime(CLOCK_MONOTONIC, &t1);
+               if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > max_time) break;
+            }
+         }
+         if (done == 0 && ocb_batch_iterate(r->batch, 0, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
+      }
+      else if (max_time == HUGE_VAL)
       {
          if (ocb_batch_iterate(r->batch, n_iter, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
          done = n_iter;
@@ -863,7 +898,7 @@ struct ocb_module
          if (done == 0 && ocb_batch_iterate(r->batch, 0, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
       }
       clock_gettime(CLOCK_MONOTONIC, &t1);
-      if (r->fp_dat && max_time == HUGE_VAL && n_iter > 0)
+      if (r->fp_dat && max_time == HUGE_VAL && trajs_fileformstr.empty() && n_iter > 0)
       {
          /* rows "iter time total obs smooth" of run 0 (mod.cpp:2811-2818); time is apportioned */
          std::vector<double> trace((size_t) r->n_runs * n_iter * 3);

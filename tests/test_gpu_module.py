@@ -198,3 +198,33 @@ def test_floating_base_through_module(world, oracle, flavour):
         with pytest.raises(RuntimeError) as ei:
             mod.create(robot=robot, adofgoal=goal, **bad)
         assert text in str(ei.value)
+
+
+def test_trajs_fileformstr_dumps(world, tmp_path):
+    """iterate trajs_fileformstr FMT (mod.cpp:2769-2795): the trajectory as it stands before every
+    iteration is written to sprintf(FMT, iter); stepping this way changes nothing in the result."""
+    env, mod, table, robot, robot_desc = world
+    mod.computedistancefield(kinbody=table, cube_extent=0.02)
+    goal = list(models.WAM7_DEMO_GOAL)
+    kw = dict(robot=robot, adofgoal=goal, n_points=30, lambda_=100.0, obs_factor=300.0)
+    h = mod.create(**kw)
+    fmt = str(tmp_path / "traj_%03d.xml")
+    mod.iterate(run=h, n_iter=4, trajs_fileformstr=fmt)
+    final = mod.gettraj(run=h, no_collision_check=True)
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["traj_%03d.xml" % k for k in range(4)]
+    import re
+    dumps = []
+    for f in files:
+        text = open(tmp_path / f).read()
+        assert 'count="30"' in text and "joint_values BarrettWAM" in text
+        body = re.search(r"<data[^>]*>\s*(.*?)\s*</data>", text, re.S).group(1)
+        dumps.append(np.array(body.split(), dtype=np.float64).reshape(30, 7))
+    h2 = mod.create(**kw)
+    assert np.array_equal(dumps[0], mod.gettraj(run=h2, no_collision_check=True))   # before iteration 0: the straight line
+    mod.iterate(run=h2, n_iter=3)
+    assert np.array_equal(dumps[3], mod.gettraj(run=h2, no_collision_check=True))   # before iteration 3
+    mod.iterate(run=h2, n_iter=1)
+    assert np.array_equal(final, mod.gettraj(run=h2, no_collision_check=True))
+    mod.destroy(run=h)
+    mod.destroy(run=h2)
