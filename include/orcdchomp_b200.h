@@ -143,6 +143,12 @@ int ocb_sdf_upload(ocb_engine *e, const ocb_sdf *sdf, int *id);
 int ocb_sdf_adopt_device(ocb_engine *e, const int sizes[3], const double lengths[3],
                          const double pose_world_gsdf[7], const double *d_data, int *id);
 int ocb_sdf_remove(ocb_engine *e, int id);
+/* cd_grid_double_interp + cd_grid_double_grad (grid.c:331-454) of resident field `id` at k points
+ * given in the GRID frame [k][3]: the device function the CHOMP kernels sample with.  errs[i] = 1
+ * where cd_grid_lookup_index rejects the point (grid.c:191-209; values / grads are then 0), else 0;
+ * values[i] may be HUGE_VAL (grid.c:402, 431, 441). */
+int ocb_sdf_sample_host(ocb_engine *e, int id, const double *points, int k, double *values,
+                        double *grads, int *errs);
 
 /* --- SDF build: cd_grid_double_bin_sdf (grid.c:637-687) --------------------- *
  * obs: 0.0 = free, HUGE_VAL = obstacle (any non-zero finite value is treated as
@@ -237,6 +243,14 @@ int ocb_batch_iterate(ocb_batch *b, int n_iter, double *cost_total, double *cost
                       double *cost_smooth, int *status);
 /* asynchronous form: enqueue only (results stay on the device) */
 int ocb_batch_iterate_async(ocb_batch *b, int n_iter);
+/* One `iterate` command split over several calls (max_time, per-iteration trajectory dumps:
+ * mod.cpp:2752-2828 runs r->iter = 0..n_iter-1 inside ONE command): the iterations of this call
+ * are numbered first_iter, first_iter+1, ... for the HMC schedule (resample when r->iter ==
+ * hmc_resample_iter, alpha = 100 exp(0.02 r->iter), mod.cpp:2755-2768).  ocb_batch_iterate is
+ * first_iter = 0. */
+int ocb_batch_iterate_from(ocb_batch *b, int first_iter, int n_iter, double *cost_total, double *cost_obs,
+                           double *cost_smooth, int *status);
+int ocb_batch_iterate_from_async(ocb_batch *b, int first_iter, int n_iter);
 int ocb_batch_get_costs(ocb_batch *b, double *cost_total, double *cost_obs,
                         double *cost_smooth, int *status);
 /* the public cd_chomp fields a caller may poke between iterations (chomp.h:40-41, 49-50,
@@ -265,6 +279,7 @@ int ocb_batch_best(ocb_batch *b, int *best_run, double *best_cost);
 int ocb_batch_destroy(ocb_batch *b);
 /* sizes for callers that allocate outputs */
 int ocb_batch_uses_jit(const ocb_batch *b);   /* 1 when this batch runs a run-time specialised kernel */
+int ocb_batch_tile_width(const ocb_batch *b); /* waypoints per tile of the tiled large-robot path (32, 16, 8); 0 = persistent kernel */
 int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof);
 /* device pointers (HBM) of the trajectory [R][n_points][n_dof] and costs [R][3],
  * for callers that keep everything resident (bench, NCCL gather)              */

@@ -248,6 +248,7 @@ EXPORTS = {
     "ocb_engine_trim": (C.c_int, [C.c_void_p]),
     "ocb_engine_enable_jit": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_batch_uses_jit": (C.c_int, [C.c_void_p]),
+    "ocb_batch_tile_width": (C.c_int, [C.c_void_p]),
     "ocb_engine_sync": (C.c_int, [C.c_void_p]),
     "ocb_sdf_upload": (C.c_int, [C.c_void_p, C.POINTER(OcbSdf), c_int_p]),
     "ocb_sdf_adopt_device": (C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p, C.c_void_p, c_int_p]),
@@ -269,8 +270,11 @@ EXPORTS = {
     "ocb_batch_create": (C.c_int, [C.c_void_p, C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_int, c_int_p, C.c_int, c_double_p, c_double_p, c_uint_p, C.POINTER(C.c_void_p)]),
     "ocb_batch_reset": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_uint_p]),
     "ocb_batch_set_traj": (C.c_int, [C.c_void_p, c_double_p]),
+    "ocb_sdf_sample_host": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, c_int_p]),
     "ocb_batch_iterate": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
     "ocb_batch_iterate_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocb_batch_iterate_from": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
+    "ocb_batch_iterate_from_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ocb_batch_get_costs": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     "ocb_batch_set_momentum": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),
     "ocb_batch_get_momentum": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),

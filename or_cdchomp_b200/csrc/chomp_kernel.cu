@@ -422,9 +422,9 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       const bool final_pass = (iter == a.n_iter);
 
       /* ---- HMC momentum resample (mod.cpp:2755-2768) ---- */
-      if (DIM(a, use_hmc) && !final_pass && iter == hmc_next)
+      if (DIM(a, use_hmc) && !final_pass && a.iter_base + iter == hmc_next)
       {
-         const double alpha = 100.0 * exp(0.02 * iter);
+         const double alpha = 100.0 * exp(0.02 * (a.iter_base + iter)); /* r->iter of the whole command */
          const double sigma = 1.0 / sqrt(alpha);
          uint32_t *saved = mts + 626;
          int *scratch = reinterpret_cast<int *>(mts + 1252);
@@ -629,6 +629,27 @@ __global__ void best_kernel(const double *costs, const int *status, int R, int *
    }
 }
 
+#ifndef OCB_JIT
+/* parity hook: the kernels' own sdf_sample at arbitrary points of the grid frame; err = 1 where
+ * cd_grid_lookup_index rejects the point, value = HUGE_VAL where interp returns it (the gradient
+ * is computed regardless, as cd_grid_double_grad does) */
+__global__ void sdf_sample_kernel(const OcbSdfDev S, const double *__restrict__ pts, int k, double *__restrict__ vals,
+                                  double *__restrict__ grads, int *__restrict__ errs)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
+   {
+      const double g[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+      double v = 0.0, gg[3] = {0.0, 0.0, 0.0};
+      const bool in = sdf_sample(S, g, v, gg);
+      errs[i] = in ? 0 : 1;
+      vals[i] = in ? v : 0.0;
+      grads[3 * i] = in ? gg[0] : 0.0;
+      grads[3 * i + 1] = in ? gg[1] : 0.0;
+      grads[3 * i + 2] = in ? gg[2] : 0.0;
+   }
+}
+#endif
+
 } /* namespace */
 
 #ifdef OCB_JIT
@@ -649,14 +670,9 @@ extern "C" size_t ocb_chomp_smem_bytes(const OcbChompArgs *a)
 template <int NT_MAX, bool FLOAT, int PP, int NN>
 static cudaError_t launch_variant(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
-   static size_t configured = 0;
-   if (smem_bytes > configured)
-   {
-      cudaError_t e = cudaFuncSetAttribute(chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
-      if (e != cudaSuccess) return e;
-      configured = smem_bytes;
-   }
+   static OcbSmemOptIn optin; /* one per instantiation, keyed by device inside */
+   cudaError_t e = optin.ensure(chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN>, smem_bytes);
+   if (e != cudaSuccess) return e;
    chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN><<<args->R, threads, smem_bytes, st>>>(*args);
    return cudaGetLastError();
 }
@@ -697,6 +713,15 @@ extern "C" cudaError_t ocb_launch_init_traj(double *traj, const double *q_start,
       if (nb > 148 * 8) nb = 148 * 8;
       normalize_rows_kernel<<<nb, 256, 0, st>>>(traj, rows, n);
    }
+   return cudaGetLastError();
+}
+
+extern "C" cudaError_t ocb_launch_sdf_sample(const OcbSdfDev *sdf, const double *d_points, int k, double *d_values,
+                                             double *d_grads, int *d_errs, cudaStream_t st)
+{
+   int blocks = (k + 127) / 128;
+   if (blocks > 148 * 8) blocks = 148 * 8;
+   sdf_sample_kernel<<<blocks, 128, 0, st>>>(*sdf, d_points, k, d_values, d_grads, d_errs);
    return cudaGetLastError();
 }
 

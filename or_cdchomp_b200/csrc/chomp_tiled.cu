@@ -508,10 +508,11 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
    __syncthreads();
 
    /* ---- HMC momentum resample (mod.cpp:2755-2768) ---- */
-   if (a.use_hmc && iter == a.hmc_next[run])
+   const int ref_iter = a.iter_base + iter; /* the reference's r->iter (mod.cpp:2752) */
+   if (a.use_hmc && ref_iter == a.hmc_next[run])
    {
       for (int e = tid; e < 625; e += NT) mts[e] = a.mt_state[(size_t) run * 625 + e];
-      const double alpha = 100.0 * exp(0.02 * iter);
+      const double alpha = 100.0 * exp(0.02 * ref_iter);
       const double sigma = 1.0 / sqrt(alpha);
       uint32_t *saved = mts + 626;
       int *scratch = reinterpret_cast<int *>(mts + 1252);
@@ -536,7 +537,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
       leapfrog_first = 1;
       __syncthreads();
       for (int e = tid; e < 625; e += NT) a.mt_state[(size_t) run * 625 + e] = mts[e];
-      if (tid == 0) a.hmc_next[run] = iter + 1 + (int) (-log(u) / a.hmc_lambda);
+      if (tid == 0) a.hmc_next[run] = ref_iter + 1 + (int) (-log(u) / a.hmc_lambda);
    }
 
    /* ---- G = G_obs / m + A T + B (chomp.c:496-517) ---- */
@@ -642,20 +643,11 @@ extern "C" size_t ocb_run_update_smem_bytes(const OcbChompArgs *a)
 extern "C" cudaError_t ocb_launch_chomp_tiled(const OcbChompArgs *args, size_t tile_smem, size_t run_smem,
                                               int run_threads, cudaStream_t st, long *launches)
 {
-   static size_t conf_tile = 0, conf_run = 0;
-   cudaError_t e;
-   if (tile_smem > conf_tile)
-   {
-      e = cudaFuncSetAttribute(chomp_tile_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tile_smem);
-      if (e != cudaSuccess) return e;
-      conf_tile = tile_smem;
-   }
-   if (run_smem > conf_run)
-   {
-      e = cudaFuncSetAttribute(chomp_run_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) run_smem);
-      if (e != cudaSuccess) return e;
-      conf_run = run_smem;
-   }
+   static OcbSmemOptIn optin_tile, optin_run; /* keyed by device inside */
+   cudaError_t e = optin_tile.ensure(chomp_tile_cost_kernel, tile_smem);
+   if (e != cudaSuccess) return e;
+   e = optin_run.ensure(chomp_run_update_kernel, run_smem);
+   if (e != cudaSuccess) return e;
    const int tile_grid = args->R * args->n_tiles;
    for (int iter = 0; iter <= args->n_iter; iter++)
    {

@@ -734,6 +734,61 @@ extern "C" int ocb_sdf_alias(ocb_engine *e, int id, const double pose_world_gsdf
 }
 
 /* -------------------------------------------------------------------- batch */
+/* device-side descriptor of a resident field (what the kernels stage in shared memory) */
+static void fill_sdf_dev(const SdfSlot &s, OcbSdfDev &d)
+{
+   memset(&d, 0, sizeof(d));
+   d.data = s.d_data;
+   for (int k = 0; k < 3; k++)
+   {
+      d.size[k] = s.sizes[k];
+      d.length[k] = s.lengths[k];
+      d.scale[k] = s.sizes[k] / s.lengths[k];
+      d.cell[k] = s.lengths[k] / s.sizes[k];
+      /* sdf_sample's exact-path thresholds (chomp_device.cuh): relative 1e-10 around the decisions */
+      d.edge_lo[k] = s.sizes[k] * (1.0 - 1e-10);
+      d.edge_hi[k] = s.sizes[k] * (1.0 + 1e-10);
+      d.near[k] = s.sizes[k] * 1e-10;
+   }
+   /* pose_gsdf_world = inverse of the snapshot pose (cd_kin_pose_invert, mod.cpp:2368) */
+   const double *p = s.pose;
+   const double qi[4] = {-p[3], -p[4], -p[5], p[6]};
+   double Ri[9];
+   quat_to_R(qi, Ri);
+   for (int r = 0; r < 3; r++) d.tgw[r] = -(Ri[3 * r] * p[0] + Ri[3 * r + 1] * p[1] + Ri[3 * r + 2] * p[2]);
+   memcpy(d.Rgw, Ri, sizeof(Ri));
+   quat_to_R(p + 3, d.Rwg);
+}
+
+/* cd_grid_double_interp + cd_grid_double_grad (grid.c:331-454) of a resident field at k points given
+ * in the GRID frame -- the device function the CHOMP kernels sample with, exposed for parity tests */
+extern "C" int ocb_sdf_sample_host(ocb_engine *e, int id, const double *points, int k, double *values,
+                                   double *grads, int *errs)
+{
+   if (!e || !points || !values || !grads || !errs || k < 0) return fail(OCB_ERR_ARG, "bad argument");
+   if (id < 0 || id >= (int) e->sdfs.size() || !e->sdfs[id].used) return fail(OCB_ERR_ARG, "bad sdf id %d", id);
+   if (k == 0) return OCB_OK;
+   CU(cudaSetDevice(e->device));
+   OcbSdfDev d;
+   fill_sdf_dev(e->sdfs[id], d);
+   double *dp = nullptr, *dv = nullptr, *dg = nullptr;
+   int *de = nullptr;
+   cudaError_t err = pool_alloc(e, (void **) &dp, (size_t) k * 3 * sizeof(double));
+   if (err == cudaSuccess) err = pool_alloc(e, (void **) &dv, (size_t) k * sizeof(double));
+   if (err == cudaSuccess) err = pool_alloc(e, (void **) &dg, (size_t) k * 3 * sizeof(double));
+   if (err == cudaSuccess) err = pool_alloc(e, (void **) &de, (size_t) k * sizeof(int));
+   if (err == cudaSuccess) err = cudaMemcpyAsync(dp, points, (size_t) k * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+   if (err == cudaSuccess) err = ocb_launch_sdf_sample(&d, dp, k, dv, dg, de, e->stream);
+   if (err == cudaSuccess) e->launches++;
+   if (err == cudaSuccess) err = cudaMemcpyAsync(values, dv, (size_t) k * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+   if (err == cudaSuccess) err = cudaMemcpyAsync(grads, dg, (size_t) k * 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+   if (err == cudaSuccess) err = cudaMemcpyAsync(errs, de, (size_t) k * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+   pool_free(e, dp); pool_free(e, dv); pool_free(e, dg); pool_free(e, de);
+   if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "sdf_sample: %s", cudaGetErrorString(err));
+   return OCB_OK;
+}
+
 struct ocb_batch
 {
    ocb_engine *e = nullptr;
@@ -1220,30 +1275,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    a.hmc_lambda = params->hmc_resample_lambda;
 
    std::vector<OcbSdfDev> sd(n_sdfs);
-   for (int i = 0; i < n_sdfs; i++)
-   {
-      const SdfSlot &s = e->sdfs[sdf_ids[i]];
-      OcbSdfDev &d = sd[i];
-      memset(&d, 0, sizeof(d));
-      d.data = s.d_data;
-      for (int k = 0; k < 3; k++)
-      {
-         d.size[k] = s.sizes[k];
-         d.length[k] = s.lengths[k];
-         d.scale[k] = s.sizes[k] / s.lengths[k];
-         d.cell[k] = s.lengths[k] / s.sizes[k];
-      }
-      /* pose_gsdf_world = inverse of the snapshot pose (cd_kin_pose_invert, mod.cpp:2368) */
-      double inv[7];
-      const double *p = s.pose;
-      const double qi[4] = {-p[3], -p[4], -p[5], p[6]};
-      double Ri[9];
-      quat_to_R(qi, Ri);
-      for (int r = 0; r < 3; r++) inv[r] = -(Ri[3 * r] * p[0] + Ri[3 * r + 1] * p[1] + Ri[3 * r + 2] * p[2]);
-      memcpy(d.Rgw, Ri, sizeof(Ri));
-      d.tgw[0] = inv[0]; d.tgw[1] = inv[1]; d.tgw[2] = inv[2];
-      quat_to_R(p + 3, d.Rwg);
-   }
+   for (int i = 0; i < n_sdfs; i++) fill_sdf_dev(e->sdfs[sdf_ids[i]], sd[i]);
 
 #define TRY(x) do { rc = (x); if (rc) { ocb_batch_destroy(b); return rc; } } while (0)
    TRY(batch_upload(b, &a.spheres, C.spheres));
@@ -1358,6 +1390,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
 }
 
 extern "C" int ocb_batch_uses_jit(const ocb_batch *b) { return (b && b->jit_kernel) ? 1 : 0; }
+extern "C" int ocb_batch_tile_width(const ocb_batch *b) { return (b && b->args.tiled) ? b->args.tile_w : 0; }
 
 extern "C" int ocb_batch_dims(const ocb_batch *b, int *n_runs, int *n_points, int *n_dof)
 {
@@ -1467,10 +1500,22 @@ extern "C" int ocb_batch_capture_gradient(ocb_batch *b, int mode)
    return OCB_OK;
 }
 
-extern "C" int ocb_batch_iterate_async(ocb_batch *b, int n_iter)
+extern "C" int ocb_batch_iterate_async(ocb_batch *b, int n_iter) { return ocb_batch_iterate_from_async(b, 0, n_iter); }
+
+extern "C" int ocb_batch_iterate_from(ocb_batch *b, int first_iter, int n_iter, double *cost_total, double *cost_obs,
+                                      double *cost_smooth, int *status)
+{
+   int rc = ocb_batch_iterate_from_async(b, first_iter, n_iter);
+   if (rc) return rc;
+   return ocb_batch_get_costs(b, cost_total, cost_obs, cost_smooth, status);
+}
+
+extern "C" int ocb_batch_iterate_from_async(ocb_batch *b, int first_iter, int n_iter)
 {
    if (!b) return fail(OCB_ERR_ARG, "you must pass a created run!");
    if (n_iter < 0) return fail(OCB_ERR_ARG, "n_iter must be >=0!");
+   if (first_iter < 0) return fail(OCB_ERR_ARG, "first_iter must be >=0!");
+   b->args.iter_base = first_iter;
    CU(cudaSetDevice(b->e->device));
    OcbChompArgs &a = b->args;
    if (a.trace_on && n_iter > b->trace_cap)

@@ -56,6 +56,9 @@ struct OcbSdfDev
    double Rgw[9];      /* rotation of pose_gsdf_world (world -> grid), row-major */
    double tgw[3];
    double Rwg[9];      /* rotation of pose_world_gsdf (grid -> world) */
+   /* sdf_sample's fast path (y = p * scale in cells): y > edge_hi is outside beyond rounding,
+    * y > edge_lo or a position within `near` of a cell face / centre plane takes the exact path */
+   double edge_lo[3], edge_hi[3], near[3];
 };
 
 struct OcbChompArgs
@@ -68,7 +71,8 @@ struct OcbChompArgs
    int tiled, ng;          /* tiled: large-robot path (chomp_tiled.cu); ng: joint frames that carry spheres */
    int n_desc, NAp;        /* NAp: padded active part of a cut2 row (>= nsa + 3); row = NAp + nsi */
    int tile_w, n_tiles;    /* tiled path: waypoints per tile (32, 16 or 8), tiles per run */
-   int floating, pad0;     /* floating base: rows start with the base pose, joint 0 is the base frame */
+   int floating, iter_base; /* floating base: rows start with the base pose, joint 0 is the base frame;
+                              iter_base: the reference's r->iter at the first iteration of this launch (HMC schedule) */
    /* robot */
    OcbJointDev joints[OCB_MAX_JOINTS];
    const OcbSphereDev *spheres;
@@ -112,6 +116,33 @@ struct OcbChompArgs
    size_t ws_stride;      /* doubles of per-run workspace in shared memory (persistent kernel) */
 };
 
+#if !defined(__CUDACC_RTC__) && defined(__cplusplus)
+#include <mutex>
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel:
+ * engines on several GPUs in one process each need their own opt-in.  Remembers, per device,
+ * the largest size a kernel has been configured for; safe across engine threads. */
+struct OcbSmemOptIn
+{
+   std::mutex mu;
+   size_t configured[64] = {0};
+   template <class K>
+   cudaError_t ensure(K kernel, size_t bytes)
+   {
+      int dev = 0;
+      cudaError_t e = cudaGetDevice(&dev);
+      if (e != cudaSuccess) return e;
+      std::lock_guard<std::mutex> lock(mu);
+      if (dev < 0 || dev >= 64 || bytes > configured[dev])
+      {
+         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+         if (e != cudaSuccess) return e;
+         if (dev >= 0 && dev < 64) configured[dev] = bytes;
+      }
+      return cudaSuccess;
+   }
+};
+#endif
+
 #ifndef __CUDACC_RTC__
 #ifdef __cplusplus
 extern "C" {
@@ -132,6 +163,8 @@ cudaError_t ocb_launch_init_traj(double *traj, const double *q_start, const doub
                                  int R, int P, int n, int floating, cudaStream_t st);
 cudaError_t ocb_launch_best(const double *costs, const int *status, int R, int *best_run,
                             double *best_cost, cudaStream_t st);
+cudaError_t ocb_launch_sdf_sample(const OcbSdfDev *sdf, const double *d_points, int k, double *d_values,
+                                  double *d_grads, int *d_errs, cudaStream_t st);
 
 /* sdf_kernels.cu */
 cudaError_t ocb_launch_dt_sqeuc(const double *d_func, double *d_out, const int sizes[3],

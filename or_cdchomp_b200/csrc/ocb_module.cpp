@@ -868,7 +868,7 @@ struct ocb_module
                fprintf(fp, "\n</data>\n</trajectory>\n");
                fclose(fp);
             }
-            if (ocb_batch_iterate(r->batch, 1, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
+            if (ocb_batch_iterate_from(r->batch, done, 1, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
             done++;
             if (status[0] == OCB_ERR_JLIMIT) break;
             if (max_time != HUGE_VAL)
@@ -890,7 +890,7 @@ struct ocb_module
           * is driven one iteration per launch so the same check applies */
          for (; done < n_iter;)
          {
-            if (ocb_batch_iterate(r->batch, 1, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
+            if (ocb_batch_iterate_from(r->batch, done, 1, total.data(), nullptr, nullptr, status.data()) != OCB_OK) fail_engine("iterate");
             done++;
             clock_gettime(CLOCK_MONOTONIC, &t1);
             if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > max_time) break;

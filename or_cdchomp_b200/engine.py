@@ -56,6 +56,17 @@ class Engine:
     def remove_sdf(self, sid):
         check(self.lib, self.lib.ocb_sdf_remove(self.h, int(sid)), "ocb_sdf_remove")
 
+    def sdf_sample(self, sid, points):
+        """value, gradient and range flag of resident field `sid` at points of its grid frame
+        (cd_grid_double_interp / grad, grid.c:331-454), evaluated by the kernels' own device function"""
+        pts = as_f64(points).reshape(-1, 3)
+        k = len(pts)
+        vals, grads = np.zeros(k), np.zeros((k, 3))
+        errs = np.zeros(k, dtype=np.int32)
+        check(self.lib, self.lib.ocb_sdf_sample_host(self.h, int(sid), dptr(pts), k, dptr(vals), dptr(grads),
+                                                     errs.ctypes.data_as(c_int_p)), "ocb_sdf_sample_host")
+        return vals, grads, errs
+
     # -- SDF build ---------------------------------------------------------
     def sdf_build(self, obs, lengths):
         """cd_grid_double_bin_sdf on host arrays (copies in and out)."""
@@ -190,6 +201,10 @@ class Batch:
     def uses_jit(self):
         return bool(self.lib.ocb_batch_uses_jit(self.h))
 
+    def tile_width(self):
+        """waypoints per tile on the tiled large-robot path, 0 on the persistent kernel"""
+        return int(self.lib.ocb_batch_tile_width(self.h))
+
     def reset(self, q_start=None, q_goal=None, seeds=None):
         """Re-arm the batch (straight lines, zero momentum, fresh rng); async."""
         qs = qg = sp = None
@@ -213,12 +228,14 @@ class Batch:
     def capture_gradient(self, mode):
         check(self.lib, self.lib.ocb_batch_capture_gradient(self.h, int(mode)), "ocb_batch_capture_gradient")
 
-    def iterate(self, n_iter):
-        """Returns (costs[R,3] = total/obs/smooth of the final cost-only pass, status[R])."""
+    def iterate(self, n_iter, first_iter=0):
+        """Returns (costs[R,3] = total/obs/smooth of the final cost-only pass, status[R]).
+        first_iter: number of this call's first iteration within one `iterate` command that is
+        split over several calls (HMC schedule, ocb_batch_iterate_from)."""
         ct, co, cs = np.empty(self.R), np.empty(self.R), np.empty(self.R)
         st = np.empty(self.R, dtype=np.int32)
-        check(self.lib, self.lib.ocb_batch_iterate(self.h, int(n_iter), dptr(ct), dptr(co), dptr(cs),
-                                                  st.ctypes.data_as(c_int_p)), "ocb_batch_iterate")
+        check(self.lib, self.lib.ocb_batch_iterate_from(self.h, int(first_iter), int(n_iter), dptr(ct), dptr(co),
+                                                       dptr(cs), st.ctypes.data_as(c_int_p)), "ocb_batch_iterate_from")
         return np.stack([ct, co, cs], axis=1), st
 
     def iterate_async(self, n_iter):

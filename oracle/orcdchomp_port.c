@@ -407,14 +407,19 @@ static int orc_sphere_cost(void *cptr, struct cd_chomp *c, int ti, double *c_poi
                for (k = 0; k < 3; k++) x_curv[k] += -proj * x_vel[k];
             }
             for (k = 0; k < 3; k++) x_curv[k] *= 1.0 / (x_vel_norm * x_vel_norm);
-            for (k = 0; k < 3; k++) x_grad[k] += -cost_sphere * x_curv[k];
-            /* c_grad += x_vel_norm * J^T x_grad   (dgemv, 1244-1245) */
-            for (j = 0; j < n; j++)
-            {
-               double acc = 0.0;
-               for (k = 0; k < 3; k++) acc += Js[k * n + j] * x_grad[k];
-               c_grad[j] += x_vel_norm * acc;
-            }
+            /* cblas_daxpy returns at once when alpha == 0 (1241): inf / NaN curvature of a
+             * sphere at rest is never read */
+            if (cost_sphere != 0.0)
+               for (k = 0; k < 3; k++) x_grad[k] += -cost_sphere * x_curv[k];
+            /* c_grad += x_vel_norm * J^T x_grad   (dgemv, 1244-1245); alpha == 0 with beta == 1
+             * is BLAS's quick return as well */
+            if (x_vel_norm != 0.0)
+               for (j = 0; j < n; j++)
+               {
+                  double acc = 0.0;
+                  for (k = 0; k < 3; k++) acc += Js[k * n + j] * x_grad[k];
+                  c_grad[j] += x_vel_norm * acc;
+               }
          }
       }
 

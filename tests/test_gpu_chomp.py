@@ -9,6 +9,23 @@ from or_cdchomp_b200 import capi, models
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(scope="module", params=["library", "jit"])
+def engine(request):
+    """both kernels are under test: the library's instantiations and the run-time specialised
+    kernel bench.py runs (ocb_engine_enable_jit); batches too large for the persistent kernel take
+    the tiled path in either case"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from or_cdchomp_b200.engine import Engine
+    e = Engine(0)
+    e.kernel_kind = request.param
+    if request.param == "jit":
+        e.enable_jit(True)
+    yield e
+    e.close()
+
 GRAD_RTOL = 1e-9
 TRAJ_ATOL = 1e-6
 COST_RTOL = 1e-9
@@ -33,6 +50,7 @@ def test_config1_100_iterations(engine, oracle, flavour, wam7, table):
     starts[0], goals[0] = models.WAM7_DEMO_START, models.WAM7_DEMO_GOAL
     sid = engine.upload_sdf(table["desc"])
     b = engine.create_batch(wam7, params, [sid], starts, goals)
+    assert b.uses_jit() == (engine.kernel_kind == "jit"), engine.lib.ocb_last_error()
     b.enable_trace(True)
     costs, status = b.iterate(100)
     traj, trace = b.get_traj(), b.get_trace(100)
@@ -621,3 +639,91 @@ def test_golden_modes(engine):
     assert np.allclose(costs, gold["dense_costs"], rtol=COST_RTOL, atol=0)
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_spheres_at_rest_contribute_nothing(engine, oracle, flavour, wam7, table):
+    """A sphere whose finite-difference velocity is exactly zero (start and goal agree on the
+    proximal joints, or start == goal): the reference divides by |v|^2 unguarded (mod.cpp:1239) but
+    the BLAS calls that would consume the result return at once for a zero scalar (daxpy 1241, dgemv
+    1244), so such a sphere contributes exactly zero -- no NaN may appear, and the oracle agrees."""
+    sd = table["desc"]
+    sid = engine.upload_sdf(sd)
+    params = capi.default_params(n_points=40, lambda_=100.0, obs_factor=300.0)
+    starts, goals = models.random_endpoints(wam7, 3, seed0=7, shrink=0.3)
+    goals[0, :2] = starts[0, :2]        # the four wam2 spheres never move
+    goals[1, :4] = starts[1, :4]        # ... nor anything up to the forearm
+    goals[2] = starts[2]                # nothing moves at all
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    b.capture_gradient(1)
+    b.iterate(1)
+    g = b.get_gradient()
+    assert np.isfinite(g).all()
+    b.close()
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(20)
+    traj = b.get_traj()
+    assert (status == 0).all() and np.isfinite(traj).all() and np.isfinite(costs).all()
+    for r in range(3):
+        run = oracle.Run(wam7, params, [sd], starts[r], goals[r], flavour=flavour)
+        _, _, _, gr = run.iterate(1, want_grads=True)
+        assert np.isfinite(gr).all()
+        assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * max(np.max(np.abs(gr[0])), 1e-300)
+        run.close()
+        run = oracle.Run(wam7, params, [sd], starts[r], goals[r], flavour=flavour)
+        ret, c, _, _ = run.iterate(20)
+        assert ret == 0 and np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL
+        assert np.allclose(costs[r], c, rtol=1e-8, atol=1e-12)
+        run.close()
+    assert np.array_equal(traj[2], np.repeat(starts[2][None], 40, 0))  # a fixed point stays put
+    b.close()
+    engine.remove_sdf(sid)
+
+
+def test_iterate_command_split_over_calls(engine, oracle, flavour, wam7, table):
+    """one `iterate n_iter K` command driven as K single-iteration launches (the module's max_time /
+    trajs_fileformstr loops): with ocb_batch_iterate_from the HMC schedule (resample when r->iter ==
+    hmc_resample_iter, alpha = 100 exp(0.02 r->iter), mod.cpp:2752-2768) is that of the single call."""
+    params = capi.default_params(n_points=37, lambda_=60.0, obs_factor=300.0, use_momentum=1, use_hmc=1,
+                                 hmc_resample_lambda=0.3)
+    seeds = np.array([3, 4, 5, 6], dtype=np.uint32)
+    starts, goals = models.random_endpoints(wam7, 1, seed0=17, shrink=0.3)
+    st, go = np.repeat(starts, len(seeds), 0), np.repeat(goals, len(seeds), 0)
+    sid = engine.upload_sdf(table["desc"])
+    K = 18
+    b1 = engine.create_batch(wam7, params, [sid], st, go, seeds=seeds)
+    c1, s1 = b1.iterate(K)
+    b2 = engine.create_batch(wam7, params, [sid], st, go, seeds=seeds)
+    for k in range(K):
+        c2, s2 = b2.iterate(1, first_iter=k)
+    assert np.array_equal(b1.get_traj(), b2.get_traj()) and np.array_equal(c1, c2)
+    for r, seed in enumerate(seeds):
+        run = oracle.Run(wam7, params, [table["desc"]], st[r], go[r], seed=int(seed), flavour=flavour)
+        ret, c, _, _ = run.iterate(K)
+        assert ret == 0 and run.hmc_next() > 1            # at least one resample after the first
+        assert np.max(np.abs(b2.get_traj()[r] - run.traj())) <= TRAJ_ATOL
+        run.close()
+    b1.close()
+    b2.close()
+    engine.remove_sdf(sid)
+
+
+def test_two_engines_in_one_process(wam7, table):
+    """two engine handles in one process (the one-host-thread-per-GPU design of SURVEY section 8e;
+    here both on device 0, and on devices 0 and 1 when the box has them): same results, and the
+    per-device shared-memory opt-in of every kernel instantiation holds for each."""
+    import torch
+    from or_cdchomp_b200.engine import Engine
+    params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
+    starts, goals = models.random_endpoints(wam7, 8)
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    out = []
+    engines = [Engine(d) for d in devs]
+    for e in engines:
+        sid = e.upload_sdf(table["desc"])
+        b = e.create_batch(wam7, params, [sid], starts, goals)
+        costs, status = b.iterate(15)
+        out.append((b.get_traj(), costs, status))
+        b.close()
+    for e in engines:
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])

@@ -324,3 +324,18 @@ def test_port_matches_golden_modes(oracle):
     ret, c, _, gr = run.iterate(6, want_grads=True)
     assert ret == 0 and np.max(np.abs(run.traj() - gold["dense_traj"][0])) <= 1e-9
     run.close()
+
+
+def test_sphere_at_rest_is_finite(oracle, flavour, wam7, table):
+    """mod.cpp:1239 divides by |v|^2 unguarded, but cblas_daxpy (1241) and cblas_dgemv (1244) return
+    at once for a zero scalar, so a sphere at rest contributes exactly zero: the restated callbacks
+    must reproduce that quick return instead of spreading NaN."""
+    params = capi.default_params(n_points=30, lambda_=100.0, obs_factor=300.0)
+    starts, goals = models.random_endpoints(wam7, 2, seed0=7, shrink=0.3)
+    goals[0, :2] = starts[0, :2]
+    goals[1] = starts[1]
+    for r in range(2):
+        run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
+        ret, c, _, gr = run.iterate(3, want_grads=True)
+        assert ret == 0 and np.isfinite(gr).all() and np.isfinite(c).all() and np.isfinite(run.traj()).all()
+        run.close()
