@@ -27,6 +27,9 @@
  *   - each SDF sample reads its 4 cells once and yields value and gradient.
  */
 #include "chomp_device.cuh"
+#ifdef OCB_JIT_ROBOT
+#include "chomp_jit_robot.cuh" /* this batch's robot as straight-line code (run-time compilation only) */
+#endif
 
 /* Sizes of the compiled robot and the mode flags: kernel arguments in the library's own
  * instantiations, literal constants when the kernel is compiled at run time for one batch
@@ -191,6 +194,12 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
    if (want_grad)
       for (int k = 0; k < 6 * DIM(a, ng); k++) Wg[k * Pp] = 0.0;
 
+#ifdef OCB_JIT_ROBOT
+   /* every self-collision range test of this waypoint in one straight-line pass */
+   const JrHits hits = jr_pair_hits(ws, Pp, t);
+   int pair_begin = 0;
+#endif
+
    for (int j = 0; j < DIM(a, nj); j++)
    {
       const OcbJointDev &J = a.joints[j];
@@ -199,31 +208,47 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
       for (int s = J.sph_begin; s < J.sph_end; s++)
       {
          const double *ps = ws + 3 * s * Pp + t;
-         double p[3], vel[3], acc[3];
+         const double p[3] = {ps[0], ps[Pp], ps[2 * Pp]};
+         const double radius = tb.radius[s];
+
+         /* --- obstacle term, first step: which field, how far (mod.cpp:1169-1198) --- */
+         double d_obs, bg[3];
+         const int best = obstacle_probe(a, tb.sdfs, p, radius, DIM(a, nsdf), d_obs, bg);
+         const bool obs = (best >= 0) && (d_obs < a.eps);
+#ifdef OCB_JIT_ROBOT
+         /* this sphere's partners in range: bits over its static partner list, then the inactive spheres */
+         const int pair_end = jr_pair_begin[s + 1];
+         unsigned hit_a = jr_hit_bits(hits, pair_begin, pair_end - pair_begin);
+         unsigned hit_i = (JR_NSI > 0) ? jr_hit_bits(hits, JR_NPA + s * JR_NSI, JR_NSI) : 0u;
+         const int pb = pair_begin;
+         pair_begin = pair_end;
+         /* neither an obstacle within epsilon nor a sphere within range: cost and force are exactly zero */
+         if (!obs && !(hit_a | hit_i)) continue;
+#endif
+         double vel[3];
 #pragma unroll
-         for (int k = 0; k < 3; k++)
-         {
-            const double pc = ps[k * Pp];
-            const double pm = ps[k * Pp - 1];
-            const double pp = ps[k * Pp + 1];
-            p[k] = pc;
-            vel[k] = (pp - pm) * inv2dt;
-            acc[k] = (pc * -2.0 + pm + pp) * invdt2;
-         }
+         for (int k = 0; k < 3; k++) vel[k] = (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
          const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
          const double rv = rsqrt(vn2);
          const double vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
          const double iv2 = rv * rv; /* 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
          const bool moving = vn > 0.000001;
-         const double radius = tb.radius[s];
          double cost_s = 0.0;
          double f[3] = {0.0, 0.0, 0.0};
 
-         /* --- obstacle term (mod.cpp:1169-1249) --- */
-         obstacle_term(a, tb.sdfs, p, vel, acc, vn, iv2, moving, radius, want_grad, cost_s, f);
+         /* --- obstacle term, second step (mod.cpp:1200-1249) --- */
+         if (obs)
+         {
+            double acc[3] = {0.0, 0.0, 0.0};
+            if (want_grad)
+            {
+#pragma unroll
+               for (int k = 0; k < 3; k++) acc[k] = (p[k] * -2.0 + ps[k * Pp - 1] + ps[k * Pp + 1]) * invdt2;
+            }
+            obstacle_apply(a, tb.sdfs[best], d_obs, bg, vel, acc, vn, iv2, moving, want_grad, cost_s, f);
+         }
 
          /* --- self collision, each unordered pair once (1251-1317) --- */
-         const double *crow = tb.cut2 + s * row;
          const double ws_self = vn * a.obs_factor_self;
          /* a partner within range: q its centre, po its column in ws (NULL: inactive, frozen) */
          auto in_range = [&](const double q[3], const double *po, int o)
@@ -289,6 +314,26 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
 #pragma unroll
             for (int r = 0; r < 3; r++) f[r] += x[r];
          };
+#ifdef OCB_JIT_ROBOT
+         /* active partners in ascending order, then the inactive ones (frozen in the world, mod.cpp:2332-2345) */
+         while (hit_a)
+         {
+            const int k = __ffs(hit_a) - 1;
+            hit_a &= hit_a - 1;
+            const int o = jr_pair_o[pb + k];
+            const double *po = ws + 3 * o * Pp + t;
+            const double q[3] = {po[0], po[Pp], po[2 * Pp]};
+            in_range(q, po, o);
+         }
+         while (hit_i)
+         {
+            const int i = __ffs(hit_i) - 1;
+            hit_i &= hit_i - 1;
+            const double q[3] = {jr_inactive_pos[i][0], jr_inactive_pos[i][1], jr_inactive_pos[i][2]};
+            in_range(q, nullptr, nsa + i);
+         }
+#else
+         const double *crow = tb.cut2 + s * row;
          /* active partners: range tests four at a time (independent chains); the padded
           * tail of the cut2 row is -1 and never passes */
          for (int o0 = s + 1; o0 < nsa; o0 += 4)
@@ -320,6 +365,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
             const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
             if (dx * dx + dy * dy + dz * dz <= crow[DIM(a, NAp) + i]) in_range(q, nullptr, nsa + i);
          }
+#endif
          cost += cost_s;
          if (want_grad)
          {
@@ -336,7 +382,14 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
       }
    }
-   if (want_grad) flush_wrenches<FLOAT, PP>(a, tb, Ts, ws, Gs, t);
+   if (want_grad)
+   {
+#ifdef OCB_JIT_ROBOT
+      jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t);
+#else
+      flush_wrenches<FLOAT, PP>(a, tb, Ts, ws, Gs, t);
+#endif
+   }
    return cost;
 }
 
@@ -453,7 +506,11 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       }
 
       /* ---- forward kinematics of all P waypoints ---- */
+#ifdef OCB_JIT_ROBOT
+      for (int t = tid; t < P; t += NT) jr_fk_waypoint<FLOAT>(Ts, ws, Pp, t);
+#else
       for (int t = tid; t < P; t += NT) fk_waypoint<FLOAT, PP>(a, tb, Ts, ws, t);
+#endif
       __syncthreads();
 
       /* ---- obstacle + self-collision cost / gradient, then G = G/m + A T + B ---- */

@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -746,9 +747,9 @@ static void fill_sdf_dev(const SdfSlot &s, OcbSdfDev &d)
       d.scale[k] = s.sizes[k] / s.lengths[k];
       d.cell[k] = s.lengths[k] / s.sizes[k];
       /* sdf_sample's exact-path thresholds (chomp_device.cuh): relative 1e-10 around the decisions */
-      d.edge_lo[k] = s.sizes[k] * (1.0 - 1e-10);
       d.edge_hi[k] = s.sizes[k] * (1.0 + 1e-10);
       d.near[k] = s.sizes[k] * 1e-10;
+      d.near_hi[k] = 0.5 - d.near[k];
    }
    /* pose_gsdf_world = inverse of the snapshot pose (cd_kin_pose_invert, mod.cpp:2368) */
    const double *p = s.pose;
@@ -1168,6 +1169,126 @@ int compile_robot(const ocb_robot *rb, double eps_self, bool floating, CompiledR
    return OCB_OK;
 }
 
+/* The compiled robot as constexpr tables for the run-time compiler (csrc/chomp_jit_robot.cuh turns
+ * them into straight-line code).  Returns an empty string when the robot does not suit that form
+ * (more pairs than the hit set has bits); the generic run-time specialised kernel is used then. */
+std::string jit_robot_header(const CompiledRobot &C, double eps_self)
+{
+   const int nj = (int) C.joints.size(), nsa = (int) C.spheres.size(), nsi = (int) C.inactive_radius.size();
+   const int NAp = nsa + 3, row = NAp + nsi;
+   /* static pair list: own sphere ascending, partner ascending, pairs on the same link left out (mod.cpp:1256) */
+   std::vector<int> pair_begin(nsa + 1, 0), pair_o, kind;
+   std::vector<double> cut2;
+   for (int s = 0; s < nsa; s++)
+   {
+      pair_begin[s] = (int) pair_o.size();
+      for (int o = s + 1; o < nsa; o++)
+      {
+         const double c2 = C.cut2[(size_t) s * row + o];
+         if (c2 < 0.0) continue;
+         int k = 0;
+         if (C.spheres[s].group == C.spheres[o].group)
+         {
+            /* rigidly attached to the same joint frame: the distance never changes (up to the rounding of the
+             * frames, ~1e-15); decided here unless it is within 1e-9 of the cut-off */
+            double d2 = 0.0;
+            for (int c = 0; c < 3; c++) d2 += (C.spheres[s].pos[c] - C.spheres[o].pos[c]) * (C.spheres[s].pos[c] - C.spheres[o].pos[c]);
+            if (d2 <= c2 * (1.0 - 1e-9)) k = 1;
+            else if (d2 >= c2 * (1.0 + 1e-9)) k = 2;
+         }
+         pair_o.push_back(o);
+         kind.push_back(k);
+         cut2.push_back(c2);
+      }
+   }
+   pair_begin[nsa] = (int) pair_o.size();
+   const int npa = (int) pair_o.size();
+   for (int s = 0; s < nsa; s++)
+      for (int i = 0; i < nsi; i++)
+      {
+         const double c2 = C.cut2[(size_t) s * row + NAp + i];
+         kind.push_back(c2 < 0.0 ? 2 : 0);
+         cut2.push_back(c2);
+      }
+   const int nbits = npa + nsa * nsi;
+   if (nbits > 128 || nbits == 0) return std::string();
+   for (int s = 0; s < nsa; s++)
+      if (pair_begin[s + 1] - pair_begin[s] > 32 || nsi > 32) return std::string();
+   const int words = (nbits + 31) / 32;
+   std::vector<unsigned> always(words, 0u);
+   for (int k = 0; k < nbits; k++)
+      if (kind[k] == 1) always[k >> 5] |= 1u << (k & 31);
+   std::vector<int> own_tests(nsa, 0);
+   for (int s = 0; s < nsa; s++)
+   {
+      for (int k = pair_begin[s]; k < pair_begin[s + 1]; k++) own_tests[s] += (kind[k] == 0);
+      for (int i = 0; i < nsi; i++) own_tests[s] += (kind[npa + s * nsi + i] == 0);
+   }
+
+   std::string h;
+   char buf[128];
+   auto def = [&](const char *name, int v) { snprintf(buf, sizeof(buf), "#define %s %d\n", name, v); h += buf; };
+   auto dbl = [&](double v)
+   {
+      if (v == HUGE_VAL) return std::string("(1.0 / 0.0)");
+      if (v == -HUGE_VAL) return std::string("(-1.0 / 0.0)");
+      snprintf(buf, sizeof(buf), "%a", v); /* hexadecimal floating literal: exact */
+      return std::string(buf);
+   };
+   auto iarr = [&](const char *name, const std::vector<int> &v)
+   {
+      h += std::string("__device__ constexpr int ") + name + "[" + std::to_string(std::max<size_t>(v.size(), 1)) + "] = {";
+      for (size_t i = 0; i < std::max<size_t>(v.size(), 1); i++) h += (i ? ", " : "") + std::to_string(i < v.size() ? v[i] : 0);
+      h += "};\n";
+   };
+   auto darr2 = [&](const char *name, const std::vector<double> &v, int cols)
+   {
+      const size_t rows = std::max<size_t>(v.size() / cols, 1);
+      h += std::string("__device__ constexpr double ") + name + "[" + std::to_string(rows) + "][" + std::to_string(cols) + "] = {";
+      for (size_t r = 0; r < rows; r++)
+      {
+         h += r ? ", {" : "{";
+         for (int c = 0; c < cols; c++) h += (c ? ", " : "") + dbl(r * cols + c < v.size() ? v[r * cols + c] : 0.0);
+         h += "}";
+      }
+      h += "};\n";
+   };
+   auto darr = [&](const char *name, const std::vector<double> &v)
+   {
+      h += std::string("__device__ constexpr double ") + name + "[" + std::to_string(std::max<size_t>(v.size(), 1)) + "] = {";
+      for (size_t i = 0; i < std::max<size_t>(v.size(), 1); i++) h += (i ? ", " : "") + dbl(i < v.size() ? v[i] : 0.0);
+      h += "};\n";
+   };
+   h += "/* generated by ocb_engine.cu (jit_robot_header): one compiled robot */\n";
+   (void) eps_self;
+   def("JR_NJ", nj); def("JR_NSA", nsa); def("JR_NSI", nsi); def("JR_NSLOTS", C.n_slots); def("JR_NG", C.n_groups);
+   def("JR_NPA", npa); def("JR_HIT_WORDS", words);
+   std::vector<double> XR, Xt, c0, c1, sp, ip;
+   std::vector<int> type, dof, load, save, sb, se, db, de;
+   for (int j = 0; j < nj; j++)
+   {
+      const OcbJointDev &J = C.joints[j];
+      XR.insert(XR.end(), J.XR, J.XR + 9);
+      Xt.insert(Xt.end(), J.Xt, J.Xt + 3);
+      c0.push_back(J.c0); c1.push_back(J.c1);
+      type.push_back(J.type); dof.push_back(J.dof); load.push_back(J.load); save.push_back(J.save);
+      sb.push_back(J.sph_begin); se.push_back(J.sph_end); db.push_back(J.desc_begin); de.push_back(J.desc_end);
+   }
+   for (int s = 0; s < nsa; s++) sp.insert(sp.end(), C.spheres[s].pos, C.spheres[s].pos + 3);
+   darr2("jr_XR", XR, 9); darr2("jr_Xt", Xt, 3); darr("jr_c0", c0); darr("jr_c1", c1);
+   iarr("jr_type", type); iarr("jr_dof", dof); iarr("jr_load", load); iarr("jr_save", save);
+   iarr("jr_sph_begin", sb); iarr("jr_sph_end", se); iarr("jr_desc_begin", db); iarr("jr_desc_end", de);
+   iarr("jr_desc", C.desc);
+   darr2("jr_sph_pos", sp, 3);
+   darr2("jr_inactive_pos", C.inactive_pos, 3);
+   iarr("jr_pair_begin", pair_begin); iarr("jr_pair_o", pair_o); iarr("jr_pair_kind", kind); darr("jr_pair_cut2", cut2);
+   iarr("jr_own_tests", own_tests);
+   h += "__device__ constexpr unsigned jr_hits_always[" + std::to_string(words) + "] = {";
+   for (int k = 0; k < words; k++) h += (k ? ", " : "") + std::to_string(always[k]) + "u";
+   h += "};\n";
+   return h;
+}
+
 void seed_mt(uint32_t *mt, unsigned int seed)
 {
    /* gsl_rng_set on mt19937: seed 0 -> 4357, 2002 initialisation */
@@ -1372,7 +1493,11 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       int min_blocks = (int) ((size_t) e->smem_per_sm / (b->smem + 1024));
       min_blocks = std::max(1, std::min(min_blocks, 65536 / (b->threads * 160)));
       char why[512] = "";
-      if (ocb_jit_chomp_kernel(&a, e->device, b->threads, min_blocks, b->smem, &b->jit_kernel, why, sizeof(why)) != 0)
+      /* the robot as straight-line code; OCB_JIT_ROBOT=0 in the environment keeps the table-driven kernel */
+      const char *env = getenv("OCB_JIT_ROBOT");
+      const std::string robot_hdr = (env && env[0] == '0') ? std::string() : jit_robot_header(C, params->epsilon_self);
+      if (ocb_jit_chomp_kernel(&a, e->device, b->threads, min_blocks, b->smem, robot_hdr.c_str(), &b->jit_kernel, why,
+                               sizeof(why)) != 0)
       {
          b->jit_kernel = nullptr; /* the library's own kernel runs instead */
          fail(OCB_ERR_CUDA, "run-time specialisation unavailable: %s", why);
@@ -1387,6 +1512,24 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
 #undef TRY
    *out = b;
    return OCB_OK;
+}
+
+/* the generated robot tables of the run-time specialised kernel (host only; for inspection and tests):
+ * returns the length of the text (0: this robot takes the generic kernel), copies at most cap-1 bytes */
+extern "C" long ocb_debug_jit_robot_header(const ocb_robot *robot, const ocb_params *params, char *buf, size_t cap)
+{
+   if (!robot || !params) return fail(OCB_ERR_ARG, "null argument");
+   CompiledRobot C;
+   int rc = compile_robot(robot, params->epsilon_self, params->floating_base != 0, C);
+   if (rc) return rc;
+   const std::string h = jit_robot_header(C, params->epsilon_self);
+   if (buf && cap)
+   {
+      const size_t n = std::min(h.size(), cap - 1);
+      memcpy(buf, h.data(), n);
+      buf[n] = 0;
+   }
+   return (long) h.size();
 }
 
 extern "C" int ocb_batch_uses_jit(const ocb_batch *b) { return (b && b->jit_kernel) ? 1 : 0; }

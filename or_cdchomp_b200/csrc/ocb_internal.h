@@ -56,9 +56,10 @@ struct OcbSdfDev
    double Rgw[9];      /* rotation of pose_gsdf_world (world -> grid), row-major */
    double tgw[3];
    double Rwg[9];      /* rotation of pose_world_gsdf (grid -> world) */
-   /* sdf_sample's fast path (y = p * scale in cells): y > edge_hi is outside beyond rounding,
-    * y > edge_lo or a position within `near` of a cell face / centre plane takes the exact path */
-   double edge_lo[3], edge_hi[3], near[3];
+   /* sdf_sample's fast path (y = p * scale in cells, u = y - floor(y) - 0.5): y > edge_hi is outside
+    * beyond rounding; |u| < near (centre plane) or |u| > near_hi (cell face, ends of the axis) takes
+    * the exact path */
+   double edge_hi[3], near[3], near_hi[3];
 };
 
 struct OcbChompArgs
@@ -152,7 +153,7 @@ cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int th
 size_t ocb_chomp_smem_bytes(const OcbChompArgs *args);
 /* ocb_jit.cpp: the persistent kernel compiled at run time for one batch's sizes */
 int ocb_jit_chomp_kernel(const OcbChompArgs *args, int device, int threads, int min_blocks, size_t smem,
-                         void **kernel_out, char *err, size_t err_cap);
+                         const char *robot_header, void **kernel_out, char *err, size_t err_cap);
 cudaError_t ocb_jit_launch(void *kernel, const OcbChompArgs *args, int threads, size_t smem, cudaStream_t st);
 /* chomp_tiled.cu */
 size_t ocb_tile_smem_bytes(const OcbChompArgs *args, int tile_w);

@@ -667,7 +667,7 @@ def test_spheres_at_rest_contribute_nothing(engine, oracle, flavour, wam7, table
         run = oracle.Run(wam7, params, [sd], starts[r], goals[r], flavour=flavour)
         _, _, _, gr = run.iterate(1, want_grads=True)
         assert np.isfinite(gr).all()
-        assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * max(np.max(np.abs(gr[0])), 1e-300)
+        assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * np.max(np.abs(gr[0])) + 1e-12  # run 2: G is rounding noise
         run.close()
         run = oracle.Run(wam7, params, [sd], starts[r], goals[r], flavour=flavour)
         ret, c, _, _ = run.iterate(20)
