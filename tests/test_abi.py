@@ -139,24 +139,54 @@ def test_libcd_struct_layouts_match_reference_headers():
 
 def test_kernel_sources_compile_under_nvrtc():
     """the persistent kernel must stay compilable without host headers: the engine compiles these
-    very sources at run time (csrc/ocb_jit.cpp).  NVRTC needs no GPU, so this runs everywhere."""
+    very sources at run time (csrc/ocb_jit.cpp), generic and with the robot written out as
+    constexpr tables (ocb_jit_robot.h, generated by the engine).  NVRTC needs no GPU."""
     try:
         from cuda.bindings import nvrtc
     except Exception:
         pytest.skip("cuda-python (nvrtc bindings) not importable")
+    import ctypes as C
+    from or_cdchomp_b200 import models
+    lib = capi.load_library()
+    lib.ocb_debug_jit_robot_header.restype = C.c_long
     csrc = os.path.join(ROOT, "or_cdchomp_b200", "csrc")
     src = open(os.path.join(csrc, "chomp_kernel.cu")).read()
-    hdrs = {"ocb_internal.h": open(os.path.join(csrc, "ocb_internal.h")).read(),
-            "chomp_device.cuh": open(os.path.join(csrc, "chomp_device.cuh")).read()}
-    for defs in (dict(NT=128, MINBLOCKS=3, FLOAT=0, PP=100, NN=7, nsa=15, nsi=1, NAp=18, n_slots=0, ng=6, nj=7, nsdf=1,
-                      n_desc=21, use_momentum=0, use_hmc=0),
-                 dict(NT=64, MINBLOCKS=1, FLOAT=1, PP=0, NN=11, nsa=9, nsi=0, NAp=12, n_slots=2, ng=5, nj=6, nsdf=3,
-                      n_desc=14, use_momentum=1, use_hmc=1)):
-        err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"chomp_kernel.cu", len(hdrs),
-                                             [v.encode() for v in hdrs.values()], [k.encode() for k in hdrs])
+    names = ["ocb_internal.h", "chomp_device.cuh", "chomp_jit_robot.cuh"]
+    hdrs = {n: open(os.path.join(csrc, n)).read() for n in names}
+
+    def robot_header(robot, params):
+        buf = C.create_string_buffer(1 << 20)
+        n = lib.ocb_debug_jit_robot_header(C.byref(robot.struct), C.byref(params), buf, len(buf))
+        assert 0 < n < len(buf)
+        return buf.value.decode()
+
+    wam = robot_header(models.wam7_robot(), capi.default_params(n_points=100))
+    assert "JR_NPA 96" in wam and "JR_HIT_WORDS 4" in wam   # 105 pairs - 9 on a shared link; + 15 x 1 inactive
+    tree = robot_header(models.prismatic_test_robot(), capi.default_params(n_points=33, floating_base=1))
+    # a robot with more sphere pairs than the hit set has bits keeps the table-driven kernel
+    buf = C.create_string_buffer(16)
+    assert lib.ocb_debug_jit_robot_header(C.byref(models.dense_sphere_arm(40).struct),
+                                          C.byref(capi.default_params()), buf, len(buf)) == 0
+    cases = [
+        (dict(NT=128, MINBLOCKS=3, FLOAT=0, PP=100, NN=7, nsa=15, nsi=1, NAp=18, n_slots=0, ng=6, nj=7, nsdf=1,
+              n_desc=21, use_momentum=0, use_hmc=0), ""),
+        (dict(NT=64, MINBLOCKS=1, FLOAT=1, PP=0, NN=11, nsa=9, nsi=0, NAp=12, n_slots=2, ng=5, nj=6, nsdf=3,
+              n_desc=14, use_momentum=1, use_hmc=1), ""),
+        (dict(NT=128, MINBLOCKS=3, FLOAT=0, PP=100, NN=7, nsa=15, nsi=1, NAp=18, n_slots=0, ng=5, nj=7, nsdf=1,
+              n_desc=22, use_momentum=0, use_hmc=0), wam),
+        (dict(NT=64, MINBLOCKS=1, FLOAT=1, PP=33, NN=11, nsa=8, nsi=0, NAp=11, n_slots=1, ng=6, nj=6, nsdf=2,
+              n_desc=14, use_momentum=1, use_hmc=1), tree),
+    ]
+    for defs, robot in cases:
+        h = dict(hdrs)
+        h["ocb_jit_robot.h"] = robot
+        err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"chomp_kernel.cu", len(h),
+                                             [v.encode() for v in h.values()], [k.encode() for k in h])
         assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS
-        opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-DOCB_JIT=1"]
+        opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-DOCB_JIT=1", b"-default-device"]
         opts += [("-DOCB_JIT_%s=%d" % kv).encode() for kv in defs.items()]
+        if robot:
+            opts.append(b"-DOCB_JIT_ROBOT=1")
         err, = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
         _, n = nvrtc.nvrtcGetProgramLogSize(prog)
         log = b" " * n
@@ -168,5 +198,6 @@ def test_kernel_sources_compile_under_nvrtc():
     # every -D the kernel reads is one ocb_jit.cpp passes
     import re as _re
     used = set(_re.findall(r"OCB_JIT_([A-Za-z_]+)", src)) | set(_re.findall(r"DIM\(a, ([A-Za-z_]+)\)", src))
-    passed = set(_re.findall(r'\{"([A-Za-z_]+)", ', open(os.path.join(csrc, "ocb_jit.cpp")).read()))
+    jit_cpp = open(os.path.join(csrc, "ocb_jit.cpp")).read()
+    passed = set(_re.findall(r'\{"([A-Za-z_]+)", ', jit_cpp)) | set(_re.findall(r"-DOCB_JIT_([A-Za-z_]+)=", jit_cpp))
     assert used - {"f"} <= passed, used - passed
