@@ -21,6 +21,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <set>
 #include <new>
 #include <string>
 #include <utility>
@@ -294,11 +296,32 @@ extern "C" int ocb_engine_create(int device, ocb_engine **out)
    return OCB_OK;
 }
 
+struct ocb_batch;
+static ocb_engine *batch_engine(const ocb_batch *b);
+
+/* Handles of live batches, process wide: a batch outliving its engine (a caller that destroys the
+ * engine first, a garbage collector that runs late) must not touch the freed engine.  Destroying an
+ * engine destroys the batches it still owns; destroying a batch that is no longer registered is a
+ * harmless no-op. */
+static std::mutex g_batches_lock;
+static std::set<ocb_batch *> g_batches;
+static void batch_free(ocb_batch *b);
+
 extern "C" int ocb_engine_destroy(ocb_engine *e)
 {
    if (!e) return OCB_OK;
    cudaSetDevice(e->device);
    cudaStreamSynchronize(e->stream);
+   {
+      std::vector<ocb_batch *> mine;
+      {
+         std::lock_guard<std::mutex> lock(g_batches_lock);
+         for (ocb_batch *b : g_batches)
+            if (batch_engine(b) == e) mine.push_back(b);
+         for (ocb_batch *b : mine) g_batches.erase(b);
+      }
+      for (ocb_batch *b : mine) batch_free(b);
+   }
    for (auto &s : e->sdfs)
       if (s.used && s.owned) pool_free(e, s.d_data);
    if (e->scratch) cudaFree(e->scratch);
@@ -1324,13 +1347,24 @@ static int batch_upload(ocb_batch *b, const T **ptr, const std::vector<T> &h)
    return OCB_OK;
 }
 
-extern "C" int ocb_batch_destroy(ocb_batch *b)
+static ocb_engine *batch_engine(const ocb_batch *b) { return b->e; }
+
+static void batch_free(ocb_batch *b)
 {
-   if (!b) return OCB_OK;
    cudaSetDevice(b->e->device);
    cudaStreamSynchronize(b->e->stream);
    for (void *p : b->owned) pool_free(b->e, p);
    delete b;
+}
+
+extern "C" int ocb_batch_destroy(ocb_batch *b)
+{
+   if (!b) return OCB_OK;
+   {
+      std::lock_guard<std::mutex> lock(g_batches_lock);
+      if (!g_batches.erase(b)) return OCB_OK; /* already gone with its engine */
+   }
+   batch_free(b);
    return OCB_OK;
 }
 
@@ -1369,6 +1403,10 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    ocb_batch *b = new (std::nothrow) ocb_batch();
    if (!b) return fail(OCB_ERR_ALLOC, "out of host memory");
    b->e = e;
+   {
+      std::lock_guard<std::mutex> lock(g_batches_lock);
+      g_batches.insert(b);
+   }
    OcbChompArgs &a = b->args;
    memset(&a, 0, sizeof(a));
    a.R = n_runs; a.P = P; a.m = m; a.n = n;

@@ -105,13 +105,20 @@ class Engine:
               "ocb_flood_relabel_host")
         return g
 
-    def computedistancefield(self, prims, sizes, lengths, cube_extent, want_sdf=True):
+    def computedistancefield(self, prims, sizes, lengths, cube_extent, want_sdf=True, out=None):
         """occupancy -> flood fill + relabel -> SDF with host outputs
-        (src/orcdchomp_mod.cpp:498-560 in the reference)."""
+        (src/orcdchomp_mod.cpp:498-560 in the reference).  out: optional (obs, sdf) host arrays to
+        fill (e.g. page-locked ones)."""
         arr = capi.make_prims(prims)
         shape = tuple(int(s) for s in sizes)
-        obs = np.empty(shape)
-        sdf = np.empty(shape) if want_sdf else None
+        if out is not None:
+            obs, sdf = out
+            assert obs.shape == shape and obs.dtype == np.float64 and obs.flags.c_contiguous
+            assert sdf is None or (sdf.shape == shape and sdf.dtype == np.float64 and sdf.flags.c_contiguous)
+            want_sdf = sdf is not None
+        else:
+            obs = np.empty(shape)
+            sdf = np.empty(shape) if want_sdf else None
         check(self.lib, self.lib.ocb_computedistancefield_host(
             self.h, arr, len(prims), _i3(sizes), _d3(lengths), float(cube_extent), dptr(obs),
             dptr(sdf) if want_sdf else None), "ocb_computedistancefield_host")
