@@ -135,6 +135,11 @@ int ocb_engine_trim(ocb_engine *e);
  * default (environment variable OCB_JIT=1 turns it on for every engine); if NVRTC is missing
  * the library's kernel is used and ocb_last_error() says why. */
 int ocb_engine_enable_jit(ocb_engine *e, int on);
+/* Inspection hook (host only, works without a GPU): the tables the run-time compiler is given for this
+ * robot -- its kinematic tree and static self-collision pair list as constexpr data, which
+ * csrc/chomp_jit_robot.cuh turns into straight-line code.  Returns the length of the text (0: this
+ * robot takes the table-driven kernel), copies at most cap-1 bytes into buf (may be NULL). */
+long ocb_debug_jit_robot_header(const ocb_robot *robot, const ocb_params *params, char *buf, size_t cap);
 
 /* --- SDF residency (replaces mod::sdfs[], mod.cpp:584-586 / 716-718 / 836) --- */
 /* copies the grid to HBM; *id indexes it in later calls */
@@ -262,6 +267,11 @@ int ocb_batch_set_lambda(ocb_batch *b, double lambda);
 /* iterations each run completed in the last iterate call: n_iter, or fewer for a run that left
  * the joint limits (the reference's r->iter when the exception is thrown, mod.cpp:2799-2803) */
 int ocb_batch_get_iterations(ocb_batch *b, int *iterations);
+/* the most projection steps of the joint-limit loop (chomp.c:608-655, at most 1000) any single iteration
+ * of the last iterate call needed, per run: 0 = the run never left its limits.  The loop is the one
+ * part of the algorithm that is not continuous in its own rounding, so this is the
+ * diagnostic that tells a well-conditioned run from a chaotic one. */
+int ocb_batch_get_limit_rounds(ocb_batch *b, int *rounds);
 /* per-iteration cost log of the last iterate call: [R][n_iter][3] (total, obs,
  * smooth) as RAVELOG_INFO prints them (mod.cpp:2798).  Enable before iterate. */
 int ocb_batch_enable_trace(ocb_batch *b, int enable);
@@ -288,6 +298,42 @@ int ocb_batch_device_ptrs(ocb_batch *b, void **d_traj, void **d_costs);
 int ocb_batch_copy_run_traj_device(ocb_batch *b, int run, void *d_dst);
 /* kernel launches issued by this engine since creation (bench bookkeeping)    */
 long ocb_engine_launch_count(const ocb_engine *e);
+
+/* ------------------------------------------------------------------------- */
+/* Several GPUs in one process: G engines, one host thread each, driven in lock
+ * step.  Runs are dealt round-robin (global run r lives on device slot r mod G), fields are
+ * replicated, nothing is exchanged during the iterations; ocb_multi_batch_best is the one exchange
+ * (arg-min of cost_total + the winner's trajectory, over NCCL when libnccl.so.2 is present and the
+ * devices are distinct, else compared on the host and copied device to device).  Outputs are in
+ * global run order, so results do not depend on G.  The reference has no counterpart: its module
+ * advances runs one after the other (mod.cpp:2752-2828). */
+typedef struct ocb_multi ocb_multi;
+typedef struct ocb_multi_batch ocb_multi_batch;
+const char *ocb_multi_last_error(void);
+/* devices: [n_devices] CUDA ordinals (NULL = 0..n-1); an ordinal may repeat (several engines on one GPU) */
+int ocb_multi_create(int n_devices, const int *devices, ocb_multi **out);
+int ocb_multi_destroy(ocb_multi *m);
+int ocb_multi_device_count(const ocb_multi *m);
+int ocb_multi_uses_nccl(const ocb_multi *m);
+int ocb_multi_engine(ocb_multi *m, int slot, ocb_engine **e);
+int ocb_multi_enable_jit(ocb_multi *m, int on);
+int ocb_multi_sdf_upload(ocb_multi *m, const ocb_sdf *sdf, int *id);
+int ocb_multi_computedistancefield_resident(ocb_multi *m, const ocb_prim *prims, int n_prims, const int sizes[3],
+                                            const double lengths[3], double cube_extent,
+                                            const double pose_world_gsdf[7], int *id);
+int ocb_multi_sdf_remove(ocb_multi *m, int id);
+/* arguments as ocb_batch_create, [n_runs] rows in global run order */
+int ocb_multi_batch_create(ocb_multi *m, const ocb_robot *robot, const ocb_params *params, int n_sdfs,
+                           const int *sdf_ids, int n_runs, const double *q_start, const double *q_goal,
+                           const unsigned int *seeds, ocb_multi_batch **out);
+int ocb_multi_batch_dims(const ocb_multi_batch *b, int *n_runs, int *n_points, int *n_dof);
+int ocb_multi_batch_iterate(ocb_multi_batch *b, int n_iter, double *cost_total, double *cost_obs,
+                            double *cost_smooth, int *status);
+int ocb_multi_batch_get_traj(ocb_multi_batch *b, double *traj);
+/* best_run = global id or -1 when every run failed; traj: host [n_points][n_dof] or NULL */
+int ocb_multi_batch_best(ocb_multi_batch *b, int *best_run, double *best_cost, double *traj);
+int ocb_multi_best_traj_device(ocb_multi *m, int slot, void **d_traj);
+int ocb_multi_batch_destroy(ocb_multi_batch *b);
 
 #ifdef __cplusplus
 }

@@ -280,6 +280,7 @@ EXPORTS = {
     "ocb_batch_get_momentum": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),
     "ocb_batch_set_lambda": (C.c_int, [C.c_void_p, C.c_double]),
     "ocb_batch_get_iterations": (C.c_int, [C.c_void_p, c_int_p]),
+    "ocb_batch_get_limit_rounds": (C.c_int, [C.c_void_p, c_int_p]),
     "ocb_batch_enable_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_batch_get_trace": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "ocb_batch_get_traj": (C.c_int, [C.c_void_p, c_double_p]),
@@ -291,6 +292,27 @@ EXPORTS = {
     "ocb_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "ocb_batch_copy_run_traj_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ocb_engine_launch_count": (C.c_long, [C.c_void_p]),
+    "ocb_debug_jit_robot_header": (C.c_long, [C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_char_p, C.c_size_t]),
+    # several GPUs in one process (csrc/ocb_multi.cpp)
+    "ocb_multi_last_error": (C.c_char_p, []),
+    "ocb_multi_create": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_void_p)]),
+    "ocb_multi_destroy": (C.c_int, [C.c_void_p]),
+    "ocb_multi_device_count": (C.c_int, [C.c_void_p]),
+    "ocb_multi_uses_nccl": (C.c_int, [C.c_void_p]),
+    "ocb_multi_engine": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ocb_multi_enable_jit": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocb_multi_sdf_upload": (C.c_int, [C.c_void_p, C.POINTER(OcbSdf), c_int_p]),
+    "ocb_multi_computedistancefield_resident": (C.c_int, [C.c_void_p, C.POINTER(OcbPrim), C.c_int, c_int_p, c_double_p,
+                                                          C.c_double, c_double_p, c_int_p]),
+    "ocb_multi_sdf_remove": (C.c_int, [C.c_void_p, C.c_int]),
+    "ocb_multi_batch_create": (C.c_int, [C.c_void_p, C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_int, c_int_p, C.c_int,
+                                         c_double_p, c_double_p, c_uint_p, C.POINTER(C.c_void_p)]),
+    "ocb_multi_batch_dims": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p]),
+    "ocb_multi_batch_iterate": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
+    "ocb_multi_batch_get_traj": (C.c_int, [C.c_void_p, c_double_p]),
+    "ocb_multi_batch_best": (C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p]),
+    "ocb_multi_best_traj_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ocb_multi_batch_destroy": (C.c_int, [C.c_void_p]),
 }
 
 

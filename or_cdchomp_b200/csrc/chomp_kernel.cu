@@ -470,6 +470,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
    double cost_obs = 0.0, cost_smooth = 0.0;
    int red_parity = 0;
    int iters_done = 0; /* iterations completed (the reference's r->iter when iterate returns or throws) */
+   int limit_rounds = 0; /* most joint-limit projection steps any iteration of this call needed */
    for (int iter = 0; iter <= a.n_iter; iter++)
    {
       const bool final_pass = (iter == a.n_iter);
@@ -572,7 +573,10 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       const int any_violation = __syncthreads_or(violated);
 
       /* ---- joint-limit projection (chomp.c:608-655) ---- */
-      if (any_violation && !project_joint_limits(a, Ts, Gs, red, ired, Pp, m, n))
+      int rounds = 0;
+      const bool limits_ok = !any_violation || project_joint_limits(a, Ts, Gs, red, ired, Pp, m, n, rounds);
+      limit_rounds = max(limit_rounds, rounds);
+      if (!limits_ok)
       {
          status = OCB_ERR_JLIMIT; /* chomp.c:651-655 returns -1 before the smoothness cost */
          break;
@@ -620,6 +624,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       a.costs[(size_t) run * 3 + 2] = cost_smooth;
       a.status[run] = status;
       a.iters_done[run] = iters_done;
+      a.limit_rounds[run] = limit_rounds;
    }
 }
 

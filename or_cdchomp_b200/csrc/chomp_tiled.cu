@@ -580,7 +580,9 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
          }
    }
    const int any_violation = __syncthreads_or(violated);
-   const bool ok = !any_violation || project_joint_limits(a, Ts, Gs, red, ired, Pp, m, n);
+   int rounds = 0;
+   const bool ok = !any_violation || project_joint_limits(a, Ts, Gs, red, ired, Pp, m, n, rounds);
+   if (tid == 0 && rounds > a.limit_rounds[run]) a.limit_rounds[run] = rounds;
 
    /* the reference has already moved the trajectory when it gives up (chomp.c:651-655) */
    __syncthreads();

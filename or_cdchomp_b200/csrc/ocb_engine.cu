@@ -1466,11 +1466,13 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    TRY(batch_alloc(b, &a.costs, R * 3));
    TRY(batch_alloc(b, &a.status, R));
    TRY(batch_alloc(b, &a.iters_done, R));
+   TRY(batch_alloc(b, &a.limit_rounds, R));
    TRY(batch_alloc(b, &b->d_start, R * n));
    TRY(batch_alloc(b, &b->d_goal, R * n));
    cudaError_t err = cudaMemsetAsync(a.costs, 0, R * 3 * sizeof(double), e->stream);
    if (err == cudaSuccess) err = cudaMemsetAsync(a.status, 0, R * sizeof(int), e->stream);
    if (err == cudaSuccess) err = cudaMemsetAsync(a.iters_done, 0, R * sizeof(int), e->stream);
+   if (err == cudaSuccess) err = cudaMemsetAsync(a.limit_rounds, 0, R * sizeof(int), e->stream);
    if (err == cudaSuccess) err = cudaMemcpyAsync(b->d_start, q_start, R * n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
    if (err == cudaSuccess) err = cudaMemcpyAsync(b->d_goal, q_goal, R * n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
    if (err == cudaSuccess) err = ocb_launch_init_traj(a.traj, b->d_start, b->d_goal, n_runs, P, n, a.floating, e->stream);
@@ -1601,6 +1603,7 @@ extern "C" int ocb_batch_reset(ocb_batch *b, const double *q_start, const double
    CU(cudaMemsetAsync(a.costs, 0, R * 3 * sizeof(double), st));
    CU(cudaMemsetAsync(a.status, 0, R * sizeof(int), st));
    CU(cudaMemsetAsync(a.iters_done, 0, R * sizeof(int), st));
+   CU(cudaMemsetAsync(a.limit_rounds, 0, R * sizeof(int), st));
    if (a.use_momentum)
    {
       CU(cudaMemsetAsync(a.AG, 0, R * a.m * a.n * sizeof(double), st));
@@ -1713,6 +1716,7 @@ extern "C" int ocb_batch_iterate_from_async(ocb_batch *b, int first_iter, int n_
       CU(cudaMemsetAsync(a.costs, 0, (size_t) a.R * 3 * sizeof(double), b->e->stream));
       CU(cudaMemsetAsync(a.status, 0, (size_t) a.R * sizeof(int), b->e->stream));
       CU(cudaMemsetAsync(a.iters_done, 0, (size_t) a.R * sizeof(int), b->e->stream));
+      CU(cudaMemsetAsync(a.limit_rounds, 0, (size_t) a.R * sizeof(int), b->e->stream));
       CU(ocb_launch_chomp_tiled(&a, b->tile_smem, b->run_smem, 256, b->e->stream, &b->e->launches));
       return OCB_OK;
    }
@@ -1747,6 +1751,15 @@ extern "C" int ocb_batch_get_iterations(ocb_batch *b, int *iterations)
    if (!b || !iterations) return fail(OCB_ERR_ARG, "null argument");
    CU(cudaSetDevice(b->e->device));
    CU(cudaMemcpyAsync(iterations, b->args.iters_done, (size_t) b->args.R * sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_get_limit_rounds(ocb_batch *b, int *rounds)
+{
+   if (!b || !rounds) return fail(OCB_ERR_ARG, "null argument");
+   CU(cudaSetDevice(b->e->device));
+   CU(cudaMemcpyAsync(rounds, b->args.limit_rounds, (size_t) b->args.R * sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
    CU(cudaStreamSynchronize(b->e->stream));
    return OCB_OK;
 }

@@ -110,6 +110,7 @@ struct OcbChompArgs
    double *costs;         /* [R][3] */
    int *status;           /* [R] */
    int *iters_done;       /* [R] iterations completed by the last iterate call */
+   int *limit_rounds;     /* [R] most joint-limit projection steps (chomp.c:608-655) one iteration of the last call took */
    double *trace;         /* [R][n_iter][3] */
    double *grad_out;      /* [R][m][n] */
    double *G_obs;         /* [R][m][n] obstacle + self-collision gradient, unscaled (tiled path) */

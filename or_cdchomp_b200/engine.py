@@ -266,6 +266,12 @@ class Batch:
         check(self.lib, self.lib.ocb_batch_get_iterations(self.h, out.ctypes.data_as(c_int_p)), "ocb_batch_get_iterations")
         return out
 
+    def get_limit_rounds(self):
+        """most joint-limit projection steps one iteration of the last iterate call needed, per run"""
+        out = np.zeros(self.R, dtype=np.int32)
+        check(self.lib, self.lib.ocb_batch_get_limit_rounds(self.h, out.ctypes.data_as(c_int_p)), "ocb_batch_get_limit_rounds")
+        return out
+
     def get_traj(self, out=None):
         if out is None:
             out = np.empty((self.R, self.P, self.n))
@@ -295,6 +301,98 @@ class Batch:
         if self.h:
             self.lib.ocb_batch_destroy(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiEngine:
+    """G engines in one process, one host thread each, behind the C ABI (csrc/ocb_multi.cpp):
+    runs dealt round-robin, fields replicated, best-cost gather over NCCL / peer copies."""
+
+    def __init__(self, devices, lib=None):
+        self.lib = lib or capi.load_library()
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        self._check(self.lib.ocb_multi_create(len(devs), devs.ctypes.data_as(c_int_p), C.byref(h)), "ocb_multi_create")
+        self.h = h
+        self.G = len(devs)
+
+    def _check(self, code, what):
+        if code != capi.OCB_OK:
+            raise capi.OcbError("%s failed with code %d: %s" % (what, code, (self.lib.ocb_multi_last_error() or b"").decode()))
+
+    def uses_nccl(self):
+        return bool(self.lib.ocb_multi_uses_nccl(self.h))
+
+    def enable_jit(self, on=True):
+        self._check(self.lib.ocb_multi_enable_jit(self.h, int(bool(on))), "ocb_multi_enable_jit")
+
+    def upload_sdf(self, sdf_desc):
+        sid = C.c_int()
+        self._check(self.lib.ocb_multi_sdf_upload(self.h, C.byref(sdf_desc.struct), C.byref(sid)), "ocb_multi_sdf_upload")
+        return sid.value
+
+    def remove_sdf(self, sid):
+        self._check(self.lib.ocb_multi_sdf_remove(self.h, int(sid)), "ocb_multi_sdf_remove")
+
+    def create_batch(self, robot, params, sdf_ids, q_start, q_goal, seeds=None):
+        return MultiBatch(self, robot, params, sdf_ids, q_start, q_goal, seeds)
+
+    def close(self):
+        if self.h:
+            self.lib.ocb_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBatch:
+    def __init__(self, multi, robot, params, sdf_ids, q_start, q_goal, seeds=None):
+        self.multi, self.lib = multi, multi.lib
+        q_start, q_goal = as_f64(q_start), as_f64(q_goal)
+        self.R, self.n = q_start.shape
+        self.P = params.n_points
+        ids = np.ascontiguousarray(sdf_ids, dtype=np.int32)
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+            sp = self._seeds.ctypes.data_as(c_uint_p)
+        h = C.c_void_p()
+        multi._check(self.lib.ocb_multi_batch_create(multi.h, C.byref(robot.struct), C.byref(params), len(ids),
+                                                     ids.ctypes.data_as(c_int_p), self.R, dptr(q_start), dptr(q_goal),
+                                                     sp, C.byref(h)), "ocb_multi_batch_create")
+        self.h = h
+
+    def iterate(self, n_iter):
+        ct, co, cs = np.empty(self.R), np.empty(self.R), np.empty(self.R)
+        st = np.empty(self.R, dtype=np.int32)
+        self.multi._check(self.lib.ocb_multi_batch_iterate(self.h, int(n_iter), dptr(ct), dptr(co), dptr(cs),
+                                                           st.ctypes.data_as(c_int_p)), "ocb_multi_batch_iterate")
+        return np.stack([ct, co, cs], axis=1), st
+
+    def get_traj(self):
+        out = np.empty((self.R, self.P, self.n))
+        self.multi._check(self.lib.ocb_multi_batch_get_traj(self.h, dptr(out)), "ocb_multi_batch_get_traj")
+        return out
+
+    def best(self):
+        idx, cost = C.c_int(), C.c_double()
+        traj = np.zeros((self.P, self.n))
+        self.multi._check(self.lib.ocb_multi_batch_best(self.h, C.byref(idx), C.byref(cost), dptr(traj)), "ocb_multi_batch_best")
+        return idx.value, cost.value, traj
+
+    def close(self):
+        if self.h and self.multi.h:
+            self.lib.ocb_multi_batch_destroy(self.h)
+        self.h = None
 
     def __del__(self):
         try:

