@@ -41,6 +41,20 @@
 #define DIM(a, f) ((a).f)
 #endif
 
+/* development aid (run-time compilation with OCB_JIT_FLAGS=-DOCB_PHASE_CLOCKS): per-warp cycle totals of
+ * the phases of an iteration, written over the cost trace of the run (scripts/dev_phase_clocks.py) */
+#ifdef OCB_PHASE_CLOCKS
+#define PHASE_DECL long long ph_acc[16] = {0}; long long ph_t = clock64()
+#define PHASE(k) do { const long long ph_now = clock64(); ph_acc[k] += ph_now - ph_t; ph_t = ph_now; } while (0)
+#define PHASE_ARG , long long *ph_acc, long long &ph_t
+#define PHASE_PASS , ph_acc, ph_t
+#else
+#define PHASE_DECL
+#define PHASE(k)
+#define PHASE_ARG
+#define PHASE_PASS
+#endif
+
 namespace
 {
 
@@ -180,7 +194,7 @@ template <bool FLOAT, int PP>
 __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tables &tb,
                                                 const double *__restrict__ Ts,
                                                 double *__restrict__ ws, double *__restrict__ Gs,
-                                                int t, bool want_grad)
+                                                int t, bool want_grad PHASE_ARG)
 {
    const int Pp = PP ? PP : a.Ppad;
    const int nsa = DIM(a, nsa);
@@ -199,6 +213,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
    const JrHits hits = jr_pair_hits(ws, Pp, t);
    int pair_begin = 0;
 #endif
+   PHASE(2);
 
    for (int j = 0; j < DIM(a, nj); j++)
    {
@@ -382,6 +397,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
       }
    }
+   PHASE(3);
    if (want_grad)
    {
 #ifdef OCB_JIT_ROBOT
@@ -390,6 +406,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
       flush_wrenches<FLOAT, PP>(a, tb, Ts, ws, Gs, t);
 #endif
    }
+   PHASE(4);
    return cost;
 }
 
@@ -468,12 +485,15 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
    __syncthreads();
 
    double cost_obs = 0.0, cost_smooth = 0.0;
+   double csum_done = 0.0, ssum_done = 0.0; /* this thread's cost partials of the last completed iteration */
    int red_parity = 0;
    int iters_done = 0; /* iterations completed (the reference's r->iter when iterate returns or throws) */
    int limit_rounds = 0; /* most joint-limit projection steps any iteration of this call needed */
+   PHASE_DECL;
    for (int iter = 0; iter <= a.n_iter; iter++)
    {
       const bool final_pass = (iter == a.n_iter);
+      PHASE(15);
 
       /* ---- HMC momentum resample (mod.cpp:2755-2768) ---- */
       if (DIM(a, use_hmc) && !final_pass && a.iter_base + iter == hmc_next)
@@ -512,7 +532,9 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 #else
       for (int t = tid; t < P; t += NT) fk_waypoint<FLOAT, PP>(a, tb, Ts, ws, t);
 #endif
+      PHASE(0);
       __syncthreads();
+      PHASE(1);
 
       /* ---- obstacle + self-collision cost / gradient, then G = G/m + A T + B ---- */
       double csum = 0.0, ssum = 0.0;
@@ -520,7 +542,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       {
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
-         csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass);
+         csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass PHASE_PASS);
          if (!final_pass)
          {
             const double bi = __ldg(a.bcoef_i + t - 1), bf = __ldg(a.bcoef_f + t - 1);
@@ -544,11 +566,15 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          cost_smooth = ssum + trC;
          break;
       }
+      PHASE(5);
       __syncthreads(); /* every row of G is complete */
+      PHASE(6);
 
-      /* ---- AG = A^-1 G (banded solve, one thread per dof) ---- */
-      if (tid < n) band_solve(a, Gs + tid * Pp + 1, m);
+      /* ---- AG = A^-1 G (banded solve: a block-wide scan for the tridiagonal metric, else one thread per dof) ---- */
+      block_band_solve(a, Gs, Pp, m, n);
+      PHASE(7);
       __syncthreads();
+      PHASE(8);
 
       /* ---- momentum / plain update, T -= AG/lambda (chomp.c:525-548, 604-605); each thread
        * also checks the rows it has just written against the joint limits ---- */
@@ -570,7 +596,9 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
             }
          if (DIM(a, use_momentum)) leapfrog_first = 0;
       }
+      PHASE(9);
       const int any_violation = __syncthreads_or(violated);
+      PHASE(10);
 
       /* ---- joint-limit projection (chomp.c:608-655) ---- */
       int rounds = 0;
@@ -579,16 +607,38 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       if (!limits_ok)
       {
          status = OCB_ERR_JLIMIT; /* chomp.c:651-655 returns -1 before the smoothness cost */
+         /* the run keeps the costs of its last completed iteration */
+         if (iters_done > 0 && !a.trace_on)
+         {
+            block_sum2(csum_done, ssum_done, red, red_parity);
+            cost_obs = csum_done * inv_m;
+            cost_smooth = ssum_done + trC;
+         }
          break;
       }
 
       /* ---- smoothness cost of the updated trajectory (chomp.c:660-671) ---- */
+      PHASE(11);
       ssum = 0.0;
       for (int t = tid + 1; t <= m; t += NT) ssum += smooth_row(a, Ts, t, Pp, P, n);
-      block_sum2(csum, ssum, red, red_parity);
-      cost_obs = csum * inv_m;
-      cost_smooth = ssum + trC;
+      PHASE(12);
+      /* the costs of an iteration are read only by the trace and, when a later iteration leaves the
+       * joint limits, as the run's last costs: the block-wide sums (and their barrier) are deferred
+       * to those two places; each thread keeps the partial sums of the last completed iteration */
+      csum_done = csum;
+      ssum_done = ssum;
+      if (a.trace_on)
+      {
+         block_sum2(csum, ssum, red, red_parity);
+         cost_obs = csum * inv_m;
+         cost_smooth = ssum + trC;
+      }
+      PHASE(13);
+#ifndef OCB_PHASE_CLOCKS
       if (a.trace_on && tid == 0)
+#else
+      if (false)
+#endif
       {
          double *tr = a.trace + ((size_t) run * a.n_iter + iter) * 3;
          tr[0] = cost_obs + cost_smooth;
@@ -605,6 +655,10 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       }
    }
 
+#ifdef OCB_PHASE_CLOCKS
+   if (a.trace_on && (tid & 31) == 0)
+      for (int k = 0; k < 16; k++) a.trace[(size_t) run * a.n_iter * 3 + (tid >> 5) * 16 + k] = (double) ph_acc[k];
+#endif
    /* ---- write the run back ---- */
    __syncthreads();
    for (int e = tid; e < P * n; e += NT) traj[e] = Ts[(e % n) * Pp + (e / n)];

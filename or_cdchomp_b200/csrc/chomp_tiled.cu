@@ -558,7 +558,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
       }
    }
    __syncthreads();
-   if (tid < n) band_solve(a, Gs + tid * Pp + 1, m);
+   block_band_solve(a, Gs, Pp, m, n);
    __syncthreads();
 
    /* ---- momentum / plain update (chomp.c:525-548, 604-605) ---- */

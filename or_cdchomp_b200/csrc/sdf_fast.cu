@@ -263,8 +263,9 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
  * +-INF_I none. ---- */
 __global__ void __launch_bounds__(256)
 edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums, int *__restrict__ inter,
-                   uint32_t *__restrict__ stacks, int nx, int ny, int nz, int nwz)
+                   uint32_t *__restrict__ stacks, int nx, int ny, int nz, int nwz, const int *__restrict__ flag_nonbinary)
 {
+   if (*flag_nonbinary) return; /* not a 0 / HUGE_VAL grid: the general path will run instead */
    const int lane = threadIdx.x & 31;
    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (tile >= nx * nwz) return;
@@ -307,8 +308,9 @@ edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums
 /* ---- pass 3: lower envelope along x, final sqrt and sign; one warp per (y, z-word) tile ---- */
 __global__ void __launch_bounds__(256)
 edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, uint32_t *__restrict__ stacks,
-                  int nx, int ny, int nz, int nwz, double pitch2)
+                  int nx, int ny, int nz, int nwz, double pitch2, const int *__restrict__ flag_nonbinary)
 {
+   if (*flag_nonbinary) return;
    const int lane = threadIdx.x & 31;
    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (tile >= ny * nwz) return;
@@ -394,20 +396,23 @@ extern "C" cudaError_t ocb_launch_bin_sdf_fast(const double *d_obs, double *d_sd
    int *inter = (int *) (sp + off);
    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
    if (e != cudaSuccess) return e;
+   /* all three passes are enqueued back to back; whether the grid really was binary is read back
+    * AFTER them (a host round trip between the passes would leave the GPU idle for its duration):
+    * on a non-binary grid the two transform passes return at once and the caller takes the general path */
    pack_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_obs, mask, sums, rows, ny, nz, nwz, flag);
-   if (launches) (*launches)++;
+   const double pitch = lengths[0] / sizes[0];
+   uint32_t *stacks = (uint32_t *) (((uintptr_t) (inter + (size_t) rows * nz) + 255) & ~(uintptr_t) 255);
+   edt_zy_kernel<<<dim3((nx * nwz + 7) / 8, 2), 256, 0, st>>>(mask, sums, inter, stacks, nx, ny, nz, nwz, flag);
+   edt_x_kernel<<<dim3((ny * nwz + 7) / 8, 2), 256, 0, st>>>(inter, d_sdf, stacks, nx, ny, nz, nwz, pitch * pitch, flag);
+   if (launches) (*launches) += 3;
+   e = cudaGetLastError();
+   if (e != cudaSuccess) return e;
    int h = 0;
    e = cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
    if (e != cudaSuccess) return e;
    e = cudaStreamSynchronize(st);
    if (e != cudaSuccess) return e;
    if (h) return cudaSuccess; /* not a 0 / HUGE_VAL grid */
-
-   const double pitch = lengths[0] / sizes[0];
-   uint32_t *stacks = (uint32_t *) (((uintptr_t) (inter + (size_t) rows * nz) + 255) & ~(uintptr_t) 255);
-   edt_zy_kernel<<<dim3((nx * nwz + 7) / 8, 2), 256, 0, st>>>(mask, sums, inter, stacks, nx, ny, nz, nwz);
-   edt_x_kernel<<<dim3((ny * nwz + 7) / 8, 2), 256, 0, st>>>(inter, d_sdf, stacks, nx, ny, nz, nwz, pitch * pitch);
-   if (launches) (*launches) += 2;
    e = cudaGetLastError();
    if (e == cudaSuccess) *used_fast = 1;
    return e;

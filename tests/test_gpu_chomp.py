@@ -213,7 +213,8 @@ def test_joint_limit_projection_and_failure(engine, oracle, flavour, wam7, table
     took (ocb_batch_get_limit_rounds); status and trajectory must match the reference on every run
     that stayed at or below 25, and those are the large majority."""
     params = capi.default_params(n_points=100, lambda_=100.0, obs_factor=500.0)
-    starts, goals = models.random_endpoints(wam7, 64, seed0=20260217, shrink=0.0)
+    R = 256
+    starts, goals = models.random_endpoints(wam7, R, seed0=20260217, shrink=0.0)
     sid = engine.upload_sdf(table["desc"])
     b = engine.create_batch(wam7, params, [sid], starts, goals)
     costs, status = b.iterate(40)
@@ -223,7 +224,7 @@ def test_joint_limit_projection_and_failure(engine, oracle, flavour, wam7, table
     assert ((status != 0) == (rounds == 1000)).all()          # a run fails exactly when step 1000 is reached
     n_fragile = n_checked = n_projected_checked = 0
     lo, hi = wam7.limit_lower, wam7.limit_upper
-    for r in range(64):
+    for r in range(R):
         run = oracle.Run(wam7, params, [table["desc"]], starts[r], goals[r], flavour=flavour)
         ret, c, _, _ = run.iterate(40)
         rtraj = run.traj()
@@ -239,7 +240,7 @@ def test_joint_limit_projection_and_failure(engine, oracle, flavour, wam7, table
         n_projected_checked += rounds[r] > 0
         assert np.max(np.abs(traj[r] - rtraj)) <= TRAJ_ATOL, r
         assert (traj[r] >= lo - 1e-9).all() and (traj[r] <= hi + 1e-9).all()
-    assert n_checked >= 50 and n_projected_checked >= 10 and n_fragile <= 10
+    assert n_checked >= 0.9 * R and n_projected_checked >= 10 and n_fragile <= 0.06 * R
     b.close()
     engine.remove_sdf(sid)
 
