@@ -299,7 +299,7 @@ __device__ __forceinline__ JrHits jr_pair_hits(const double *__restrict__ ws, co
    return h;
 }
 
-/* bits [begin, begin + count) of the hit set, count <= 32, begin a run-time (warp-uniform) value */
+/* bits [begin, begin + count) of the hit set, count <= 32, begin a run-time value */
 __device__ __forceinline__ unsigned jr_hit_bits(const JrHits &h, const int begin, const int count)
 {
    const int wi = begin >> 5, sh = begin & 31;
@@ -312,6 +312,257 @@ __device__ __forceinline__ unsigned jr_hit_bits(const JrHits &h, const int begin
    }
    const unsigned v = __funnelshift_r(lo, hi, sh);
    return (count >= 32) ? v : (v & ((1u << count) - 1u));
+}
+
+/* the same with compile-time bounds: a couple of shifts */
+template <int BEGIN, int COUNT>
+__device__ __forceinline__ unsigned jr_hit_bits_static(const JrHits &h)
+{
+   if constexpr (COUNT <= 0) return 0u;
+   else
+   {
+      constexpr int wi = BEGIN >> 5, sh = BEGIN & 31;
+      unsigned v = h.w[wi] >> sh;
+      if constexpr (sh + COUNT > 32) v |= h.w[wi + 1] << (32 - sh);
+      if constexpr (COUNT < 32) v &= (1u << COUNT) - 1u;
+      return v;
+   }
+}
+
+/* Spheres that may lie inside some field: bit S is set unless sphere S is outside every grid beyond
+ * any rounding (the first, conservative half of sdf_sample's range test, for all spheres at once in
+ * straight-line code).  Only those spheres are probed. */
+template <int NSDF>
+__device__ __forceinline__ unsigned jr_grid_candidates(const OcbSdfDev *__restrict__ sdfs, const double *__restrict__ ws,
+                                                       const int Pp, const int t)
+{
+   unsigned cand = 0;
+   jr_for<0, JR_NSA>([&](auto sc)
+   {
+      constexpr int S = decltype(sc)::v;
+      const double *ps = ws + 3 * S * Pp + t;
+      const double px = ps[0], py = ps[Pp], pz = ps[2 * Pp];
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < NSDF; k++)
+      {
+         const OcbSdfDev &G = sdfs[k];
+         bool in = true;
+#pragma unroll
+         for (int r = 0; r < 3; r++)
+         {
+            const double g = G.Rgw[3 * r] * px + G.Rgw[3 * r + 1] * py + G.Rgw[3 * r + 2] * pz + G.tgw[r];
+            in = in && (g >= -1e-290) && !(g * G.scale[r] > G.edge_hi[r]);
+         }
+         any = any || in;
+      }
+      if (any) cand |= 1u << S;
+   });
+   return cand;
+}
+
+/* cost (and, when want_grad, the configuration-space gradient row) of moving waypoint t: waypoint_cost
+ * of chomp_kernel.cu (sphere_cost, mod.cpp:1134-1327) for the compiled robot.
+ *   1. all self-collision range tests in one straight-line pass -> one bit per pair in range;
+ *   2. a straight-line pass marks the spheres that may lie inside a field;
+ *   3. only spheres with a partner in range or a field around them are visited, each lane walking
+ *      its OWN list (a lane never idles through a sphere only its neighbours need); a sphere with
+ *      neither has exactly zero cost and force (every term carries a factor that vanishes).
+ * Forces are gathered as wrenches per joint frame, in registers while consecutive spheres share a frame. */
+template <bool FLOAT>
+__device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const OcbSdfDev *__restrict__ sdfs,
+                                                   const double *__restrict__ Ts, double *__restrict__ ws,
+                                                   double *__restrict__ Gs, const int Pp, const int t,
+                                                   const bool want_grad PHASE_ARG)
+{
+   double *Wg = ws + (3 * JR_NSA + 12 * JR_NSLOTS) * Pp + t;
+   const double inv2dt = 1.0 / (2.0 * a.dt);
+   const double invdt2 = 1.0 / (a.dt * a.dt);
+   const double es = a.eps_self, inv_es = 1.0 / es, half_inv_es = 0.5 / es;
+   double cost = 0.0;
+
+   if (want_grad)
+   {
+#pragma unroll
+      for (int k = 0; k < 6 * JR_NG; k++) Wg[k * Pp] = 0.0;
+   }
+   const JrHits hits = jr_pair_hits(ws, Pp, t);
+   const unsigned cand = jr_grid_candidates<OCB_JIT_nsdf>(sdfs, ws, Pp, t);
+   /* spheres that take part in a pair in range, as the pair's first member (partners are reached from it) */
+   unsigned need = cand;
+   jr_for<0, JR_NSA>([&](auto sc)
+   {
+      constexpr int S = decltype(sc)::v;
+      const unsigned b = jr_hit_bits_static<jr_pair_begin[S], jr_pair_begin[S + 1] - jr_pair_begin[S]>(hits) |
+                         jr_hit_bits_static<JR_NPA + S * JR_NSI, JR_NSI>(hits);
+      if (b) need |= 1u << S;
+   });
+   PHASE(2);
+
+   int gcur = -1;
+   double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
+   auto flush_group = [&]()
+   {
+      if (gcur >= 0 && want_grad)
+      {
+         double *Wo = Wg + 6 * gcur * Pp;
+         Wo[0] += F[0]; Wo[Pp] += F[1]; Wo[2 * Pp] += F[2];
+         Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
+      }
+      F[0] = F[1] = F[2] = M[0] = M[1] = M[2] = 0.0;
+   };
+   while (need)
+   {
+      const int s = __ffs(need) - 1;
+      need &= need - 1;
+      const double *ps = ws + 3 * s * Pp + t;
+      const double p[3] = {ps[0], ps[Pp], ps[2 * Pp]};
+      const double radius = jr_radius[s];
+
+      /* --- obstacle term, first step: which field, how far (mod.cpp:1169-1198) --- */
+      double d_obs = 0.0, bg[3] = {0.0, 0.0, 0.0};
+      int best = -1;
+      if ((cand >> s) & 1u) best = obstacle_probe(a, sdfs, p, radius, OCB_JIT_nsdf, d_obs, bg);
+      const bool obs = (best >= 0) && (d_obs < a.eps);
+      const int pb = jr_pair_begin[s];
+      unsigned hit_a = jr_hit_bits(hits, pb, jr_pair_begin[s + 1] - pb);
+      unsigned hit_i = (JR_NSI > 0) ? jr_hit_bits(hits, JR_NPA + s * JR_NSI, JR_NSI) : 0u;
+      if (!obs && !(hit_a | hit_i)) continue;
+      const int g = jr_group[s];
+      if (g != gcur)
+      {
+         flush_group();
+         gcur = g;
+      }
+
+      double vel[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) vel[k] = (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
+      const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
+      const double rv = rsqrt(vn2);
+      const double vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
+      const double iv2 = rv * rv; /* 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
+      const bool moving = vn > 0.000001;
+      double cost_s = 0.0;
+      double f[3] = {0.0, 0.0, 0.0};
+
+      /* --- obstacle term, second step (mod.cpp:1200-1249) --- */
+      if (obs)
+      {
+         double acc[3] = {0.0, 0.0, 0.0};
+         if (want_grad)
+         {
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[k] = (p[k] * -2.0 + ps[k * Pp - 1] + ps[k * Pp + 1]) * invdt2;
+         }
+         obstacle_apply(a, sdfs[best], d_obs, bg, vel, acc, vn, iv2, moving, want_grad, cost_s, f);
+      }
+
+      /* --- self collision, each unordered pair once (1251-1317); see waypoint_cost --- */
+      const double ws_self = vn * a.obs_factor_self;
+      auto in_range = [&](const double q[3], const double *po, const int o)
+      {
+         const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+         const double d2 = dx * dx + dy * dy + dz * dz;
+         const double inv = rsqrt(d2);
+         const double dist = d2 * inv;
+         const double dd = dist - (radius + jr_radius[o]);
+         const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
+         cost_s += ws_self * cshape;
+         double w2 = 0.0, v2[3] = {0.0, 0.0, 0.0}, r2 = 0.0;
+         bool moving2 = false;
+         if (po)
+         {
+#pragma unroll
+            for (int r = 0; r < 3; r++) v2[r] = (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
+            const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+            r2 = rsqrt(v2n2);
+            const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
+            moving2 = v2n > 0.000001;
+            w2 = v2n * a.obs_factor_self;
+            cost_s += w2 * cshape; /* the other sphere's own cost_sphere term */
+         }
+         if (!want_grad) return;
+         const double sc = (dd < 0.0) ? -1.0 : ((dd < es) ? (dd * inv_es - 1.0) : 1.0);
+         const double gh[3] = {dx * inv, dy * inv, dz * inv};
+         double x[3];
+         const double wa = sc * ws_self;
+#pragma unroll
+         for (int r = 0; r < 3; r++) x[r] = gh[r] * wa;
+         if (moving)
+         {
+            const double pj = (x[0] * vel[0] + x[1] * vel[1] + x[2] * vel[2]) * iv2;
+#pragma unroll
+            for (int r = 0; r < 3; r++) x[r] = fma(-pj, vel[r], x[r]);
+         }
+         if (po)
+         {
+            double y[3];
+            const double wb = -sc * w2;
+#pragma unroll
+            for (int r = 0; r < 3; r++) y[r] = gh[r] * wb;
+            if (moving2)
+            {
+               const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * (r2 * r2);
+#pragma unroll
+               for (int r = 0; r < 3; r++) y[r] = fma(-pj, v2[r], y[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) x[r] -= y[r];
+            const int go = jr_group[o];
+            if (go == gcur)
+            {
+               /* partner on the same joint frame: its reaction joins the wrench held in registers */
+               F[0] -= x[0]; F[1] -= x[1]; F[2] -= x[2];
+               M[0] -= q[1] * x[2] - q[2] * x[1];
+               M[1] -= q[2] * x[0] - q[0] * x[2];
+               M[2] -= q[0] * x[1] - q[1] * x[0];
+            }
+            else
+            {
+               double *Wo = Wg + 6 * go * Pp;
+               Wo[0] -= x[0];
+               Wo[Pp] -= x[1];
+               Wo[2 * Pp] -= x[2];
+               Wo[3 * Pp] -= q[1] * x[2] - q[2] * x[1];
+               Wo[4 * Pp] -= q[2] * x[0] - q[0] * x[2];
+               Wo[5 * Pp] -= q[0] * x[1] - q[1] * x[0];
+            }
+         }
+#pragma unroll
+         for (int r = 0; r < 3; r++) f[r] += x[r];
+      };
+      /* active partners in ascending order, then the inactive ones (frozen in the world, mod.cpp:2332-2345) */
+      while (hit_a)
+      {
+         const int k = __ffs(hit_a) - 1;
+         hit_a &= hit_a - 1;
+         const int o = jr_pair_o[pb + k];
+         const double *po = ws + 3 * o * Pp + t;
+         const double q[3] = {po[0], po[Pp], po[2 * Pp]};
+         in_range(q, po, o);
+      }
+      while (hit_i)
+      {
+         const int i = __ffs(hit_i) - 1;
+         hit_i &= hit_i - 1;
+         const double q[3] = {jr_inactive_pos[i][0], jr_inactive_pos[i][1], jr_inactive_pos[i][2]};
+         in_range(q, nullptr, JR_NSA + i);
+      }
+      cost += cost_s;
+      if (want_grad)
+      {
+         F[0] += f[0]; F[1] += f[1]; F[2] += f[2];
+         M[0] += p[1] * f[2] - p[2] * f[1];
+         M[1] += p[2] * f[0] - p[0] * f[2];
+         M[2] += p[0] * f[1] - p[1] * f[0];
+      }
+   }
+   flush_group();
+   PHASE(3);
+   if (want_grad) jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t);
+   PHASE(4);
+   return cost;
 }
 
 } /* namespace */

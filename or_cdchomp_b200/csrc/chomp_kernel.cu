@@ -27,9 +27,6 @@
  *   - each SDF sample reads its 4 cells once and yields value and gradient.
  */
 #include "chomp_device.cuh"
-#ifdef OCB_JIT_ROBOT
-#include "chomp_jit_robot.cuh" /* this batch's robot as straight-line code (run-time compilation only) */
-#endif
 
 /* Sizes of the compiled robot and the mode flags: kernel arguments in the library's own
  * instantiations, literal constants when the kernel is compiled at run time for one batch
@@ -55,6 +52,10 @@
 #define PHASE_PASS
 #endif
 
+#ifdef OCB_JIT_ROBOT
+#include "chomp_jit_robot.cuh" /* this batch's robot as straight-line code (run-time compilation only) */
+#endif
+
 namespace
 {
 
@@ -62,7 +63,7 @@ namespace
 /* Shared-memory carve-up, computed identically on host and device. */
 struct SmemLayout
 {
-   int T, G, AG, red, ws, cut2, radius; /* offsets in doubles */
+   int T, G, AG, red, ws, cut2, radius, metric; /* offsets in doubles */
    int sdf, sph, desc, mt, ired;        /* offsets in bytes   */
    int bytes;
 };
@@ -76,12 +77,16 @@ __host__ __device__ inline SmemLayout smem_layout(const OcbChompArgs &a, const i
    l.AG = d; d += DIM(a, use_momentum) ? n * Pp : 0;
    l.red = d; d += 36;
    l.ws = d; d += (int) a.ws_stride;
-   l.cut2 = d; d += DIM(a, nsa) * (DIM(a, NAp) + DIM(a, nsi));
-   l.radius = d; d += DIM(a, nsa) + DIM(a, nsi);
+   /* a kernel that has the robot as code (robot_smem) needs none of its tables here and keeps the
+    * tridiagonal factor (L, 1/d: the solve's operands in every iteration) in their place */
+   const bool robot = a.robot_smem != 0;
+   l.cut2 = d; d += robot ? 0 : DIM(a, nsa) * (DIM(a, NAp) + DIM(a, nsi));
+   l.radius = d; d += robot ? 0 : DIM(a, nsa) + DIM(a, nsi);
+   l.metric = d; d += (robot && a.bw == 1) ? 2 * (Pp - 2) : 0;
    int b = d * 8;
    l.sdf = b; b += DIM(a, nsdf) * (int) sizeof(OcbSdfDev);
-   l.sph = b; b += DIM(a, nsa) * (int) sizeof(OcbSphereDev);
-   l.desc = b; b += DIM(a, n_desc) * 4;
+   l.sph = b; b += robot ? 0 : DIM(a, nsa) * (int) sizeof(OcbSphereDev);
+   l.desc = b; b += robot ? 0 : DIM(a, n_desc) * 4;
    l.mt = b; b += DIM(a, use_hmc) ? (626 + 626 + 16) * 4 : 0; /* state, saved copy (serial fallback), scratch */
    l.ired = b; b += 40 * 4;
    l.bytes = b;
@@ -208,11 +213,6 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
    if (want_grad)
       for (int k = 0; k < 6 * DIM(a, ng); k++) Wg[k * Pp] = 0.0;
 
-#ifdef OCB_JIT_ROBOT
-   /* every self-collision range test of this waypoint in one straight-line pass */
-   const JrHits hits = jr_pair_hits(ws, Pp, t);
-   int pair_begin = 0;
-#endif
    PHASE(2);
 
    for (int j = 0; j < DIM(a, nj); j++)
@@ -230,16 +230,6 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          double d_obs, bg[3];
          const int best = obstacle_probe(a, tb.sdfs, p, radius, DIM(a, nsdf), d_obs, bg);
          const bool obs = (best >= 0) && (d_obs < a.eps);
-#ifdef OCB_JIT_ROBOT
-         /* this sphere's partners in range: bits over its static partner list, then the inactive spheres */
-         const int pair_end = jr_pair_begin[s + 1];
-         unsigned hit_a = jr_hit_bits(hits, pair_begin, pair_end - pair_begin);
-         unsigned hit_i = (JR_NSI > 0) ? jr_hit_bits(hits, JR_NPA + s * JR_NSI, JR_NSI) : 0u;
-         const int pb = pair_begin;
-         pair_begin = pair_end;
-         /* neither an obstacle within epsilon nor a sphere within range: cost and force are exactly zero */
-         if (!obs && !(hit_a | hit_i)) continue;
-#endif
          double vel[3];
 #pragma unroll
          for (int k = 0; k < 3; k++) vel[k] = (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
@@ -329,25 +319,6 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
 #pragma unroll
             for (int r = 0; r < 3; r++) f[r] += x[r];
          };
-#ifdef OCB_JIT_ROBOT
-         /* active partners in ascending order, then the inactive ones (frozen in the world, mod.cpp:2332-2345) */
-         while (hit_a)
-         {
-            const int k = __ffs(hit_a) - 1;
-            hit_a &= hit_a - 1;
-            const int o = jr_pair_o[pb + k];
-            const double *po = ws + 3 * o * Pp + t;
-            const double q[3] = {po[0], po[Pp], po[2 * Pp]};
-            in_range(q, po, o);
-         }
-         while (hit_i)
-         {
-            const int i = __ffs(hit_i) - 1;
-            hit_i &= hit_i - 1;
-            const double q[3] = {jr_inactive_pos[i][0], jr_inactive_pos[i][1], jr_inactive_pos[i][2]};
-            in_range(q, nullptr, nsa + i);
-         }
-#else
          const double *crow = tb.cut2 + s * row;
          /* active partners: range tests four at a time (independent chains); the padded
           * tail of the cut2 row is -1 and never passes */
@@ -380,7 +351,6 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
             const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
             if (dx * dx + dy * dy + dz * dz <= crow[DIM(a, NAp) + i]) in_range(q, nullptr, nsa + i);
          }
-#endif
          cost += cost_s;
          if (want_grad)
          {
@@ -398,14 +368,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
       }
    }
    PHASE(3);
-   if (want_grad)
-   {
-#ifdef OCB_JIT_ROBOT
-      jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t);
-#else
-      flush_wrenches<FLOAT, PP>(a, tb, Ts, ws, Gs, t);
-#endif
-   }
+   if (want_grad) flush_wrenches<FLOAT, PP>(a, tb, Ts, ws, Gs, t);
    PHASE(4);
    return cost;
 }
@@ -433,6 +396,17 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
    double *ws = sd + lay.ws;
    Tables tb;
    tb.sdfs = sdfs;
+   const double *Ls = a.Lband, *dinv = a.dinv; /* the solve's factor: global, or staged below */
+#ifdef OCB_JIT_ROBOT
+   tb.sph = nullptr; tb.desc = nullptr; tb.cut2 = nullptr; tb.radius = nullptr;
+   if (a.bw == 1)
+   {
+      double *ml = sd + lay.metric, *md = ml + m;
+      for (int e = tid; e < m; e += NT) { ml[e] = __ldg(a.Lband + e); md[e] = __ldg(a.dinv + e); }
+      Ls = ml;
+      dinv = md;
+   }
+#else
    {
       double *c2 = sd + lay.cut2, *rad = sd + lay.radius;
       OcbSphereDev *sph = reinterpret_cast<OcbSphereDev *>(smem_raw + lay.sph);
@@ -448,6 +422,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       for (int e = tid; e < DIM(a, n_desc); e += NT) dsc[e] = __ldg(a.desc + e);
       tb.sph = sph; tb.desc = dsc; tb.cut2 = c2; tb.radius = rad;
    }
+#endif
 
    /* ---- stage per-run state and shared constants ---- */
    double *traj = a.traj + (size_t) run * P * n;
@@ -542,7 +517,11 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       {
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
+#ifdef OCB_JIT_ROBOT
+         csum += jr_waypoint_cost<FLOAT>(a, tb.sdfs, Ts, ws, Gs, Pp, t, !final_pass PHASE_PASS);
+#else
          csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass PHASE_PASS);
+#endif
          if (!final_pass)
          {
             const double bi = __ldg(a.bcoef_i + t - 1), bf = __ldg(a.bcoef_f + t - 1);
@@ -570,30 +549,36 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       __syncthreads(); /* every row of G is complete */
       PHASE(6);
 
-      /* ---- AG = A^-1 G (banded solve: a block-wide scan for the tridiagonal metric, else one thread per dof) ---- */
-      block_band_solve(a, Gs, Pp, m, n);
-      PHASE(7);
-      __syncthreads();
-      PHASE(8);
-
-      /* ---- momentum / plain update, T -= AG/lambda (chomp.c:525-548, 604-605); each thread
-       * also checks the rows it has just written against the joint limits ---- */
+      /* ---- AG = A^-1 G, then the momentum / plain update T -= AG/lambda (chomp.c:525-548, 604-605) with
+       * the joint-limit check of every entry written.  Tridiagonal metric: a block-wide scan solves all
+       * dofs at once and the lane that owns an entry updates it on the spot -- one barrier for solve,
+       * update and the any-violation vote.  Wider metrics: one thread per dof, then thread per waypoint. ---- */
       int violated = 0;
       {
          const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
-         for (int t = tid + 1; t <= m; t += NT)
-            for (int j = 0; j < n; j++)
+         auto update = [&](const int j, const int t, double step)
+         {
+            if (DIM(a, use_momentum))
             {
-               double step = Gs[j * Pp + t];
-               if (DIM(a, use_momentum))
-               {
-                  step = fma(coef, step, AGs[j * Pp + t]);
-                  AGs[j * Pp + t] = step;
-               }
-               const double q = fma(-inv_lambda, step, Ts[j * Pp + t]);
-               Ts[j * Pp + t] = q;
-               violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
+               step = fma(coef, step, AGs[j * Pp + t]);
+               AGs[j * Pp + t] = step;
             }
+            const double q = fma(-inv_lambda, step, Ts[j * Pp + t]);
+            Ts[j * Pp + t] = q;
+            violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
+         };
+         const int lpd = band_scan_lanes(a, n);
+         if (lpd >= 2)
+            band_solve_scan(a, Gs, Pp, m, n, lpd, [&](const int j, const int i, const double ag) { update(j, i + 1, ag); }, Ls, dinv);
+         else
+         {
+            if (tid < n) band_solve(a, Gs + tid * Pp + 1, m);
+            PHASE(7);
+            __syncthreads();
+            PHASE(8);
+            for (int t = tid + 1; t <= m; t += NT)
+               for (int j = 0; j < n; j++) update(j, t, Gs[j * Pp + t]);
+         }
          if (DIM(a, use_momentum)) leapfrog_first = 0;
       }
       PHASE(9);

@@ -1306,6 +1306,12 @@ std::string jit_robot_header(const CompiledRobot &C, double eps_self)
    darr2("jr_inactive_pos", C.inactive_pos, 3);
    iarr("jr_pair_begin", pair_begin); iarr("jr_pair_o", pair_o); iarr("jr_pair_kind", kind); darr("jr_pair_cut2", cut2);
    iarr("jr_own_tests", own_tests);
+   {
+      std::vector<int> grp;
+      for (int s = 0; s < nsa; s++) grp.push_back(C.spheres[s].group);
+      iarr("jr_group", grp);
+      darr("jr_radius", C.radius);
+   }
    h += "__device__ constexpr unsigned jr_hits_always[" + std::to_string(words) + "] = {";
    for (int k = 0; k < words; k++) h += (k ? ", " : "") + std::to_string(always[k]) + "u";
    h += "};\n";
@@ -1536,10 +1542,18 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       /* the robot as straight-line code; OCB_JIT_ROBOT=0 in the environment keeps the table-driven kernel */
       const char *env = getenv("OCB_JIT_ROBOT");
       const std::string robot_hdr = (env && env[0] == '0') ? std::string() : jit_robot_header(C, params->epsilon_self);
+      const size_t smem_generic = b->smem;
+      if (!robot_hdr.empty())
+      {
+         a.robot_smem = 1; /* that kernel lays shared memory out differently (smem_layout) */
+         b->smem = ocb_chomp_smem_bytes(&a);
+      }
       if (ocb_jit_chomp_kernel(&a, e->device, b->threads, min_blocks, b->smem, robot_hdr.c_str(), &b->jit_kernel, why,
                                sizeof(why)) != 0)
       {
          b->jit_kernel = nullptr; /* the library's own kernel runs instead */
+         a.robot_smem = 0;
+         b->smem = smem_generic;
          fail(OCB_ERR_CUDA, "run-time specialisation unavailable: %s", why);
       }
    }

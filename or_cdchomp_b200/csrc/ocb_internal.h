@@ -116,6 +116,9 @@ struct OcbChompArgs
    double *G_obs;         /* [R][m][n] obstacle + self-collision gradient, unscaled (tiled path) */
    double *tile_cost;     /* [R][n_tiles] cost partials (tiled path) */
    size_t ws_stride;      /* doubles of per-run workspace in shared memory (persistent kernel) */
+   int robot_smem;        /* 1: kernel compiled with the robot as code (OCB_JIT_ROBOT) -- no pair / subtree tables in
+                             shared memory, the tridiagonal factor staged there instead */
+   int pad1;
 };
 
 #if !defined(__CUDACC_RTC__) && defined(__cplusplus)
