@@ -23,6 +23,10 @@
 
 #include "ocb_jit_robot.h" /* generated: JR_* sizes and jr_* tables */
 
+#ifndef JR_PAIRS_AT_ONCE
+#define JR_PAIRS_AT_ONCE 2 /* sphere pairs in range worked off per step of the pair loop (1 or 2) */
+#endif
+
 namespace
 {
 
@@ -337,9 +341,10 @@ __device__ __forceinline__ unsigned jr_grid_candidates(const OcbSdfDev *__restri
                                                        const int Pp, const int t)
 {
    unsigned cand = 0;
-   jr_for<0, JR_NSA>([&](auto sc)
+   /* three spheres at a time: independent work for the scheduler without the register pressure of all fifteen */
+#pragma unroll 3
+   for (int S = 0; S < JR_NSA; S++)
    {
-      constexpr int S = decltype(sc)::v;
       const double *ps = ws + 3 * S * Pp + t;
       const double px = ps[0], py = ps[Pp], pz = ps[2 * Pp];
       bool any = false;
@@ -357,210 +362,204 @@ __device__ __forceinline__ unsigned jr_grid_candidates(const OcbSdfDev *__restri
          any = any || in;
       }
       if (any) cand |= 1u << S;
-   });
+   }
    return cand;
 }
 
-/* cost (and, when want_grad, the configuration-space gradient row) of moving waypoint t: waypoint_cost
- * of chomp_kernel.cu (sphere_cost, mod.cpp:1134-1327) for the compiled robot.
+/* finite-difference velocity of a sphere column (mod.cpp:1099-1113) with its norm, 1/|v|^2 and the
+ * "moving" predicate of sphere_cost (1226, 1302) */
+struct JrVel
+{
+   double v[3], vn, iv2;
+   bool moving;
+};
+
+__device__ __forceinline__ JrVel jr_velocity(const double *__restrict__ ps, const int Pp, const double inv2dt)
+{
+   JrVel k;
+#pragma unroll
+   for (int r = 0; r < 3; r++) k.v[r] = (ps[r * Pp + 1] - ps[r * Pp - 1]) * inv2dt;
+   const double vn2 = k.v[0] * k.v[0] + k.v[1] * k.v[1] + k.v[2] * k.v[2];
+   const double rv = rsqrt(vn2);
+   k.vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
+   k.iv2 = rv * rv; /* unguarded (inf at rest), as mod.cpp:1239 */
+   k.moving = k.vn > 0.000001;
+   return k;
+}
+
+/* cost (and, when WANT_GRAD, the configuration-space gradient row) of moving waypoint t: waypoint_cost
+ * of chomp_kernel.cu (sphere_cost, mod.cpp:1134-1327) for the compiled robot, organised for
+ * instruction-level parallelism -- a warp of this kernel is one long dependency chain, and three
+ * warps per scheduler do not hide it:
  *   1. all self-collision range tests in one straight-line pass -> one bit per pair in range;
- *   2. a straight-line pass marks the spheres that may lie inside a field;
- *   3. only spheres with a partner in range or a field around them are visited, each lane walking
- *      its OWN list (a lane never idles through a sphere only its neighbours need); a sphere with
- *      neither has exactly zero cost and force (every term carries a factor that vanishes).
- * Forces are gathered as wrenches per joint frame, in registers while consecutive spheres share a frame. */
-template <bool FLOAT>
+ *   2. a straight-line pass marks the spheres that may lie inside a field; only those are probed, and
+ *      only a sphere with a field value below epsilon has an obstacle term at all;
+ *   3. the pairs in range are then worked off PAIR by pair, two at a time, each a branch-free block
+ *      that needs nothing from the previous one: both spheres' velocities, both directed terms
+ *      (mod.cpp:1281-1317), the force on one sphere and its reaction on the other added straight to
+ *      the wrenches of their joint frames (F, M about the world origin, in shared memory).
+ * Sums therefore run in pair order instead of sphere order: results agree with waypoint_cost to rounding. */
+template <bool FLOAT, bool WANT_GRAD>
 __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const OcbSdfDev *__restrict__ sdfs,
                                                    const double *__restrict__ Ts, double *__restrict__ ws,
-                                                   double *__restrict__ Gs, const int Pp, const int t,
-                                                   const bool want_grad PHASE_ARG)
+                                                   double *__restrict__ Gs, const int Pp, const int t PHASE_ARG)
 {
    double *Wg = ws + (3 * JR_NSA + 12 * JR_NSLOTS) * Pp + t;
    const double inv2dt = 1.0 / (2.0 * a.dt);
    const double invdt2 = 1.0 / (a.dt * a.dt);
    const double es = a.eps_self, inv_es = 1.0 / es, half_inv_es = 0.5 / es;
+   const double ofs = a.obs_factor_self;
    double cost = 0.0;
 
-   if (want_grad)
+   if (WANT_GRAD)
    {
 #pragma unroll
       for (int k = 0; k < 6 * JR_NG; k++) Wg[k * Pp] = 0.0;
    }
    const JrHits hits = jr_pair_hits(ws, Pp, t);
-   const unsigned cand = jr_grid_candidates<OCB_JIT_nsdf>(sdfs, ws, Pp, t);
-   /* spheres that take part in a pair in range, as the pair's first member (partners are reached from it) */
-   unsigned need = cand;
-   jr_for<0, JR_NSA>([&](auto sc)
-   {
-      constexpr int S = decltype(sc)::v;
-      const unsigned b = jr_hit_bits_static<jr_pair_begin[S], jr_pair_begin[S + 1] - jr_pair_begin[S]>(hits) |
-                         jr_hit_bits_static<JR_NPA + S * JR_NSI, JR_NSI>(hits);
-      if (b) need |= 1u << S;
-   });
+#ifdef EXP_NOCAND
+   unsigned cand = (1u << JR_NSA) - 1u;
+#else
+   unsigned cand = jr_grid_candidates<OCB_JIT_nsdf>(sdfs, ws, Pp, t);
+#endif
    PHASE(2);
 
-   int gcur = -1;
-   double F[3] = {0.0, 0.0, 0.0}, M[3] = {0.0, 0.0, 0.0};
-   auto flush_group = [&]()
+   /* force f at point c on joint frame g: its wrench about the world origin */
+   auto add_wrench = [&](const int g, const double c[3], const double f[3], const double sign)
    {
-      if (gcur >= 0 && want_grad)
-      {
-         double *Wo = Wg + 6 * gcur * Pp;
-         Wo[0] += F[0]; Wo[Pp] += F[1]; Wo[2 * Pp] += F[2];
-         Wo[3 * Pp] += M[0]; Wo[4 * Pp] += M[1]; Wo[5 * Pp] += M[2];
-      }
-      F[0] = F[1] = F[2] = M[0] = M[1] = M[2] = 0.0;
+      double *Wo = Wg + 6 * g * Pp;
+      Wo[0] = fma(sign, f[0], Wo[0]);
+      Wo[Pp] = fma(sign, f[1], Wo[Pp]);
+      Wo[2 * Pp] = fma(sign, f[2], Wo[2 * Pp]);
+      Wo[3 * Pp] = fma(sign, c[1] * f[2] - c[2] * f[1], Wo[3 * Pp]);
+      Wo[4 * Pp] = fma(sign, c[2] * f[0] - c[0] * f[2], Wo[4 * Pp]);
+      Wo[5 * Pp] = fma(sign, c[0] * f[1] - c[1] * f[0], Wo[5 * Pp]);
    };
-   while (need)
+
+   /* --- obstacle terms (mod.cpp:1169-1249) --- */
+   while (cand)
    {
-      const int s = __ffs(need) - 1;
-      need &= need - 1;
+      const int s = __ffs(cand) - 1;
+      cand &= cand - 1;
       const double *ps = ws + 3 * s * Pp + t;
       const double p[3] = {ps[0], ps[Pp], ps[2 * Pp]};
-      const double radius = jr_radius[s];
-
-      /* --- obstacle term, first step: which field, how far (mod.cpp:1169-1198) --- */
-      double d_obs = 0.0, bg[3] = {0.0, 0.0, 0.0};
-      int best = -1;
-      if ((cand >> s) & 1u) best = obstacle_probe(a, sdfs, p, radius, OCB_JIT_nsdf, d_obs, bg);
-      const bool obs = (best >= 0) && (d_obs < a.eps);
-      const int pb = jr_pair_begin[s];
-      unsigned hit_a = jr_hit_bits(hits, pb, jr_pair_begin[s + 1] - pb);
-      unsigned hit_i = (JR_NSI > 0) ? jr_hit_bits(hits, JR_NPA + s * JR_NSI, JR_NSI) : 0u;
-      if (!obs && !(hit_a | hit_i)) continue;
-      const int g = jr_group[s];
-      if (g != gcur)
+      double d_obs, bg[3];
+      const int best = obstacle_probe(a, sdfs, p, jr_radius[s], OCB_JIT_nsdf, d_obs, bg);
+      if (best < 0 || !(d_obs < a.eps)) continue;
+      const JrVel k = jr_velocity(ps, Pp, inv2dt);
+      double acc[3] = {0.0, 0.0, 0.0};
+      if (WANT_GRAD)
       {
-         flush_group();
-         gcur = g;
+#pragma unroll
+         for (int r = 0; r < 3; r++) acc[r] = (p[r] * -2.0 + ps[r * Pp - 1] + ps[r * Pp + 1]) * invdt2;
       }
+      double cost_s = 0.0, f[3] = {0.0, 0.0, 0.0};
+      obstacle_apply(a, sdfs[best], d_obs, bg, k.v, acc, k.vn, k.iv2, k.moving, WANT_GRAD, cost_s, f);
+      cost += cost_s;
+      if (WANT_GRAD) add_wrench(jr_group[s], p, f, 1.0);
+   }
 
-      double vel[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) vel[k] = (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
-      const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
-      const double rv = rsqrt(vn2);
-      const double vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
-      const double iv2 = rv * rv; /* 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
-      const bool moving = vn > 0.000001;
-      double cost_s = 0.0;
-      double f[3] = {0.0, 0.0, 0.0};
-
-      /* --- obstacle term, second step (mod.cpp:1200-1249) --- */
-      if (obs)
+   /* --- self collision (mod.cpp:1251-1317): one pair of active spheres in range; live = 0 turns the
+    * block into a no-op (the filler of an odd count) --- */
+   auto active_pair = [&](const int kk, const double live)
+   {
+      const unsigned info = jr_pair_info[kk]; /* s | o << 8 | group(s) << 16 | group(o) << 24 */
+      const int s = info & 0xff, o = (info >> 8) & 0xff;
+      const double *ps = ws + 3 * s * Pp + t, *po = ws + 3 * o * Pp + t;
+      const double p[3] = {ps[0], ps[Pp], ps[2 * Pp]}, q[3] = {po[0], po[Pp], po[2 * Pp]};
+      const JrVel ks = jr_velocity(ps, Pp, inv2dt), ko = jr_velocity(po, Pp, inv2dt);
+      const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      const double inv = rsqrt(d2);
+      const double dist = d2 * inv;
+      const double dd = dist - jr_pair_rsum[kk];
+      /* cost shape shared by both directions (1281-1289) */
+      const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
+      const double w_s = ks.vn * ofs * live, w_o = ko.vn * ofs * live;
+      cost += w_s * cshape;
+      cost += w_o * cshape;
+      if (WANT_GRAD)
       {
-         double acc[3] = {0.0, 0.0, 0.0};
-         if (want_grad)
-         {
-#pragma unroll
-            for (int k = 0; k < 3; k++) acc[k] = (p[k] * -2.0 + ps[k * Pp - 1] + ps[k * Pp + 1]) * invdt2;
-         }
-         obstacle_apply(a, sdfs[best], d_obs, bg, vel, acc, vn, iv2, moving, want_grad, cost_s, f);
-      }
-
-      /* --- self collision, each unordered pair once (1251-1317); see waypoint_cost --- */
-      const double ws_self = vn * a.obs_factor_self;
-      auto in_range = [&](const double q[3], const double *po, const int o)
-      {
-         const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
-         const double d2 = dx * dx + dy * dy + dz * dz;
-         const double inv = rsqrt(d2);
-         const double dist = d2 * inv;
-         const double dd = dist - (radius + jr_radius[o]);
-         const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
-         cost_s += ws_self * cshape;
-         double w2 = 0.0, v2[3] = {0.0, 0.0, 0.0}, r2 = 0.0;
-         bool moving2 = false;
-         if (po)
-         {
-#pragma unroll
-            for (int r = 0; r < 3; r++) v2[r] = (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
-            const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-            r2 = rsqrt(v2n2);
-            const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
-            moving2 = v2n > 0.000001;
-            w2 = v2n * a.obs_factor_self;
-            cost_s += w2 * cshape; /* the other sphere's own cost_sphere term */
-         }
-         if (!want_grad) return;
          const double sc = (dd < 0.0) ? -1.0 : ((dd < es) ? (dd * inv_es - 1.0) : 1.0);
          const double gh[3] = {dx * inv, dy * inv, dz * inv};
-         double x[3];
-         const double wa = sc * ws_self;
+         double x[3], y[3];
+         const double wa = sc * w_s, wb = -sc * w_o;
 #pragma unroll
-         for (int r = 0; r < 3; r++) x[r] = gh[r] * wa;
-         if (moving)
+         for (int r = 0; r < 3; r++) { x[r] = gh[r] * wa; y[r] = gh[r] * wb; }
+         /* each directed term loses its component along its own sphere's velocity (1302-1306) */
+         const double pjx = ks.moving ? (x[0] * ks.v[0] + x[1] * ks.v[1] + x[2] * ks.v[2]) * ks.iv2 : 0.0;
+         const double pjy = ko.moving ? (y[0] * ko.v[0] + y[1] * ko.v[1] + y[2] * ko.v[2]) * ko.iv2 : 0.0;
+#pragma unroll
+         for (int r = 0; r < 3; r++)
          {
-            const double pj = (x[0] * vel[0] + x[1] * vel[1] + x[2] * vel[2]) * iv2;
-#pragma unroll
-            for (int r = 0; r < 3; r++) x[r] = fma(-pj, vel[r], x[r]);
+            x[r] = fma(-pjx, ks.v[r], x[r]);
+            y[r] = fma(-pjy, ko.v[r], y[r]);
+            x[r] -= y[r]; /* (J_s - J_o)^T x + (J_o - J_s)^T y = J_s^T (x - y) - J_o^T (x - y) */
          }
-         if (po)
-         {
-            double y[3];
-            const double wb = -sc * w2;
-#pragma unroll
-            for (int r = 0; r < 3; r++) y[r] = gh[r] * wb;
-            if (moving2)
-            {
-               const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * (r2 * r2);
-#pragma unroll
-               for (int r = 0; r < 3; r++) y[r] = fma(-pj, v2[r], y[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < 3; r++) x[r] -= y[r];
-            const int go = jr_group[o];
-            if (go == gcur)
-            {
-               /* partner on the same joint frame: its reaction joins the wrench held in registers */
-               F[0] -= x[0]; F[1] -= x[1]; F[2] -= x[2];
-               M[0] -= q[1] * x[2] - q[2] * x[1];
-               M[1] -= q[2] * x[0] - q[0] * x[2];
-               M[2] -= q[0] * x[1] - q[1] * x[0];
-            }
-            else
-            {
-               double *Wo = Wg + 6 * go * Pp;
-               Wo[0] -= x[0];
-               Wo[Pp] -= x[1];
-               Wo[2 * Pp] -= x[2];
-               Wo[3 * Pp] -= q[1] * x[2] - q[2] * x[1];
-               Wo[4 * Pp] -= q[2] * x[0] - q[0] * x[2];
-               Wo[5 * Pp] -= q[0] * x[1] - q[1] * x[0];
-            }
-         }
-#pragma unroll
-         for (int r = 0; r < 3; r++) f[r] += x[r];
-      };
-      /* active partners in ascending order, then the inactive ones (frozen in the world, mod.cpp:2332-2345) */
-      while (hit_a)
-      {
-         const int k = __ffs(hit_a) - 1;
-         hit_a &= hit_a - 1;
-         const int o = jr_pair_o[pb + k];
-         const double *po = ws + 3 * o * Pp + t;
-         const double q[3] = {po[0], po[Pp], po[2 * Pp]};
-         in_range(q, po, o);
+         add_wrench((info >> 16) & 0xff, p, x, 1.0);
+         add_wrench((info >> 24) & 0xff, q, x, -1.0);
       }
-      while (hit_i)
+   };
+#pragma unroll
+   for (int w = 0; w < JR_HIT_WORDS; w++)
+   {
+      /* bits of active pairs in this word */
+      const unsigned amask = (32 * w >= JR_NPA) ? 0u : ((JR_NPA - 32 * w >= 32) ? 0xffffffffu : ((1u << ((JR_NPA - 32 * w) & 31)) - 1u));
+      unsigned bits = hits.w[w] & amask;
+      while (bits)
       {
-         const int i = __ffs(hit_i) - 1;
-         hit_i &= hit_i - 1;
-         const double q[3] = {jr_inactive_pos[i][0], jr_inactive_pos[i][1], jr_inactive_pos[i][2]};
-         in_range(q, nullptr, JR_NSA + i);
-      }
-      cost += cost_s;
-      if (want_grad)
-      {
-         F[0] += f[0]; F[1] += f[1]; F[2] += f[2];
-         M[0] += p[1] * f[2] - p[2] * f[1];
-         M[1] += p[2] * f[0] - p[0] * f[2];
-         M[2] += p[0] * f[1] - p[1] * f[0];
+         const int k1 = 32 * w + __ffs(bits) - 1;
+         bits &= bits - 1;
+#if JR_PAIRS_AT_ONCE == 2
+         const bool two = bits != 0;
+         const int k2 = two ? 32 * w + __ffs(bits) - 1 : k1;
+         bits &= bits - 1; /* no-op on zero */
+         active_pair(k1, 1.0);
+         active_pair(k2, two ? 1.0 : 0.0);
+#else
+         active_pair(k1, 1.0);
+#endif
       }
    }
-   flush_group();
+   /* an active sphere against an inactive one, frozen in the world (mod.cpp:2332-2345): one directed term */
+   if constexpr (JR_NSI > 0)
+   {
+#pragma unroll
+      for (int w = 0; w < JR_HIT_WORDS; w++)
+      {
+         const unsigned imask = (32 * w + 32 <= JR_NPA) ? 0u : ((32 * w >= JR_NPA) ? 0xffffffffu : ~((1u << ((JR_NPA - 32 * w) & 31)) - 1u));
+         unsigned bits = hits.w[w] & imask;
+         while (bits)
+         {
+            const int kk = 32 * w + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int s = (kk - JR_NPA) / JR_NSI, i = (kk - JR_NPA) % JR_NSI;
+            const double *ps = ws + 3 * s * Pp + t;
+            const double p[3] = {ps[0], ps[Pp], ps[2 * Pp]};
+            const JrVel ks = jr_velocity(ps, Pp, inv2dt);
+            const double dx = p[0] - jr_inactive_pos[i][0], dy = p[1] - jr_inactive_pos[i][1], dz = p[2] - jr_inactive_pos[i][2];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            const double inv = rsqrt(d2);
+            const double dist = d2 * inv;
+            const double dd = dist - (jr_radius[s] + jr_radius[JR_NSA + i]);
+            const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
+            const double w_s = ks.vn * ofs;
+            cost += w_s * cshape;
+            if (WANT_GRAD)
+            {
+               const double sc = (dd < 0.0) ? -1.0 : ((dd < es) ? (dd * inv_es - 1.0) : 1.0);
+               const double wa = sc * w_s;
+               double x[3] = {dx * inv * wa, dy * inv * wa, dz * inv * wa};
+               const double pjx = ks.moving ? (x[0] * ks.v[0] + x[1] * ks.v[1] + x[2] * ks.v[2]) * ks.iv2 : 0.0;
+#pragma unroll
+               for (int r = 0; r < 3; r++) x[r] = fma(-pjx, ks.v[r], x[r]);
+               add_wrench(jr_group[s], p, x, 1.0);
+            }
+         }
+      }
+   }
    PHASE(3);
-   if (want_grad) jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t);
+   if (WANT_GRAD) jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t);
    PHASE(4);
    return cost;
 }

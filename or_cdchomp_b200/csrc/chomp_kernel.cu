@@ -518,7 +518,8 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
 #ifdef OCB_JIT_ROBOT
-         csum += jr_waypoint_cost<FLOAT>(a, tb.sdfs, Ts, ws, Gs, Pp, t, !final_pass PHASE_PASS);
+         csum += final_pass ? jr_waypoint_cost<FLOAT, false>(a, tb.sdfs, Ts, ws, Gs, Pp, t PHASE_PASS)
+                            : jr_waypoint_cost<FLOAT, true>(a, tb.sdfs, Ts, ws, Gs, Pp, t PHASE_PASS);
 #else
          csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass PHASE_PASS);
 #endif

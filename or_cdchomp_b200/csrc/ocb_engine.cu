@@ -1234,7 +1234,7 @@ std::string jit_robot_header(const CompiledRobot &C, double eps_self)
          cut2.push_back(c2);
       }
    const int nbits = npa + nsa * nsi;
-   if (nbits > 128 || nbits == 0) return std::string();
+   if (nbits > 128 || nbits == 0 || nsa + nsi > 255 || C.n_groups > 255) return std::string();
    for (int s = 0; s < nsa; s++)
       if (pair_begin[s + 1] - pair_begin[s] > 32 || nsi > 32) return std::string();
    const int words = (nbits + 31) / 32;
@@ -1306,6 +1306,23 @@ std::string jit_robot_header(const CompiledRobot &C, double eps_self)
    darr2("jr_inactive_pos", C.inactive_pos, 3);
    iarr("jr_pair_begin", pair_begin); iarr("jr_pair_o", pair_o); iarr("jr_pair_kind", kind); darr("jr_pair_cut2", cut2);
    iarr("jr_own_tests", own_tests);
+   {
+      /* per active pair: the two spheres and their joint frames in one word, and the sum of the radii */
+      std::vector<double> rsum;
+      h += "__device__ constexpr unsigned jr_pair_info[" + std::to_string(std::max(npa, 1)) + "] = {";
+      int k = 0;
+      for (int s = 0; s < nsa; s++)
+         for (int e = pair_begin[s]; e < pair_begin[s + 1]; e++, k++)
+         {
+            const int o = pair_o[e];
+            const unsigned info = (unsigned) s | ((unsigned) o << 8) | ((unsigned) C.spheres[s].group << 16) | ((unsigned) C.spheres[o].group << 24);
+            h += (k ? ", " : "") + std::to_string(info) + "u";
+            rsum.push_back(C.spheres[s].radius + C.radius[o]);
+         }
+      if (npa == 0) h += "0u";
+      h += "};\n";
+      darr("jr_pair_rsum", rsum);
+   }
    {
       std::vector<int> grp;
       for (int s = 0; s < nsa; s++) grp.push_back(C.spheres[s].group);

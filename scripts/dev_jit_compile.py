@@ -22,6 +22,7 @@ cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3"
 cmd += ["-DOCB_JIT_%s=%d" % kv for kv in defs.items()]
 if robot_mode:
     cmd.append("-DOCB_JIT_ROBOT=1")
+cmd += os.environ.get("OCB_JIT_FLAGS", "").split()
 cmd.append(os.path.join(ROOT, "or_cdchomp_b200", "csrc", "chomp_kernel.cu"))
 r = subprocess.run(cmd, capture_output=True, text=True)
 import re
