@@ -24,7 +24,7 @@
 #include "ocb_jit_robot.h" /* generated: JR_* sizes and jr_* tables */
 
 #ifndef JR_PAIRS_AT_ONCE
-#define JR_PAIRS_AT_ONCE 2 /* sphere pairs in range worked off per step of the pair loop (1 or 2) */
+#define JR_PAIRS_AT_ONCE 1 /* sphere pairs in range worked off per step of the pair loop (1 or 2) */
 #endif
 
 namespace
@@ -45,6 +45,53 @@ __device__ __forceinline__ void jr_for(F &&f)
       f(JrIC<B>{});
       jr_for<B + 1, E>(f);
    }
+}
+
+/* ---- branch-free elementary functions ---------------------------------------------------------
+ * CUDA's rsqrt() and sincos() each end in a branch to a special-case path (denormals, huge arguments).
+ * A branch closes the scheduler's window: the three square roots of a sphere pair, or the seven joint
+ * angles of a sweep, are then evaluated one after the other although they do not depend on each
+ * other, and a warp of this kernel has little else to overlap them with.  These versions are the
+ * same algorithms without the branch; the callers keep their arguments in range. */
+
+/* 1 / sqrt(x) for a normal positive x: the MUFU.RSQ64H seed and the refinement step of rsqrt()'s own
+ * fast path, operation for operation (identical results) */
+__device__ __forceinline__ double jr_rsqrt(const double x)
+{
+   double y;
+   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+   const double e = fma(x, -(y * y), 1.0);
+   const double c = fma(e, 0.375, 0.5);
+   return fma(c, y * e, y);
+}
+
+/* sin and cos of |x| <= 1e4: Cody-Waite reduction by pi/2 in three pieces, the fdlibm kernels
+ * (k_sin.c, k_cos.c) on [-pi/4, pi/4], quadrant by selection; error below 1 ulp */
+__device__ __forceinline__ void jr_sincos(const double x, double &s, double &c)
+{
+   const double q = rint(x * 0x1.45f306dc9c883p-1);
+   const int iq = (int) q;
+   double r = fma(-q, 0x1.921fb54442d18p+0, x);
+   r = fma(-q, 0x1.1a62633145c07p-54, r);
+   r = fma(-q, -0x1.f1976b7ed8fbcp-110, r);
+   const double z = r * r;
+   double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+   ps = fma(z, ps, 2.75573137070700676789e-06);
+   ps = fma(z, ps, -1.98412698298579493134e-04);
+   ps = fma(z, ps, 8.33333333332248946124e-03);
+   ps = fma(z, ps, -1.66666666666666324348e-01);
+   const double sn = fma(r * z, ps, r);
+   double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+   pc = fma(z, pc, -2.75573143513906633035e-07);
+   pc = fma(z, pc, 2.48015872894767294178e-05);
+   pc = fma(z, pc, -1.38888888888741095749e-03);
+   pc = fma(z, pc, 4.16666666666666019037e-02);
+   const double hz = 0.5 * z, w = 1.0 - hz;
+   const double cs = w + (((1.0 - w) - hz) + z * (z * pc));
+   const bool swap = iq & 1;
+   const double a0 = swap ? cs : sn, b0 = swap ? sn : cs;
+   s = (iq & 2) ? -a0 : a0;
+   c = ((iq + 1) & 2) ? -b0 : b0;
 }
 
 /* r * x for a literal x, exact shortcuts for +-1 */
@@ -90,11 +137,11 @@ template <int J, int K> struct JrXt { static constexpr double x = jr_Xt[J][K]; }
 template <int S, int K> struct JrSP { static constexpr double x = jr_sph_pos[S][K]; };
 
 /* One step of the forward sweep for joint J (fk_step of chomp_device.cuh with the tables folded in).
- * sc: this waypoint's sine / cosine of every revolute joint; COMPUTE_SC fills it, else it is read. */
-template <int J, bool SAVE, bool FLOAT, bool COMPUTE_SC>
+ * sc: this waypoint's sine / cosine of every joint angle (jr_trig). */
+template <int J, bool SAVE, bool FLOAT>
 __device__ __forceinline__ void jr_fk_step(const double *__restrict__ Tt, const int Pp, double *__restrict__ slots,
                                            const int t, double R[9], double tr[3], double ax[3], double org[3],
-                                           double *sc)
+                                           const double *sc)
 {
    double Rn[9], tn[3];
    constexpr int load = jr_load[J];
@@ -140,16 +187,7 @@ __device__ __forceinline__ void jr_fk_step(const double *__restrict__ Tt, const 
    org[0] = tn[0]; org[1] = tn[1]; org[2] = tn[2];
    if constexpr (jr_type[J] == OCB_JOINT_REVOLUTE)
    {
-      double s, c;
-      if constexpr (COMPUTE_SC)
-      {
-         double v;
-         if constexpr (jr_c0[J] == 1.0 && jr_c1[J] == 0.0) v = Tt[jr_dof[J] * Pp];
-         else v = fma(jr_c0[J], Tt[jr_dof[J] * Pp], jr_c1[J]);
-         sincos(v, &s, &c);
-         if (sc) { sc[2 * J] = s; sc[2 * J + 1] = c; }
-      }
-      else { s = sc[2 * J]; c = sc[2 * J + 1]; }
+      const double s = sc[2 * J], c = sc[2 * J + 1];
 #pragma unroll
       for (int r = 0; r < 3; r++)
       {
@@ -181,20 +219,55 @@ __device__ __forceinline__ void jr_fk_step(const double *__restrict__ Tt, const 
    }
 }
 
+/* sine and cosine of every revolute joint's angle at this waypoint, all at once: seven independent
+ * evaluations in one straight line; an angle beyond the range of jr_sincos (never, for a joint with
+ * limits) is redone with sincos() afterwards */
+__device__ __forceinline__ void jr_trig(const double *__restrict__ Tt, const int Pp, double sc[2 * JR_NJ])
+{
+   bool big = false;
+   jr_for<0, JR_NJ>([&](auto jc)
+   {
+      constexpr int J = decltype(jc)::v;
+      if constexpr (jr_type[J] == OCB_JOINT_REVOLUTE)
+      {
+         double v;
+         if constexpr (jr_c0[J] == 1.0 && jr_c1[J] == 0.0) v = Tt[jr_dof[J] * Pp];
+         else v = fma(jr_c0[J], Tt[jr_dof[J] * Pp], jr_c1[J]);
+         big = big || !(fabs(v) <= 1e4);
+         jr_sincos(v, sc[2 * J], sc[2 * J + 1]);
+      }
+      else
+      {
+         sc[2 * J] = 0.0;
+         sc[2 * J + 1] = 1.0;
+      }
+   });
+   if (big)
+   {
+      jr_for<0, JR_NJ>([&](auto jc)
+      {
+         constexpr int J = decltype(jc)::v;
+         if constexpr (jr_type[J] == OCB_JOINT_REVOLUTE)
+            sincos(fma(jr_c0[J], Tt[jr_dof[J] * Pp], jr_c1[J]), &sc[2 * J], &sc[2 * J + 1]);
+      });
+   }
+}
+
 /* world positions of the active spheres of waypoint t (fk_waypoint of chomp_kernel.cu) */
 template <bool FLOAT>
 __device__ __forceinline__ void jr_fk_waypoint(const double *__restrict__ Ts, double *__restrict__ ws, const int Pp,
                                                const int t)
 {
    double *slots = ws + 3 * JR_NSA * Pp;
-   double R[9], tr[3], ax[3], org[3];
+   double R[9], tr[3], ax[3], org[3], sc[2 * JR_NJ];
+   jr_trig(Ts + t, Pp, sc);
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
    jr_for<0, JR_NJ>([&](auto jc)
    {
       constexpr int J = decltype(jc)::v;
-      jr_fk_step<J, true, FLOAT, true>(Ts + t, Pp, slots, t, R, tr, ax, org, nullptr);
+      jr_fk_step<J, true, FLOAT>(Ts + t, Pp, slots, t, R, tr, ax, org, sc);
       jr_for<jr_sph_begin[J], jr_sph_end[J]>([&](auto sc)
       {
          constexpr int S = decltype(sc)::v;
@@ -213,14 +286,15 @@ __device__ __forceinline__ void jr_flush_wrenches(const double *__restrict__ Ts,
 {
    double *slots = ws + 3 * JR_NSA * Pp;
    const double *Wg = ws + (3 * JR_NSA + 12 * JR_NSLOTS) * Pp + t;
-   double R[9], tr[3], ax[3], org[3];
+   double R[9], tr[3], ax[3], org[3], sc[2 * JR_NJ];
+   jr_trig(Ts + t, Pp, sc);
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
    jr_for<0, JR_NJ>([&](auto jc)
    {
       constexpr int J = decltype(jc)::v;
-      jr_fk_step<J, false, FLOAT, true>(Ts + t, Pp, slots, t, R, tr, ax, org, nullptr);
+      jr_fk_step<J, false, FLOAT>(Ts + t, Pp, slots, t, R, tr, ax, org, sc);
       double F0 = 0.0, F1 = 0.0, F2 = 0.0, M0 = 0.0, M1 = 0.0, M2 = 0.0;
       jr_for<jr_desc_begin[J], jr_desc_end[J]>([&](auto dc)
       {
@@ -380,9 +454,11 @@ __device__ __forceinline__ JrVel jr_velocity(const double *__restrict__ ps, cons
 #pragma unroll
    for (int r = 0; r < 3; r++) k.v[r] = (ps[r * Pp + 1] - ps[r * Pp - 1]) * inv2dt;
    const double vn2 = k.v[0] * k.v[0] + k.v[1] * k.v[1] + k.v[2] * k.v[2];
-   const double rv = rsqrt(vn2);
-   k.vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
-   k.iv2 = rv * rv; /* unguarded (inf at rest), as mod.cpp:1239 */
+   /* a finite difference of positions of size O(1) is either exactly zero or far above 1e-145 */
+   const bool rest = !(vn2 >= 1e-290);
+   const double rv = jr_rsqrt(rest ? 1.0 : vn2);
+   k.vn = rest ? 0.0 : vn2 * rv;
+   k.iv2 = rest ? HUGE_VAL : rv * rv; /* unguarded (inf at rest), as mod.cpp:1239 */
    k.moving = k.vn > 0.000001;
    return k;
 }
@@ -470,7 +546,7 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
       const JrVel ks = jr_velocity(ps, Pp, inv2dt), ko = jr_velocity(po, Pp, inv2dt);
       const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
       const double d2 = dx * dx + dy * dy + dz * dz;
-      const double inv = rsqrt(d2);
+      const double inv = jr_rsqrt(d2); /* two spheres in range of each other on different links: d2 is no denormal */
       const double dist = d2 * inv;
       const double dd = dist - jr_pair_rsum[kk];
       /* cost shape shared by both directions (1281-1289) */
@@ -539,7 +615,7 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
             const JrVel ks = jr_velocity(ps, Pp, inv2dt);
             const double dx = p[0] - jr_inactive_pos[i][0], dy = p[1] - jr_inactive_pos[i][1], dz = p[2] - jr_inactive_pos[i][2];
             const double d2 = dx * dx + dy * dy + dz * dz;
-            const double inv = rsqrt(d2);
+            const double inv = jr_rsqrt(d2);
             const double dist = d2 * inv;
             const double dd = dist - (jr_radius[s] + jr_radius[JR_NSA + i]);
             const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);

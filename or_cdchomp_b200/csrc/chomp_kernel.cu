@@ -518,8 +518,10 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          if (!final_pass)
             for (int j = 0; j < n; j++) Gs[j * Pp + t] = 0.0;
 #ifdef OCB_JIT_ROBOT
-         csum += final_pass ? jr_waypoint_cost<FLOAT, false>(a, tb.sdfs, Ts, ws, Gs, Pp, t PHASE_PASS)
-                            : jr_waypoint_cost<FLOAT, true>(a, tb.sdfs, Ts, ws, Gs, Pp, t PHASE_PASS);
+         /* few fields: their descriptors are read straight from the kernel parameters */
+         const OcbSdfDev *fields = (OCB_JIT_nsdf <= OCB_INLINE_SDFS) ? a.sdf_inline : tb.sdfs;
+         csum += final_pass ? jr_waypoint_cost<FLOAT, false>(a, fields, Ts, ws, Gs, Pp, t PHASE_PASS)
+                            : jr_waypoint_cost<FLOAT, true>(a, fields, Ts, ws, Gs, Pp, t PHASE_PASS);
 #else
          csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass PHASE_PASS);
 #endif

@@ -1458,6 +1458,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
 
    std::vector<OcbSdfDev> sd(n_sdfs);
    for (int i = 0; i < n_sdfs; i++) fill_sdf_dev(e->sdfs[sdf_ids[i]], sd[i]);
+   for (int i = 0; i < n_sdfs && i < OCB_INLINE_SDFS; i++) a.sdf_inline[i] = sd[i];
 
 #define TRY(x) do { rc = (x); if (rc) { ocb_batch_destroy(b); return rc; } } while (0)
    TRY(batch_upload(b, &a.spheres, C.spheres));

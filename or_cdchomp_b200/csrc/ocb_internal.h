@@ -16,6 +16,7 @@ typedef unsigned long long uint64_t;
 #define OCB_MAX_JOINTS 24   /* moving joints carried in kernel-parameter (constant) space */
 #define OCB_MAX_SDFS 64  /* descriptors are staged in shared memory */
 #define OCB_MAX_BW 8        /* half bandwidth of the smoothness metric (= derivative D) */
+#define OCB_INLINE_SDFS 2    /* field descriptors carried in the kernel parameters themselves */
 
 /* parent-transform source of a joint in the forward sweep */
 #define OCB_LOAD_PREV (-1)
@@ -119,6 +120,9 @@ struct OcbChompArgs
    int robot_smem;        /* 1: kernel compiled with the robot as code (OCB_JIT_ROBOT) -- no pair / subtree tables in
                              shared memory, the tridiagonal factor staged there instead */
    int pad1;
+   /* the first fields' descriptors by value: kernel parameters live in the constant bank, so a kernel
+    * compiled for <= OCB_INLINE_SDFS fields reads them as instruction operands (no loads, no registers) */
+   OcbSdfDev sdf_inline[OCB_INLINE_SDFS];
 };
 
 #if !defined(__CUDACC_RTC__) && defined(__cplusplus)
