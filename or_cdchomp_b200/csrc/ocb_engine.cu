@@ -1448,6 +1448,19 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    a.floating = floating ? 1 : 0;
    for (int j = 0; j < a.nj; j++) a.joints[j] = C.joints[j];
    a.trc_ss = M.ss; a.trc_sg = M.sg; a.trc_gg = M.gg;
+   {
+      /* the same band in every row?  (entries outside the matrix are never read: band_AT skips them) */
+      const int bw = params->derivative, W = 2 * bw + 1, mid = m / 2;
+      bool same = m > 2 * bw + 1;
+      for (int i = 0; i < m && same; i++)
+         for (int k = -bw; k <= bw; k++)
+         {
+            if (i + k < 0 || i + k >= m) continue;
+            if (M.Aband[(size_t) i * W + k + bw] != M.Aband[(size_t) mid * W + k + bw]) { same = false; break; }
+         }
+      a.band_toeplitz = same ? 1 : 0;
+      for (int k = 0; k < W; k++) a.band_row[k] = same ? M.Aband[(size_t) mid * W + k] : 0.0;
+   }
    a.lambda = params->lambda;
    a.dt = dt;
    a.eps = params->epsilon;

@@ -98,6 +98,10 @@ struct OcbChompArgs
    const double *bcoef_i; /* [m]     */
    const double *bcoef_f; /* [m]     */
    double trc_ss, trc_sg, trc_gg;
+   /* band_toeplitz: every row of A holds the same band (true for derivative = 1: A = (m+1) tridiag(-1, 2, -1));
+    * band_row is that band, read as instruction operands instead of m x (2 bw + 1) table loads */
+   int band_toeplitz, pad2;
+   double band_row[2 * OCB_MAX_BW + 1];
    /* parameters */
    double lambda, dt, eps, eps_self, obs_factor, obs_factor_self, hmc_lambda;
    const double *lim_lo;
