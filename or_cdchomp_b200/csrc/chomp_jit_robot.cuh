@@ -576,25 +576,36 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
          add_wrench((info >> 24) & 0xff, q, x, -1.0);
       }
    };
-#pragma unroll
-   for (int w = 0; w < JR_HIT_WORDS; w++)
    {
-      /* bits of active pairs in this word */
-      const unsigned amask = (32 * w >= JR_NPA) ? 0u : ((JR_NPA - 32 * w >= 32) ? 0xffffffffu : ((1u << ((JR_NPA - 32 * w) & 31)) - 1u));
-      unsigned bits = hits.w[w] & amask;
-      while (bits)
+      /* every lane walks its OWN list of pairs in range, in ascending order across the words of the hit
+       * set: the loop runs as often as the busiest lane has pairs */
+      unsigned bits[JR_HIT_WORDS];
+      unsigned any = 0;
+#pragma unroll
+      for (int w = 0; w < JR_HIT_WORDS; w++)
       {
-         const int k1 = 32 * w + __ffs(bits) - 1;
-         bits &= bits - 1;
-#if JR_PAIRS_AT_ONCE == 2
-         const bool two = bits != 0;
-         const int k2 = two ? 32 * w + __ffs(bits) - 1 : k1;
-         bits &= bits - 1; /* no-op on zero */
-         active_pair(k1, 1.0);
-         active_pair(k2, two ? 1.0 : 0.0);
-#else
-         active_pair(k1, 1.0);
-#endif
+         const unsigned amask = (32 * w >= JR_NPA) ? 0u : ((JR_NPA - 32 * w >= 32) ? 0xffffffffu : ((1u << ((JR_NPA - 32 * w) & 31)) - 1u));
+         bits[w] = hits.w[w] & amask;
+         any |= bits[w];
+      }
+      while (any)
+      {
+         int kk = 0;
+         bool found = false;
+         any = 0;
+#pragma unroll
+         for (int w = 0; w < JR_HIT_WORDS; w++)
+         {
+            const bool take = !found && bits[w] != 0;
+            if (take)
+            {
+               kk = 32 * w + __ffs(bits[w]) - 1;
+               bits[w] &= bits[w] - 1;
+            }
+            found = found || take;
+            any |= bits[w];
+         }
+         active_pair(kk, 1.0);
       }
    }
    /* an active sphere against an inactive one, frozen in the world (mod.cpp:2332-2345): one directed term */
