@@ -48,22 +48,12 @@ __device__ __forceinline__ void jr_for(F &&f)
 }
 
 /* ---- branch-free elementary functions ---------------------------------------------------------
- * CUDA's rsqrt() and sincos() each end in a branch to a special-case path (denormals, huge arguments).
+ * CUDA's rsqrt() and sincos() each end in a branch to a special-case path (denormals, huge arguments);
+ * fast_rsqrt (chomp_device.cuh) and jr_sincos below do without.
  * A branch closes the scheduler's window: the three square roots of a sphere pair, or the seven joint
  * angles of a sweep, are then evaluated one after the other although they do not depend on each
  * other, and a warp of this kernel has little else to overlap them with.  These versions are the
  * same algorithms without the branch; the callers keep their arguments in range. */
-
-/* 1 / sqrt(x) for a normal positive x: the MUFU.RSQ64H seed and the refinement step of rsqrt()'s own
- * fast path, operation for operation (identical results) */
-__device__ __forceinline__ double jr_rsqrt(const double x)
-{
-   double y;
-   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-   const double e = fma(x, -(y * y), 1.0);
-   const double c = fma(e, 0.375, 0.5);
-   return fma(c, y * e, y);
-}
 
 /* sin and cos of |x| <= 1e4: Cody-Waite reduction by pi/2 in three pieces, the fdlibm kernels
  * (k_sin.c, k_cos.c) on [-pi/4, pi/4], quadrant by selection; error below 1 ulp */
@@ -454,11 +444,7 @@ __device__ __forceinline__ JrVel jr_velocity(const double *__restrict__ ps, cons
 #pragma unroll
    for (int r = 0; r < 3; r++) k.v[r] = (ps[r * Pp + 1] - ps[r * Pp - 1]) * inv2dt;
    const double vn2 = k.v[0] * k.v[0] + k.v[1] * k.v[1] + k.v[2] * k.v[2];
-   /* a finite difference of positions of size O(1) is either exactly zero or far above 1e-145 */
-   const bool rest = !(vn2 >= 1e-290);
-   const double rv = jr_rsqrt(rest ? 1.0 : vn2);
-   k.vn = rest ? 0.0 : vn2 * rv;
-   k.iv2 = rest ? HUGE_VAL : rv * rv; /* unguarded (inf at rest), as mod.cpp:1239 */
+   speed_terms(vn2, k.vn, k.iv2);
    k.moving = k.vn > 0.000001;
    return k;
 }
@@ -546,7 +532,7 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
       const JrVel ks = jr_velocity(ps, Pp, inv2dt), ko = jr_velocity(po, Pp, inv2dt);
       const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
       const double d2 = dx * dx + dy * dy + dz * dz;
-      const double inv = jr_rsqrt(d2); /* two spheres in range of each other on different links: d2 is no denormal */
+      const double inv = fast_rsqrt(d2); /* two spheres in range of each other on different links: d2 is no denormal */
       const double dist = d2 * inv;
       const double dd = dist - jr_pair_rsum[kk];
       /* cost shape shared by both directions (1281-1289) */
@@ -626,7 +612,7 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
             const JrVel ks = jr_velocity(ps, Pp, inv2dt);
             const double dx = p[0] - jr_inactive_pos[i][0], dy = p[1] - jr_inactive_pos[i][1], dz = p[2] - jr_inactive_pos[i][2];
             const double d2 = dx * dx + dy * dy + dz * dz;
-            const double inv = jr_rsqrt(d2);
+            const double inv = fast_rsqrt(d2);
             const double dist = d2 * inv;
             const double dd = dist - (jr_radius[s] + jr_radius[JR_NSA + i]);
             const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);

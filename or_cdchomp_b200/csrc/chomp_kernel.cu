@@ -234,9 +234,8 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
 #pragma unroll
          for (int k = 0; k < 3; k++) vel[k] = (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
          const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
-         const double rv = rsqrt(vn2);
-         const double vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
-         const double iv2 = rv * rv; /* 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
+         double vn, iv2; /* |v| and 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
+         speed_terms(vn2, vn, iv2);
          const bool moving = vn > 0.000001;
          double cost_s = 0.0;
          double f[3] = {0.0, 0.0, 0.0};
@@ -260,21 +259,22 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          {
             const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
             const double d2 = dx * dx + dy * dy + dz * dz;
-            const double inv = rsqrt(d2);
+            const double inv = fast_rsqrt(d2); /* spheres on different links within range of each other: no denormal */
             const double dist = d2 * inv;
             const double dd = dist - (radius + tb.radius[o]);
             /* cost shape shared by both directions (1281-1289) */
             const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
             cost_s += ws_self * cshape;
-            double w2 = 0.0, v2[3] = {0.0, 0.0, 0.0}, r2 = 0.0;
+            double w2 = 0.0, v2[3] = {0.0, 0.0, 0.0}, r2 = 0.0; /* r2: 1 / |v2|^2 */
             bool moving2 = false;
             if (po)
             {
 #pragma unroll
                for (int r = 0; r < 3; r++) v2[r] = (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
                const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-               r2 = rsqrt(v2n2);
-               const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
+               double v2n, iv22;
+               speed_terms(v2n2, v2n, iv22);
+               r2 = iv22;
                moving2 = v2n > 0.000001;
                w2 = v2n * a.obs_factor_self;
                cost_s += w2 * cshape; /* the other sphere's own cost_sphere term */
@@ -301,7 +301,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
                for (int r = 0; r < 3; r++) y[r] = gh[r] * wb;
                if (moving2)
                {
-                  const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * (r2 * r2);
+                  const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * r2;
 #pragma unroll
                   for (int r = 0; r < 3; r++) y[r] = fma(-pj, v2[r], y[r]);
                }

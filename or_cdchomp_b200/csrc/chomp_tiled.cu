@@ -80,9 +80,7 @@ __device__ __forceinline__ void sphere_state(const double *__restrict__ pcol, in
       S.acc[k] = (pc * -2.0 + pm + pp) * invdt2;
    }
    const double vn2 = S.vel[0] * S.vel[0] + S.vel[1] * S.vel[1] + S.vel[2] * S.vel[2];
-   const double rv = rsqrt(vn2);
-   S.vn = (vn2 > 0.0) ? vn2 * rv : 0.0;
-   S.iv2 = rv * rv; /* unguarded, as mod.cpp:1239 */
+   speed_terms(vn2, S.vn, S.iv2); /* unguarded, as mod.cpp:1239 */
    S.moving = S.vn > 0.000001;
 }
 
@@ -102,7 +100,7 @@ __device__ __forceinline__ void self_pair_term(const PairConst &K, const SphereS
    const double es = K.es, inv_es = K.inv_es, half_inv_es = K.half_inv_es;
    const double dx = S.p[0] - q[0], dy = S.p[1] - q[1], dz = S.p[2] - q[2];
    const double d2 = dx * dx + dy * dy + dz * dz;
-   const double inv = rsqrt(d2);
+   const double inv = fast_rsqrt(d2);
    const double dd = d2 * inv - rsum;
    const double cshape = (dd < 0.0) ? (0.5 * es - dd) : half_inv_es * (dd - es) * (dd - es);
    const double ws_self = S.vn * K.obs_factor_self;
@@ -115,8 +113,8 @@ __device__ __forceinline__ void self_pair_term(const PairConst &K, const SphereS
 #pragma unroll
       for (int r = 0; r < 3; r++) v2[r] = (po[r * CS + 1] - po[r * CS - 1]) * inv2dt;
       const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-      r2 = rsqrt(v2n2);
-      const double v2n = (v2n2 > 0.0) ? v2n2 * r2 : 0.0;
+      double v2n;
+      speed_terms(v2n2, v2n, r2); /* r2: 1 / |v2|^2 */
       moving2 = v2n > 0.000001;
       w2 = v2n * K.obs_factor_self;
       cost_s += w2 * cshape; /* the partner's own cost_sphere term */
@@ -143,7 +141,7 @@ __device__ __forceinline__ void self_pair_term(const PairConst &K, const SphereS
       for (int r = 0; r < 3; r++) y[r] = gh[r] * wb;
       if (moving2)
       {
-         const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * (r2 * r2);
+         const double pj = (y[0] * v2[0] + y[1] * v2[1] + y[2] * v2[2]) * r2;
 #pragma unroll
          for (int r = 0; r < 3; r++) y[r] = fma(-pj, v2[r], y[r]);
       }
