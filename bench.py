@@ -714,7 +714,7 @@ def main():
     extras = {}
     want = [w for w in args.only.split(",") if w] or ["cfg3", "cfg4", "cfg5", "hbm"]
     with_cpu = not args.no_cpu_baseline
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:   # single-GPU measurements: not repeated under torchrun
         if "cfg3" in want:
             extras["cfg3_sdf_build"] = measure_sdf_build(torch, eng, stream, device, with_cpu)
             eng.trim()
