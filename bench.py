@@ -398,7 +398,7 @@ def measure_sdf_build(torch, eng, stream, device, with_cpu=True, n=400):
     for _ in range(2):
         eng.computedistancefield(gp, sizes, lengths, ce, out=(out_obs, out_sdf))
     e2e_s = (time.perf_counter() - t0) / 2
-    traffic = load_json("profiles", "traffic.json").get("sdf_build_bytes_400cubed_r2") if n == 400 else None
+    traffic = (load_json("profiles", "traffic.json").get("sdf_build_bytes_400cubed_r2") or {}).get("total") if n == 400 else None
     rec = {"metric": "sdf_build_mvoxels_per_s", "value": ncell / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "workload": "BASELINE configs[2]: computedistancefield, 64 boxes + 32 spheres, cube_extent %g -> %s voxels"
                        % (ce, "x".join(str(int(s)) for s in sizes)),

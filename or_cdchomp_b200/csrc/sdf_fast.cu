@@ -145,14 +145,16 @@ __device__ __forceinline__ int dz2_nearest(uint32_t bits, int lane, int zbase, i
  * is not pushed, and (b) emit is called only between the first and the last positive sample.
  * With a few percent of obstacle cells this leaves a handful of envelope entries per line. */
 template <bool ONLY_AT_POSITIVE, class Load8, class Emit>
-__device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ stack, size_t stride, Load8 load8, Emit emit)
+__device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ stack, size_t stride, Load8 load8, Emit emit,
+                                              int q_begin = 0)
 {
+   /* samples q_begin .. len-1 (the caller knows that nothing outside matters) */
    int np = 0;
    int v1 = 0, g1 = 0; /* top entry    */
    int v0 = 0, g0 = 0; /* second entry */
    int q_lo = len, q_hi = -1; /* samples whose result is wanted */
    int g_prev = 1;            /* height left of the batch (nothing there: treated as non-zero) */
-   for (int q0 = 0; q0 < len; q0 += 8)
+   for (int q0 = q_begin; q0 < len; q0 += 8)
    {
       int vals[8];
       load8(q0, vals);
@@ -208,7 +210,7 @@ __device__ __forceinline__ void envelope_pass(int len, uint32_t *__restrict__ st
    }
    if (!ONLY_AT_POSITIVE)
    {
-      q_lo = 0;
+      q_lo = q_begin;
       q_hi = len - 1;
    }
    if (np == 0)
@@ -305,24 +307,36 @@ edt_zy_kernel(const uint32_t *__restrict__ mask, const RowSum *__restrict__ sums
    else envelope_pass<true>(ny, stack, nlines, load8, emit);
 }
 
-/* ---- pass 3: lower envelope along x, final sqrt and sign; one warp per (y, z-word) tile ---- */
+/* ---- pass 3: lower envelope along x, final sqrt and sign; one warp per (y, z-word) tile, one thread
+ * per line, BOTH fields by the same thread:
+ *   - the obstacle field (distance to the nearest obstacle, wanted at free cells) is a full
+ *     envelope pass over the line; which cells are free comes from the packed bit mask
+ *     (one word per 32 lines and x: 1/8 byte per cell), not from a second read of the intermediate;
+ *   - the free-cell field (wanted at obstacle cells only) is needed on the few lines that contain
+ *     obstacle cells at all, and there only between the free cells that bracket them
+ *     (first obstacle - 1 .. last obstacle + 1: any source further out is further away and no lower),
+ *     so its pass re-reads just that stretch.
+ * The intermediate is therefore read once (plus those stretches) instead of four times. ---- */
 __global__ void __launch_bounds__(256)
-edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, uint32_t *__restrict__ stacks,
-                  int nx, int ny, int nz, int nwz, double pitch2, const int *__restrict__ flag_nonbinary)
+edt_x_kernel(const int *__restrict__ inter, const uint32_t *__restrict__ mask, double *__restrict__ sdf,
+             uint32_t *__restrict__ stacks, int nx, int ny, int nz, int nwz, double pitch2,
+             const int *__restrict__ flag_nonbinary)
 {
    if (*flag_nonbinary) return;
    const int lane = threadIdx.x & 31;
    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (tile >= ny * nwz) return;
-   const int field = blockIdx.y;
    const int y = tile / nwz, wz = tile % nwz;
    const int z = wz * 32 + lane;
    const bool in = z < nz;
    const size_t slab = (size_t) ny * nz;
    const size_t col = (size_t) y * nz + (in ? z : 0);
    const size_t nlines = (size_t) ny * nwz * 32;
-   uint32_t *stack = stacks + (size_t) field * nx * nlines + (size_t) tile * 32 + lane;
-   auto load8 = [&](int x0, int vals[8])
+   uint32_t *stack = stacks + (size_t) tile * 32 + lane;
+   const uint32_t *mcol = mask + (size_t) wz * ny + y; /* + x * nwz * ny: the tile's obstacle bits at x */
+   const size_t mstride = (size_t) nwz * ny;
+   int o_lo = nx, o_hi = -1; /* first / last obstacle cell of the line */
+   auto load_obstacle_field = [&](int x0, int vals[8])
    {
       int raw[8];
 #pragma unroll
@@ -333,21 +347,48 @@ edt_x_kernel(const int *__restrict__ inter, double *__restrict__ sdf, uint32_t *
          const int v = raw[k];
          int g = INF_I;
          if (in && x0 + k < nx)
-            g = (field == 0) ? (v > 0 ? v : 0)   /* obstacle cells are the zeros of the obstacle field */
-                             : (v < 0 ? -v : 0);
+         {
+            g = v > 0 ? v : 0; /* obstacle cells are the zeros of the obstacle field */
+            if (v < 0)
+            {
+               o_lo = min(o_lo, x0 + k);
+               o_hi = x0 + k;
+            }
+         }
          vals[k] = g;
       }
    };
-   auto emit = [&](int x, int val)
+   auto emit_free_cells = [&](int x, int val)
    {
       if (!in) return;
-      const int v = __ldg(inter + (size_t) x * slab + col);
-      const double d = (val >= INF_I) ? (double) HUGE_VAL : sqrt((double) val * pitch2);
-      if (field == 0 && v > 0) sdf[x * slab + col] = d;   /* free cell: + distance to obstacles */
-      if (field == 1 && v < 0) sdf[x * slab + col] = -d;  /* obstacle cell: - distance to free  */
+      const bool is_obs = (__ldg(mcol + (size_t) x * mstride) >> lane) & 1u;
+      if (is_obs) return;
+      sdf[x * slab + col] = (val >= INF_I) ? (double) HUGE_VAL : sqrt((double) val * pitch2); /* + distance to obstacles */
    };
-   if (field == 0) envelope_pass<false>(nx, stack, nlines, load8, emit);
-   else envelope_pass<true>(nx, stack, nlines, load8, emit);
+   envelope_pass<false>(nx, stack, nlines, load_obstacle_field, emit_free_cells);
+   if (o_hi < 0) return; /* no obstacle cell on this line */
+   const int x_begin = max(o_lo - 1, 0), x_end = min(o_hi + 2, nx);
+   auto load_free_field = [&](int x0, int vals[8])
+   {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+      {
+         int g = INF_I;
+         if (x0 + k < x_end)
+         {
+            const int v = __ldg(inter + (size_t) (x0 + k) * slab + col);
+            g = v < 0 ? -v : 0; /* free cells are the zeros of the free-cell field */
+         }
+         vals[k] = g;
+      }
+   };
+   auto emit_obstacle_cells = [&](int x, int val)
+   {
+      const bool is_obs = (__ldg(mcol + (size_t) x * mstride) >> lane) & 1u;
+      if (!is_obs) return;
+      sdf[x * slab + col] = (val >= INF_I) ? -(double) HUGE_VAL : -sqrt((double) val * pitch2); /* - distance to free cells */
+   };
+   envelope_pass<true>(x_end, stack, nlines, load_free_field, emit_obstacle_cells, x_begin);
 }
 
 } /* namespace */
@@ -403,7 +444,7 @@ extern "C" cudaError_t ocb_launch_bin_sdf_fast(const double *d_obs, double *d_sd
    const double pitch = lengths[0] / sizes[0];
    uint32_t *stacks = (uint32_t *) (((uintptr_t) (inter + (size_t) rows * nz) + 255) & ~(uintptr_t) 255);
    edt_zy_kernel<<<dim3((nx * nwz + 7) / 8, 2), 256, 0, st>>>(mask, sums, inter, stacks, nx, ny, nz, nwz, flag);
-   edt_x_kernel<<<dim3((ny * nwz + 7) / 8, 2), 256, 0, st>>>(inter, d_sdf, stacks, nx, ny, nz, nwz, pitch * pitch, flag);
+   edt_x_kernel<<<(ny * nwz + 7) / 8, 256, 0, st>>>(inter, mask, d_sdf, stacks, nx, ny, nz, nwz, pitch * pitch, flag);
    if (launches) (*launches) += 3;
    e = cudaGetLastError();
    if (e != cudaSuccess) return e;
