@@ -559,7 +559,7 @@ def measure_hbm_field(torch, eng, stream, device, with_cpu, steps=3):
         flavour = po.best_flavour()
         sdf_host = eng.download_sdf(sid, sizes)
         sd = capi.SdfDesc(sdf_host, lengths, gpose)
-        k = 96
+        k = 40
         v, dt = cpu_baseline(flavour, robot, params, [sd], starts[:k], goals[:k], N_ITER, threads=1)
         rec["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if flavour == "reference" else "port",
                                "sample": "first %d runs x %d iterations on the same 512 MB field, one thread (%.1f s)" % (k, N_ITER, dt)}
