@@ -240,8 +240,8 @@ extern "C" int cd_chomp_create(struct cd_chomp **cp, int m, int n, int D, double
    for (int d = 0; d < D; d++)
    {
       c->wds[d] = (d < D - 1) ? 0.0 : 1.0;               /* chomp.c:127-128 */
-      c->inits[d] = c->initsfinals + (size_t) d * n;      /* zero vectors, chomp.c:131-141 */
-      c->finals[d] = c->initsfinals + (size_t) (D + d) * n;
+      c->inits[d] = c->initsfinals + (size_t) (2 * d) * n;      /* zero vectors, interleaved as chomp.c:131-141 */
+      c->finals[d] = c->initsfinals + (size_t) (2 * d + 1) * n;
    }
    for (int j = 0; j < n; j++)
    {

@@ -839,6 +839,25 @@ struct ocb_module
       if (i < argv.size()) bad_args(argv, i);
       if (!r) throw module_error("you must pass a created run!");
       if (n_iter < 0) throw module_error("n_iter must be >=0!");
+      if (!trajs_fileformstr.empty())
+      {
+         /* the string is used as a printf format with the iteration number (mod.cpp:2779, sprintf): exactly
+          * one integer conversion is accepted, anything else (%s, %n, a second conversion) is refused here
+          * instead of being undefined behaviour in the planner process */
+         int convs = 0;
+         bool ok = true;
+         for (size_t k = 0; k < trajs_fileformstr.size() && ok; k++)
+         {
+            if (trajs_fileformstr[k] != '%') continue;
+            size_t e = k + 1;
+            if (e < trajs_fileformstr.size() && trajs_fileformstr[e] == '%') { k = e; continue; }
+            while (e < trajs_fileformstr.size() && strchr("0123456789-+ #", trajs_fileformstr[e])) e++;
+            if (e < trajs_fileformstr.size() && strchr("diu", trajs_fileformstr[e])) convs++;
+            else ok = false;
+            k = e;
+         }
+         if (!ok || convs != 1) throw module_error("trajs_fileformstr must contain exactly one %d-style conversion!");
+      }
       if (!trajs_fileformstr.empty() && r->floating)
          throw module_error("Error: trajs_fileformstr and floating_base combined is not yet implemented!"); /* mod.cpp:2772-2776 */
       std::vector<double> total(r->n_runs);
