@@ -82,6 +82,12 @@ int ocb_module_destroy(ocb_module *m);
 int ocb_module_send_command(ocb_module *m, const char *cmd, char *out, size_t out_cap, size_t *out_len);
 /* text of the exception thrown by the last failed command on this thread */
 const char *ocb_module_last_error(void);
+/* The <orcdchomp><spheres> block of a robot / kinbody XML text, read as the reference's XML reader
+ * reads it (src/orcdchomp_kdata.cpp:65-98): every <sphere link=".." pos="x y z" radius="r"/> in
+ * document order.  link_names [cap][64], pos [cap][3], radius [cap] (each may be NULL); *n_out = number
+ * of spheres found (only the first cap are stored).  Returns 0, or -2 with the reason in err. */
+int ocb_kdata_parse_spheres(const char *xml, int cap, char *link_names, double *pos, double *radius,
+                            int *n_out, char *err, size_t err_cap);
 /* numeric access to a run handle returned by create / createbatch ("%p" text) */
 int ocb_module_run_batch(ocb_module *m, const char *handle, ocb_batch **batch);
 

@@ -10,6 +10,7 @@ CUDA engine and the CPU oracle consume; it is "a WAM-like 7-dof arm with a
 3-finger hand", not a calibrated Barrett model.
 """
 import math
+import os
 
 import numpy as np
 
@@ -74,25 +75,39 @@ WAM7_DEMO_START = np.array([2.5, -1.8, 0.0, 2.0, 0.0, 0.2, 0.0])
 # the demo's goal comes from ikfast (not reproducible offline); fixed stand-in
 WAM7_DEMO_GOAL = np.array([0.6, 0.9, 0.3, 1.4, -0.4, 0.5, 0.8])
 
-# scripts/barrettwam_withspheres.robot.xml:24-45, in XML order
-WAM7_SPHERES = [
-    ("wam0", (0.22, 0.14, 0.346), 0.15),
-    ("wam2", (0.0, 0.0, 0.2), 0.06),
-    ("wam2", (0.0, 0.0, 0.3), 0.06),
-    ("wam2", (0.0, 0.0, 0.4), 0.06),
-    ("wam2", (0.0, 0.0, 0.5), 0.06),
-    ("wam3", (0.0, 0.0, 0.0), 0.06),
-    ("wam4", (0.0, 0.0, 0.2), 0.06),
-    ("wam4", (0.0, 0.0, 0.1), 0.06),
-    ("wam4", (0.0, 0.0, 0.3), 0.06),
-    ("wam6", (0.0, 0.0, 0.1), 0.06),
-    ("Finger0-1", (0.05, -0.01, 0.0), 0.04),
-    ("Finger1-1", (0.05, -0.01, 0.0), 0.04),
-    ("Finger2-1", (0.05, -0.01, 0.0), 0.04),
-    ("Finger0-2", (0.05, 0.0, 0.0), 0.04),
-    ("Finger1-2", (0.05, 0.0, 0.0), 0.04),
-    ("Finger2-2", (0.05, 0.0, 0.0), 0.04),
-]
+def parse_spheres_xml(text):
+    """The <orcdchomp><spheres> block of a robot XML text -> [(link, (x, y, z), radius), ...] in
+    document order, read by the library's own reader (ocb_kdata_parse_spheres: the element and
+    attribute handling of src/orcdchomp_kdata.cpp:65-98 in the reference)."""
+    import ctypes as C
+    from . import capi
+    lib = capi.load_library()
+    fn = lib.ocb_kdata_parse_spheres
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_char_p, C.c_int, C.c_char_p, capi.c_double_p, capi.c_double_p, capi.c_int_p, C.c_char_p, C.c_size_t]
+    cap = 512
+    names = C.create_string_buffer(cap * 64)
+    pos = np.zeros((cap, 3))
+    rad = np.zeros(cap)
+    n = C.c_int()
+    err = C.create_string_buffer(256)
+    rc = fn(text.encode() if isinstance(text, str) else text, cap, names, capi.dptr(pos), capi.dptr(rad),
+            C.byref(n), err, len(err))
+    if rc:
+        raise ValueError(err.value.decode())
+    out = []
+    for k in range(min(n.value, cap)):
+        link = names.raw[k * 64:(k + 1) * 64].split(b"\0", 1)[0].decode()
+        out.append((link, (float(pos[k, 0]), float(pos[k, 1]), float(pos[k, 2])), float(rad[k])))
+    return out
+
+
+def wam7_spheres():
+    """The WAM + BarrettHand sphere model, parsed from the robot XML's <orcdchomp> block
+    (data/barrettwam_spheres.robot.xml; values of scripts/barrettwam_withspheres.robot.xml:24-45)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "data", "barrettwam_spheres.robot.xml")) as f:
+        return parse_spheres_xml(f.read())
 
 
 def wam7_robot(base_pose=None, hand_values=(0.5, 0.5, 0.5, 0.3)):
@@ -132,6 +147,7 @@ def wam7_robot(base_pose=None, hand_values=(0.5, 0.5, 0.5, 0.3)):
     add("Finger2-2", 15, (0.07, 0, 0), I, JOINT_REVOLUTE, (0, 0, 1), -1, (0, c2 / 3.0 + 0.7))
 
     names = [l[0] for l in links]
+    spheres = wam7_spheres()
     return RobotDesc(
         names=names,
         parent=[l[1] for l in links],
@@ -142,9 +158,9 @@ def wam7_robot(base_pose=None, hand_values=(0.5, 0.5, 0.5, 0.3)):
         dof_coeff=[l[6] for l in links],
         base_pose=base_pose,
         limit_lower=WAM7_LIMITS[:, 0], limit_upper=WAM7_LIMITS[:, 1],
-        sphere_link=[names.index(s[0]) for s in WAM7_SPHERES],
-        sphere_pos=[s[1] for s in WAM7_SPHERES],
-        sphere_radius=[s[2] for s in WAM7_SPHERES])
+        sphere_link=[names.index(s[0]) for s in spheres],
+        sphere_pos=[s[1] for s in spheres],
+        sphere_radius=[s[2] for s in spheres])
 
 
 def dense_sphere_arm(n_spheres=200, seed=5):

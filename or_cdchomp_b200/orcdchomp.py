@@ -32,6 +32,8 @@ _MODULE_EXPORTS = {
     "ocb_module_send_command": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ocb_module_last_error": (C.c_char_p, []),
     "ocb_module_run_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ocb_kdata_parse_spheres": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, c_double_p, c_double_p, capi.c_int_p,
+                                          C.c_char_p, C.c_size_t]),
 }
 
 
