@@ -581,6 +581,8 @@ def main():
                     help="headline only: skip the cfg3 / cfg4 / cfg5 / HBM-field sub-records")
     ap.add_argument("--only", default="", help="comma list of sub-records to run (cfg3,cfg4,cfg5,hbm); default all")
     ap.add_argument("--no-jit", action="store_true", help="use the library's own kernel instead of the run-time specialised one")
+    ap.add_argument("--shrink", type=float, default=0.05,
+                    help="end points drawn in the joint limits shrunk by this fraction (BASELINE: 0.05; experiments only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -629,7 +631,7 @@ def main():
         results do not depend on N; joint-limit-heavy runs spread evenly over the ranks)"""
         total = args.runs * world if scaling == "weak" else args.runs
         ids = np.arange(rank, total, world)
-        s_all, g_all = models.random_endpoints(robot, total)
+        s_all, g_all = models.random_endpoints(robot, total, shrink=args.shrink)
         starts, goals = np.ascontiguousarray(s_all[ids]), np.ascontiguousarray(g_all[ids])
         bb = BatchBench(torch, eng, stream, device, robot, params, [sid], starts, goals)
         batch = bb.batch

@@ -1569,6 +1569,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       /* blocks per SM the shared memory allows, not more than ~160 registers per thread can feed */
       int min_blocks = (int) ((size_t) e->smem_per_sm / (b->smem + 1024));
       min_blocks = std::max(1, std::min(min_blocks, 65536 / (b->threads * 160)));
+      if (const char *mb = getenv("OCB_JIT_MINBLOCKS")) min_blocks = std::max(1, atoi(mb)); /* development knob */
       char why[512] = "";
       /* the robot as straight-line code; OCB_JIT_ROBOT=0 in the environment keeps the table-driven kernel */
       const char *env = getenv("OCB_JIT_ROBOT");

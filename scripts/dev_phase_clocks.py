@@ -29,3 +29,16 @@ tot = acc.sum(axis=1)
 print("cycles per iteration per warp:", (tot / 100).round(0))
 for k in range(16):
     print("%-10s " % names[k] + "  ".join("%5.1f%%" % (100 * acc[w, k] / tot[w]) for w in range(nw)) + "   %8.0f cyc/iter (warp 0)" % (acc[0, k] / 100))
+
+# distribution over runs: the slowest runs set the launch time of a small batch
+per_run = tr[:, :nw * 16].reshape(R, nw, 16)[:, 0, :]
+tot_run = per_run.sum(axis=1)
+its = b.get_iterations()
+rounds = b.get_limit_rounds()
+order = np.argsort(-tot_run)
+print("total cycles per run: median %.3g  p90 %.3g  p99 %.3g  max %.3g  (sum of the 8 slowest / sum of all: %.3f)" % (
+    np.median(tot_run), np.percentile(tot_run, 90), np.percentile(tot_run, 99), tot_run.max(), tot_run[order[:8]].sum() / tot_run.sum()))
+for r in order[:8]:
+    print("  run %4d: %.3g cycles (%.1fx median), iterations %3d, max limit rounds %4d, limits phase %.0f%%" % (
+        r, tot_run[r], tot_run[r] / np.median(tot_run), its[r], rounds[r], 100 * per_run[r, 11] / tot_run[r]))
+print("runs over 2x median: %d, over 1.3x: %d" % ((tot_run > 2 * np.median(tot_run)).sum(), (tot_run > 1.3 * np.median(tot_run)).sum()))
