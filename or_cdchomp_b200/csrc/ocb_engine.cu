@@ -1549,7 +1549,9 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    {
       a.tiled = 1;
       a.tile_w = 0;
-      for (int tw = 32; tw >= 8; tw /= 2)
+      int tw_max = 32;
+      if (const char *tw_env = getenv("OCB_TILE_W")) tw_max = std::max(8, std::min(32, atoi(tw_env))); /* development knob */
+      for (int tw = tw_max; tw >= 8; tw /= 2)
          if (ocb_tile_smem_bytes(&a, tw) <= (size_t) e->smem_optin) { a.tile_w = tw; break; }
       b->run_smem = ocb_run_update_smem_bytes(&a);
       if (!a.tile_w || b->run_smem > (size_t) e->smem_optin)
