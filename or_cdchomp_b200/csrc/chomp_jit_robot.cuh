@@ -23,10 +23,6 @@
 
 #include "ocb_jit_robot.h" /* generated: JR_* sizes and jr_* tables */
 
-#ifndef JR_PAIRS_AT_ONCE
-#define JR_PAIRS_AT_ONCE 1 /* sphere pairs in range worked off per step of the pair loop (1 or 2) */
-#endif
-
 namespace
 {
 
@@ -456,8 +452,8 @@ __device__ __forceinline__ JrVel jr_velocity(const double *__restrict__ ps, cons
  *   1. all self-collision range tests in one straight-line pass -> one bit per pair in range;
  *   2. a straight-line pass marks the spheres that may lie inside a field; only those are probed, and
  *      only a sphere with a field value below epsilon has an obstacle term at all;
- *   3. the pairs in range are then worked off PAIR by pair, two at a time, each a branch-free block
- *      that needs nothing from the previous one: both spheres' velocities, both directed terms
+ *   3. the pairs in range are then worked off PAIR by pair, every lane walking its own list, each pair a
+ *      branch-free block that needs nothing from the previous one: both spheres' velocities, both directed terms
  *      (mod.cpp:1281-1317), the force on one sphere and its reaction on the other added straight to
  *      the wrenches of their joint frames (F, M about the world origin, in shared memory).
  * Sums therefore run in pair order instead of sphere order: results agree with waypoint_cost to rounding. */
@@ -521,8 +517,7 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
       if (WANT_GRAD) add_wrench(jr_group[s], p, f, 1.0);
    }
 
-   /* --- self collision (mod.cpp:1251-1317): one pair of active spheres in range; live = 0 turns the
-    * block into a no-op (the filler of an odd count) --- */
+   /* --- self collision (mod.cpp:1251-1317): one pair of active spheres in range (live: a weight of 1) --- */
    auto active_pair = [&](const int kk, const double live)
    {
       const unsigned info = jr_pair_info[kk]; /* s | o << 8 | group(s) << 16 | group(o) << 24 */

@@ -771,3 +771,43 @@ def test_multi_engine_c_abi(wam7, table):
         mb.close()
         m.remove_sdf(msid)
         m.close()
+
+
+def test_three_fields_best_of_k(engine, oracle, flavour, wam7, table):
+    """WAM7 against three fields with different poses (more than the two descriptors the run-time
+    specialised kernel carries in its parameters): best-of-K selection (mod.cpp:1169-1189), gradient
+    and a short descent against the oracle."""
+    rng = np.random.default_rng(21)
+    x = (np.arange(20) + 0.5) / 20
+    sds = [table["desc"]]
+    for k in range(2):
+        f = (0.1 + 0.6 * np.abs(x[:, None, None] - rng.uniform(0.3, 0.7)) + 0.5 * np.abs(x[None, :, None] - rng.uniform(0.3, 0.7))
+             + 0.2 * x[None, None, :])
+        pose = models.pose_make(rng.uniform(-0.9, -0.5, size=3) + np.array([0.3, 0.2, 0.4]),
+                                models.quat_from_axis_angle(rng.normal(size=3), rng.uniform(0.1, 0.8)))
+        sds.append(capi.SdfDesc(f, [1.6, 1.6, 1.6], pose))
+    params = capi.default_params(n_points=60, lambda_=120.0, obs_factor=300.0, epsilon=0.12)
+    starts, goals = models.random_endpoints(wam7, 4, seed0=77, shrink=0.2)
+    ids = [engine.upload_sdf(s) for s in sds]
+    b = engine.create_batch(wam7, params, ids, starts, goals)
+    b.capture_gradient(1)
+    b.iterate(1)
+    g = b.get_gradient()
+    b.close()
+    b = engine.create_batch(wam7, params, ids, starts, goals)
+    costs, status = b.iterate(30)
+    traj = b.get_traj()
+    b.close()
+    for r in range(4):
+        run = oracle.Run(wam7, params, sds, starts[r], goals[r], flavour=flavour)
+        _, _, _, gr = run.iterate(1, want_grads=True)
+        assert np.max(np.abs(g[r] - gr[0])) <= GRAD_RTOL * np.max(np.abs(gr[0]))
+        run.close()
+        run = oracle.Run(wam7, params, sds, starts[r], goals[r], flavour=flavour)
+        ret, c, _, _ = run.iterate(30)
+        assert ret == 0 and status[r] == 0
+        assert np.max(np.abs(traj[r] - run.traj())) <= TRAJ_ATOL
+        assert np.allclose(costs[r], c, rtol=1e-8, atol=0)
+        run.close()
+    for i in ids:
+        engine.remove_sdf(i)
