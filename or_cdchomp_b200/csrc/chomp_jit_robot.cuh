@@ -242,11 +242,16 @@ __device__ __forceinline__ void jr_trig(const double *__restrict__ Tt, const int
 /* world positions of the active spheres of waypoint t (fk_waypoint of chomp_kernel.cu) */
 template <bool FLOAT>
 __device__ __forceinline__ void jr_fk_waypoint(const double *__restrict__ Ts, double *__restrict__ ws, const int Pp,
-                                               const int t)
+                                               const int t, double *__restrict__ trig)
 {
    double *slots = ws + 3 * JR_NSA * Pp;
    double R[9], tr[3], ax[3], org[3], sc[2 * JR_NJ];
    jr_trig(Ts + t, Pp, sc);
+#ifndef JR_NO_TRIG_CACHE
+   /* the J^T sweep of this iteration needs the same sines and cosines: parked in global memory (L2) */
+#pragma unroll
+   for (int k = 0; k < 2 * JR_NJ; k++) trig[k * Pp + t] = sc[k];
+#endif
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
@@ -268,12 +273,18 @@ __device__ __forceinline__ void jr_fk_waypoint(const double *__restrict__ Ts, do
 /* J^T f of waypoint t from the per-joint-frame wrenches (flush_wrenches of chomp_kernel.cu) */
 template <bool FLOAT>
 __device__ __forceinline__ void jr_flush_wrenches(const double *__restrict__ Ts, double *__restrict__ ws,
-                                                  double *__restrict__ Gs, const int Pp, const int t)
+                                                  double *__restrict__ Gs, const int Pp, const int t,
+                                                  const double *__restrict__ trig)
 {
    double *slots = ws + 3 * JR_NSA * Pp;
    const double *Wg = ws + (3 * JR_NSA + 12 * JR_NSLOTS) * Pp + t;
    double R[9], tr[3], ax[3], org[3], sc[2 * JR_NJ];
+#ifndef JR_NO_TRIG_CACHE
+#pragma unroll
+   for (int k = 0; k < 2 * JR_NJ; k++) sc[k] = trig[k * Pp + t];
+#else
    jr_trig(Ts + t, Pp, sc);
+#endif
 #pragma unroll
    for (int k = 0; k < 9; k++) R[k] = 0.0;
    tr[0] = tr[1] = tr[2] = 0.0;
@@ -460,7 +471,8 @@ __device__ __forceinline__ JrVel jr_velocity(const double *__restrict__ ps, cons
 template <bool FLOAT, bool WANT_GRAD>
 __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const OcbSdfDev *__restrict__ sdfs,
                                                    const double *__restrict__ Ts, double *__restrict__ ws,
-                                                   double *__restrict__ Gs, const int Pp, const int t PHASE_ARG)
+                                                   double *__restrict__ Gs, const int Pp, const int t,
+                                                   const double *__restrict__ trig PHASE_ARG)
 {
    double *Wg = ws + (3 * JR_NSA + 12 * JR_NSLOTS) * Pp + t;
    const double inv2dt = 1.0 / (2.0 * a.dt);
@@ -627,7 +639,7 @@ __device__ __forceinline__ double jr_waypoint_cost(const OcbChompArgs &a, const 
       }
    }
    PHASE(3);
-   if (WANT_GRAD) jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t);
+   if (WANT_GRAD) jr_flush_wrenches<FLOAT>(Ts, ws, Gs, Pp, t, trig);
    PHASE(4);
    return cost;
 }

@@ -503,7 +503,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 
       /* ---- forward kinematics of all P waypoints ---- */
 #ifdef OCB_JIT_ROBOT
-      for (int t = tid; t < P; t += NT) jr_fk_waypoint<FLOAT>(Ts, ws, Pp, t);
+      for (int t = tid; t < P; t += NT) jr_fk_waypoint<FLOAT>(Ts, ws, Pp, t, a.trig_cache + (size_t) run * 2 * DIM(a, nj) * Pp);
 #else
       for (int t = tid; t < P; t += NT) fk_waypoint<FLOAT, PP>(a, tb, Ts, ws, t);
 #endif
@@ -520,8 +520,9 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 #ifdef OCB_JIT_ROBOT
          /* few fields: their descriptors are read straight from the kernel parameters */
          const OcbSdfDev *fields = (OCB_JIT_nsdf <= OCB_INLINE_SDFS) ? a.sdf_inline : tb.sdfs;
-         csum += final_pass ? jr_waypoint_cost<FLOAT, false>(a, fields, Ts, ws, Gs, Pp, t PHASE_PASS)
-                            : jr_waypoint_cost<FLOAT, true>(a, fields, Ts, ws, Gs, Pp, t PHASE_PASS);
+         const double *trig = a.trig_cache + (size_t) run * 2 * DIM(a, nj) * Pp;
+         csum += final_pass ? jr_waypoint_cost<FLOAT, false>(a, fields, Ts, ws, Gs, Pp, t, trig PHASE_PASS)
+                            : jr_waypoint_cost<FLOAT, true>(a, fields, Ts, ws, Gs, Pp, t, trig PHASE_PASS);
 #else
          csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass PHASE_PASS);
 #endif

@@ -1581,6 +1581,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       {
          a.robot_smem = 1; /* that kernel lays shared memory out differently (smem_layout) */
          b->smem = ocb_chomp_smem_bytes(&a);
+         if (!a.trig_cache) TRY(batch_alloc(b, &a.trig_cache, R * 2 * a.nj * a.Ppad));
       }
       if (ocb_jit_chomp_kernel(&a, e->device, b->threads, min_blocks, b->smem, robot_hdr.c_str(), &b->jit_kernel, why,
                                sizeof(why)) != 0)

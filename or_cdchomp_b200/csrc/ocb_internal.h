@@ -120,6 +120,8 @@ struct OcbChompArgs
    double *grad_out;      /* [R][m][n] */
    double *G_obs;         /* [R][m][n] obstacle + self-collision gradient, unscaled (tiled path) */
    double *tile_cost;     /* [R][n_tiles] cost partials (tiled path) */
+   double *trig_cache;    /* [R][2 nj][Ppad]: sine / cosine of every joint angle, written by the forward sweep and read
+                             back by the J^T sweep of the same iteration (compiled-robot kernel; stays in L2) */
    size_t ws_stride;      /* doubles of per-run workspace in shared memory (persistent kernel) */
    int robot_smem;        /* 1: kernel compiled with the robot as code (OCB_JIT_ROBOT) -- no pair / subtree tables in
                              shared memory, the tridiagonal factor staged there instead */
