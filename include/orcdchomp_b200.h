@@ -91,6 +91,29 @@ typedef struct ocb_sdf
    const double *data;          /* host pointer, sizes[0]*sizes[1]*sizes[2] doubles   */
 } ocb_sdf;
 
+/* One hard end-effector constraint: a task space region whose zero-width axes are held at zero
+ * (the `create` command's con_tsr / everyn_tsr / start_tsr arguments, src/orcdchomp_mod.cpp:1930-1996;
+ * callbacks con_tsr / con_everyn_tsr / con_start_tsr 1330-1784; projection src/libcd/chomp.c:553-600).
+ * The constrained frame is  robot link `link` * pose_link_ee  (a manipulator's end effector and its
+ * local tool transform, or a bare link with the identity).  Its pose seen from the TSR's frame,
+ * inv(T0w) * frame * inv(Twe), is written as [x y z roll pitch yaw]; entry i of that vector is held at
+ * zero when Bw[i][0] == 0 && Bw[i][1] == 0 (mod.cpp:2466-2519); the other bounds are not used. */
+#define OCB_CON_START 0   /* con_tsr 'start ...': first moving waypoint                      */
+#define OCB_CON_END   1   /* con_tsr 'end ...'  : last moving waypoint                       */
+#define OCB_CON_ALL   2   /* con_tsr 'all ...' and everyn_tsr: every moving waypoint         */
+#define OCB_CON_START_TSR 3 /* start_tsr: the start point itself joins the optimised rows
+                               (m = n_points-1, no initial boundary row, mod.cpp:2316, 2571-2578)
+                               and carries the constraint; at most one, not with floating_base */
+typedef struct ocb_constraint
+{
+   int where;                   /* OCB_CON_*                                            */
+   int link;                    /* robot link index of the constrained frame            */
+   double pose_link_ee[7];      /* frame in the link: [x y z qx qy qz qw]                */
+   double T0w[7];               /* tsr->T0w (parsed by tsr_create_parse, mod.cpp:3068)   */
+   double Twe[7];               /* tsr->Twe                                              */
+   double Bw[6][2];             /* bounds, rows x y z roll pitch yaw                     */
+} ocb_constraint;
+
 /* Per-batch parameters = the `create` command's numeric arguments and defaults
  * (src/orcdchomp_mod.cpp:1818-1848, 1875, 1888-2079). */
 typedef struct ocb_params
@@ -110,6 +133,9 @@ typedef struct ocb_params
                                    q_start / q_goal rows are that long, robot->base_pose is not used, all
                                    spheres are active, pose columns of the Jacobian are scaled by 0.01,
                                    quaternions are re-normalised after every iteration              */
+   int n_constraints;           /* hard constraints, in the order the reference adds them:
+                                   start_tsr, everyn_tsr, then the con_tsr list (mod.cpp:2571-2613) */
+   const ocb_constraint *constraints;
 } ocb_params;
 
 void ocb_params_default(ocb_params *p);

@@ -61,6 +61,21 @@ class OcbSdf(C.Structure):
     ]
 
 
+class OcbConstraint(C.Structure):
+    """ocb_constraint (include/orcdchomp_b200.h): one TSR hard constraint."""
+    _fields_ = [
+        ("where", C.c_int),
+        ("link", C.c_int),
+        ("pose_link_ee", C.c_double * 7),
+        ("T0w", C.c_double * 7),
+        ("Twe", C.c_double * 7),
+        ("Bw", (C.c_double * 2) * 6),
+    ]
+
+
+CON_START, CON_END, CON_ALL, CON_START_TSR = 0, 1, 2, 3
+
+
 class OcbParams(C.Structure):
     _fields_ = [
         ("n_points", C.c_int),
@@ -74,6 +89,8 @@ class OcbParams(C.Structure):
         ("obs_factor", C.c_double),
         ("obs_factor_self", C.c_double),
         ("floating_base", C.c_int),
+        ("n_constraints", C.c_int),
+        ("constraints", C.POINTER(OcbConstraint)),
     ]
 
 
@@ -94,10 +111,43 @@ def default_params(**kw):
     for k, v in kw.items():
         if k == "lambda":
             k = "lambda_"
+        if k == "constraints":
+            set_constraints(p, v)
+            continue
         if not hasattr(p, k):
             raise TypeError("unknown parameter %r" % k)
         setattr(p, k, v)
     return p
+
+
+_IDENTITY_POSE = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+
+
+def make_constraint(where, link, Bw, T0w=_IDENTITY_POSE, Twe=_IDENTITY_POSE, pose_link_ee=_IDENTITY_POSE):
+    """One ocb_constraint.  `where`: CON_START / CON_END / CON_ALL / CON_START_TSR (or their names);
+    `Bw`: 6 x 2 bounds, rows x y z roll pitch yaw -- a row of zeros holds that entry at zero."""
+    if isinstance(where, str):
+        where = {"start": CON_START, "end": CON_END, "all": CON_ALL, "start_tsr": CON_START_TSR}[where]
+    c = OcbConstraint()
+    c.where, c.link = int(where), int(link)
+    for name, val in (("pose_link_ee", pose_link_ee), ("T0w", T0w), ("Twe", Twe)):
+        v = np.asarray(val, dtype=np.float64).reshape(7)
+        for i in range(7):
+            getattr(c, name)[i] = v[i]
+    b = np.asarray(Bw, dtype=np.float64).reshape(6, 2)
+    for i in range(6):
+        c.Bw[i][0], c.Bw[i][1] = b[i, 0], b[i, 1]
+    return c
+
+
+def set_constraints(params, constraints):
+    """Attach a list of OcbConstraint to an OcbParams (the array is kept alive on the object)."""
+    constraints = list(constraints or [])
+    arr = (OcbConstraint * max(len(constraints), 1))(*constraints)
+    params._constraints_keepalive = arr
+    params.n_constraints = len(constraints)
+    params.constraints = C.cast(arr, C.POINTER(OcbConstraint)) if constraints else None
+    return params
 
 
 def as_f64(a):

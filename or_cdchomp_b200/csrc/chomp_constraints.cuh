@@ -1,0 +1,336 @@
+/* chomp_constraints.cuh -- hard end-effector constraints (task space regions) of the CHOMP update.
+ *
+ * What it replaces in the reference (paths relative to the reference root):
+ *   con_tsr / con_everyn_tsr / con_start_tsr      src/orcdchomp_mod.cpp:1330-1497, 1500-1657, 1659-1784
+ *     (value = chosen entries of [x y z yaw pitch roll] of  inv(T0w) * frame * inv(Twe);  Jacobian =
+ *      xyzypr_J * pose_jac_inverse * xm(inv(T0w)) * [angular; linear-at-origin] world Jacobian)
+ *   cd_kin_pose_to_xyzypr, cd_kin_pose_to_xyzypr_J src/libcd/kin.c:615-647, 680-718
+ *   cd_spatial_xm_from_pose, cd_spatial_pose_jac, cd_spatial_pose_jac_inverse
+ *                                                 src/libcd/spatial.c:71-102, 295-337, 339-375
+ *   the projection in cd_chomp_iterate            src/libcd/chomp.c:553-600 (dgemv / dgemm / LAPACKE_dgesv)
+ *
+ * Differences of FORM: the frame's Jacobian is never stored in world coordinates -- every joint column
+ * [axis; origin x axis] goes straight through the k x 6 map of its constraint; the three 6 x 6 products of
+ * the reference collapse to  lin = R_A v + (t_A - p) x (R_A w),  ang = E (R_A w)  with E the 3 x 3 product of
+ * the reference's yaw-pitch-roll and quaternion-rate tables.  The linear system is solved by the block with
+ * the same row-pivoted elimination LAPACK performs.
+ */
+#ifndef OCB_CHOMP_CONSTRAINTS_CUH
+#define OCB_CHOMP_CONSTRAINTS_CUH
+
+#include "chomp_device.cuh"
+
+namespace
+{
+
+/* unit quaternion [x y z w] of a rotation matrix, largest component first (its sign is free: every use
+ * below is even in q) */
+__device__ inline void con_quat_of(const double R[9], double q[4])
+{
+   const double tr = R[0] + R[4] + R[8];
+   if (tr >= R[0] && tr >= R[4] && tr >= R[8])
+   {
+      const double w = 0.5 * sqrt(1.0 + tr), s = 0.25 / w;
+      q[3] = w; q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+   }
+   else if (R[0] >= R[4] && R[0] >= R[8])
+   {
+      const double x = 0.5 * sqrt(1.0 + R[0] - R[4] - R[8]), s = 0.25 / x;
+      q[0] = x; q[1] = (R[1] + R[3]) * s; q[2] = (R[2] + R[6]) * s; q[3] = (R[7] - R[5]) * s;
+   }
+   else if (R[4] >= R[8])
+   {
+      const double y = 0.5 * sqrt(1.0 - R[0] + R[4] - R[8]), s = 0.25 / y;
+      q[1] = y; q[0] = (R[1] + R[3]) * s; q[2] = (R[5] + R[7]) * s; q[3] = (R[2] - R[6]) * s;
+   }
+   else
+   {
+      const double z = 0.5 * sqrt(1.0 - R[0] - R[4] + R[8]), s = 0.25 / z;
+      q[2] = z; q[0] = (R[2] + R[6]) * s; q[1] = (R[5] + R[7]) * s; q[3] = (R[3] - R[1]) * s;
+   }
+}
+
+/* what a constraint needs of its frame at one waypoint: the six candidate values, the point the linear
+ * rows pivot about, and the angular map E */
+struct ConFrame
+{
+   double xyzypr[6];
+   double arm[3];  /* t_A - p: lin = R_A v + arm x (R_A w) */
+   double E[9];    /* [yaw; pitch; roll] rates from the angular velocity in the TSR frame */
+};
+
+__device__ inline void con_frame(const OcbConDev &c, const double R[9], const double tr[3], ConFrame &f)
+{
+   /* frame in the world, then seen from the TSR:  A * (joint frame * C) */
+   double Rf[9], tf[3], Rt[9], p[3];
+#pragma unroll
+   for (int r = 0; r < 3; r++)
+   {
+#pragma unroll
+      for (int k = 0; k < 3; k++) Rf[3 * r + k] = R[3 * r] * c.CR[k] + R[3 * r + 1] * c.CR[3 + k] + R[3 * r + 2] * c.CR[6 + k];
+      tf[r] = R[3 * r] * c.Ct[0] + R[3 * r + 1] * c.Ct[1] + R[3 * r + 2] * c.Ct[2] + tr[r];
+   }
+#pragma unroll
+   for (int r = 0; r < 3; r++)
+   {
+#pragma unroll
+      for (int k = 0; k < 3; k++) Rt[3 * r + k] = c.AR[3 * r] * Rf[k] + c.AR[3 * r + 1] * Rf[3 + k] + c.AR[3 * r + 2] * Rf[6 + k];
+      p[r] = c.AR[3 * r] * tf[0] + c.AR[3 * r + 1] * tf[1] + c.AR[3 * r + 2] * tf[2] + c.At[r];
+   }
+   double q[4];
+   con_quat_of(Rt, q);
+   const double qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+   /* kin.c:615-647 */
+   f.xyzypr[0] = p[0]; f.xyzypr[1] = p[1]; f.xyzypr[2] = p[2];
+   const double half_sinp = qw * qy - qz * qx;
+   const double quarter_turn = 1.5707963267948966;
+   if (half_sinp > 0.49999)
+   {
+      f.xyzypr[3] = -2.0 * atan2(qx, qw); f.xyzypr[4] = quarter_turn; f.xyzypr[5] = 0.0;
+   }
+   else if (half_sinp < -0.49999)
+   {
+      f.xyzypr[3] = 2.0 * atan2(qx, qw); f.xyzypr[4] = -quarter_turn; f.xyzypr[5] = 0.0;
+   }
+   else
+   {
+      f.xyzypr[3] = atan2(2.0 * (qw * qz + qx * qy), 1.0 - 2.0 * (qy * qy + qz * qz));
+      f.xyzypr[4] = asin(2.0 * half_sinp);
+      f.xyzypr[5] = atan2(2.0 * (qw * qx + qy * qz), 1.0 - 2.0 * (qx * qx + qy * qy));
+   }
+#pragma unroll
+   for (int r = 0; r < 3; r++) f.arm[r] = c.At[r] - p[r];
+   /* Y = d[yaw pitch roll]/d[qx qy qz qw] (kin.c:694-716, general branch only, as the reference) */
+   double Y[12];
+   {
+      double nu = 2.0 * (qw * qz + qx * qy), de = 1.0 - 2.0 * (qy * qy + qz * qz);
+      double dn = de / (de * de + nu * nu), nn = nu / (de * de + nu * nu);
+      Y[0] = dn * (2.0 * qy);
+      Y[1] = dn * (2.0 * qx) + nn * (4.0 * qy);
+      Y[2] = dn * (2.0 * qw) + nn * (4.0 * qz);
+      Y[3] = dn * (2.0 * qz);
+      const double as = 2.0 * half_sinp;
+      const double s = 2.0 / sqrt(1.0 - as * as);
+      Y[4] = -s * qz; Y[5] = s * qw; Y[6] = -s * qx; Y[7] = s * qy;
+      nu = 2.0 * (qw * qx + qy * qz);
+      de = 1.0 - 2.0 * (qx * qx + qy * qy);
+      dn = de / (de * de + nu * nu);
+      nn = nu / (de * de + nu * nu);
+      Y[8] = dn * (2.0 * qw) + nn * (4.0 * qx);
+      Y[9] = dn * (2.0 * qz) + nn * (4.0 * qy);
+      Y[10] = dn * (2.0 * qy);
+      Y[11] = dn * (2.0 * qx);
+   }
+   /* H = d[qx qy qz qw]/d(omega) (spatial.c:361-373) */
+   const double hx = 0.5 * qx, hy = 0.5 * qy, hz = 0.5 * qz, hw = 0.5 * qw;
+   const double H[12] = {hw, hz, -hy, -hz, hw, hx, hy, -hx, hw, -hx, -hy, -hz};
+#pragma unroll
+   for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+         f.E[3 * r + k] = Y[4 * r] * H[k] + Y[4 * r + 1] * H[3 + k] + Y[4 * r + 2] * H[6 + k] + Y[4 * r + 3] * H[9 + k];
+}
+
+/* one world Jacobian column [w; v] through the constraint's map: entries of d[x y z yaw pitch roll] */
+__device__ inline void con_map_column(const OcbConDev &c, const ConFrame &f, const double w[3], const double v[3],
+                                      double out[6])
+{
+   double wt[3], vt[3];
+#pragma unroll
+   for (int r = 0; r < 3; r++)
+   {
+      wt[r] = c.AR[3 * r] * w[0] + c.AR[3 * r + 1] * w[1] + c.AR[3 * r + 2] * w[2];
+      vt[r] = c.AR[3 * r] * v[0] + c.AR[3 * r + 1] * v[1] + c.AR[3 * r + 2] * v[2];
+   }
+   out[0] = vt[0] + (f.arm[1] * wt[2] - f.arm[2] * wt[1]);
+   out[1] = vt[1] + (f.arm[2] * wt[0] - f.arm[0] * wt[2]);
+   out[2] = vt[2] + (f.arm[0] * wt[1] - f.arm[1] * wt[0]);
+#pragma unroll
+   for (int r = 0; r < 3; r++) out[3 + r] = f.E[3 * r] * wt[0] + f.E[3 * r + 1] * wt[1] + f.E[3 * r + 2] * wt[2];
+}
+
+__device__ inline bool con_applies(const OcbConDev &c, int i, int m)
+{
+   return c.where == OCB_CON_ALL || (c.where == OCB_CON_START && i == 0) || (c.where == OCB_CON_END && i == m - 1) ||
+          (c.where == OCB_CON_START_TSR && i == 0);
+}
+
+/* Values h and Jacobian rows J (row length n) of every constraint on moving waypoint t (column t of the
+ * [item][waypoint] arrays), written at the waypoint's rows of the run's stacked system; then
+ * h += -1/lambda * J AG_t  (chomp.c:562-565).  The joint frames of waypoint t are those the forward
+ * sweep of this iteration left in the workspace. */
+template <bool FLOAT>
+__device__ inline void con_eval_waypoint(const OcbChompArgs &a, const double *__restrict__ Ts,
+                                         double *__restrict__ slots, const double *__restrict__ AGc,
+                                         int Pp, int t, int m, int n, double inv_lambda,
+                                         double *__restrict__ Jc, double *__restrict__ hc)
+{
+   const int i = t - 1;
+   int row = a.con_row0[i];
+   for (int ci = 0; ci < a.n_con; ci++)
+   {
+      const OcbConDev &c = a.cons[ci];
+      if (!con_applies(c, i, m)) continue;
+      /* first walk: the frame */
+      double R[9], tr[3], ax[3], org[3];
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = 0.0;
+      R[0] = R[4] = R[8] = 1.0;
+      tr[0] = tr[1] = tr[2] = 0.0;
+      ConFrame f;
+      if (c.joint < 0)
+         con_frame(c, R, tr, f);
+      else
+         for (int j = 0; j <= c.joint; j++)
+         {
+            const OcbJointDev &J = a.joints[j];
+            fk_step<false, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
+            if (j == c.joint) con_frame(c, R, tr, f);
+         }
+      double *Jr = Jc + (size_t) row * n;
+      for (int e = 0; e < c.k * n; e++) Jr[e] = 0.0;
+      for (int r = 0; r < c.k; r++) hc[row + r] = f.xyzypr[c.rows[r]];
+      /* second walk: the columns of the joints that move the frame */
+      if (c.joint >= 0)
+      {
+         for (int j = 0; j <= c.joint; j++)
+         {
+            const OcbJointDev &J = a.joints[j];
+            fk_step<false, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
+            if (!((c.anc >> j) & 1ull) || J.c0 == 0.0) continue;
+            double w[3], v[3], col[6];
+            if (J.type == OCB_JOINT_REVOLUTE)
+            {
+               w[0] = ax[0]; w[1] = ax[1]; w[2] = ax[2];
+               v[0] = org[1] * ax[2] - org[2] * ax[1];
+               v[1] = org[2] * ax[0] - org[0] * ax[2];
+               v[2] = org[0] * ax[1] - org[1] * ax[0];
+            }
+            else
+            {
+               w[0] = w[1] = w[2] = 0.0;
+               v[0] = ax[0]; v[1] = ax[1]; v[2] = ax[2];
+            }
+            con_map_column(c, f, w, v, col);
+            for (int r = 0; r < c.k; r++) Jr[r * n + J.dof] = fma(J.c0, col[c.rows[r]], Jr[r * n + J.dof]);
+         }
+         if (FLOAT)
+         {
+            /* the seven pose entries (spatial.c:295-337): columns of [omega; v at the origin] */
+            const double x = Ts[t], y = Ts[Pp + t], z = Ts[2 * Pp + t];
+            const double bx = 2.0 * Ts[3 * Pp + t], by = 2.0 * Ts[4 * Pp + t], bz = 2.0 * Ts[5 * Pp + t],
+                         bw = 2.0 * Ts[6 * Pp + t];
+            const double Jsp[6][7] = {
+               {0, 0, 0, bw, -bz, by, -bx},
+               {0, 0, 0, bz, bw, -bx, -by},
+               {0, 0, 0, -by, bx, bw, -bz},
+               {1, 0, 0, -z * bz - y * by, -z * bw + y * bx, z * bx + y * bw, z * by - y * bz},
+               {0, 1, 0, z * bw + x * by, -z * bz - x * bx, z * by - x * bw, -z * bx + x * bz},
+               {0, 0, 1, -y * bw + x * bz, y * bz + x * bw, -y * by - x * bx, y * bx - x * by}};
+            for (int e = 0; e < 7; e++)
+            {
+               const double w[3] = {Jsp[0][e], Jsp[1][e], Jsp[2][e]}, v[3] = {Jsp[3][e], Jsp[4][e], Jsp[5][e]};
+               double col[6];
+               con_map_column(c, f, w, v, col);
+               for (int r = 0; r < c.k; r++) Jr[r * n + e] = col[c.rows[r]];
+            }
+         }
+      }
+      for (int r = 0; r < c.k; r++)
+      {
+         double acc = 0.0;
+         for (int j = 0; j < n; j++) acc += Jr[r * n + j] * AGc[j * Pp + t];
+         hc[row + r] = fma(-inv_lambda, acc, hc[row + r]);
+      }
+      row += c.k;
+   }
+}
+
+/* S = J Ainv J^T over the stacked rows (chomp.c:567-575): entry (r, q) couples the waypoints of the two rows */
+__device__ inline void con_build_system(const OcbChompArgs &a, const double *__restrict__ Jc, double *__restrict__ S,
+                                        int m, int n)
+{
+   const int K = a.con_K;
+   for (int e = threadIdx.x; e < K * K; e += blockDim.x)
+   {
+      const int r = e / K, q = e - r * K;
+      const double *Ja = Jc + (size_t) r * n, *Jb = Jc + (size_t) q * n;
+      double acc = 0.0;
+      for (int j = 0; j < n; j++) acc += Ja[j] * Jb[j];
+      S[e] = __ldg(a.Ainv + (size_t) a.con_row_wp[r] * m + a.con_row_wp[q]) * acc;
+   }
+}
+
+/* S x = b by the whole block: elimination with partial pivoting on rows (the factorisation LAPACKE_dgesv
+ * performs, chomp.c:579-581), then back substitution by warp 0.  S (K x K, row-major) and b live in
+ * global memory and are overwritten; x is left in b.  red / ired: block scratch in shared memory (>= 10).
+ * Returns non-zero when a pivot is exactly zero (b is then not a solution). */
+__device__ inline int con_solve(double *__restrict__ S, double *__restrict__ b, int K, double *red, int *ired)
+{
+   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = NT >> 5;
+   for (int k = 0; k < K; k++)
+   {
+      /* pivot: largest |S[i][k]|, i >= k; the first of equals */
+      double best = -1.0;
+      int at = K;
+      for (int i = k + tid; i < K; i += NT)
+      {
+         const double v = fabs(S[(size_t) i * K + k]);
+         if (v > best) { best = v; at = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+         const int oa = __shfl_xor_sync(0xffffffffu, at, o);
+         if (ov > best || (ov == best && oa < at)) { best = ov; at = oa; }
+      }
+      if (lane == 0) { red[warp] = best; ired[warp] = at; }
+      __syncthreads();
+      best = red[0];
+      at = ired[0];
+      for (int w = 1; w < nw; w++)
+         if (red[w] > best || (red[w] == best && ired[w] < at)) { best = red[w]; at = ired[w]; }
+      if (!(best > 0.0)) return k + 1; /* uniform: every thread reads the same partials */
+      if (at != k)
+      {
+         for (int j = k + tid; j < K; j += NT)
+         {
+            const double u = S[(size_t) k * K + j];
+            S[(size_t) k * K + j] = S[(size_t) at * K + j];
+            S[(size_t) at * K + j] = u;
+         }
+         if (tid == 0) { const double u = b[k]; b[k] = b[at]; b[at] = u; }
+      }
+      __syncthreads();
+      /* eliminate column k below the pivot: one warp per row, lanes across the row */
+      const double pinv = 1.0 / S[(size_t) k * K + k];
+      const double bk = b[k];
+      for (int i = k + 1 + warp; i < K; i += nw)
+      {
+         const double f = S[(size_t) i * K + k] * pinv;
+         if (f != 0.0)
+         {
+            for (int j = k + 1 + lane; j < K; j += 32) S[(size_t) i * K + j] = fma(-f, S[(size_t) k * K + j], S[(size_t) i * K + j]);
+            if (lane == 0) b[i] = fma(-f, bk, b[i]);
+         }
+      }
+      __syncthreads();
+   }
+   if (warp == 0)
+      for (int k = K - 1; k >= 0; k--)
+      {
+         double acc = 0.0;
+         for (int j = k + 1 + lane; j < K; j += 32) acc += S[(size_t) k * K + j] * b[j];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+         if (lane == 0) b[k] = (b[k] - acc) / S[(size_t) k * K + k];
+         __syncwarp();
+      }
+   __syncthreads();
+   return 0;
+}
+
+} /* namespace */
+
+#endif

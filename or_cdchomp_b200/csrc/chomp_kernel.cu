@@ -55,6 +55,9 @@
 #ifdef OCB_JIT_ROBOT
 #include "chomp_jit_robot.cuh" /* this batch's robot as straight-line code (run-time compilation only) */
 #endif
+#ifndef OCB_JIT
+#include "chomp_constraints.cuh" /* hard constraints: library kernel only */
+#endif
 
 namespace
 {
@@ -373,7 +376,7 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
    return cost;
 }
 
-template <bool FLOAT, int PP, int NN>
+template <bool FLOAT, int PP, int NN, bool CONS = false>
 __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -558,6 +561,66 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
        * dofs at once and the lane that owns an entry updates it on the spot -- one barrier for solve,
        * update and the any-violation vote.  Wider metrics: one thread per dof, then thread per waypoint. ---- */
       int violated = 0;
+#ifndef OCB_JIT
+      if (CONS)
+      {
+         /* ---- the same with hard constraints (chomp.c:553-600): AG first, then the constraint values h and
+          * Jacobians J at the current T; S = J A^-1 J^T; S x = h - J AG / lambda; T -= AG / lambda + A^-1 J^T x,
+          * which zeroes the linearised constraints at the new T.  Thread per dof for the two solves, thread
+          * per waypoint for the rows, the whole block for S and its factorisation (global scratch). ---- */
+         const int K = a.con_K;
+         double *Jc = a.con_scratch + (size_t) run * a.con_stride, *hc = Jc + (size_t) K * n, *h0 = hc + K, *S = h0 + K;
+         double *slots = ws + 3 * DIM(a, nsa) * Pp;
+         block_band_solve(a, Gs, Pp, m, n);
+         __syncthreads();
+         const double *AGc = Gs;
+         if (DIM(a, use_momentum))
+         {
+            const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
+            for (int t = tid + 1; t <= m; t += NT)
+               for (int j = 0; j < n; j++) AGs[j * Pp + t] = fma(coef, Gs[j * Pp + t], AGs[j * Pp + t]);
+            leapfrog_first = 0;
+            AGc = AGs;
+         }
+         for (int t = tid + 1; t <= m; t += NT)
+            if (a.con_row0[t] > a.con_row0[t - 1])
+               con_eval_waypoint<FLOAT>(a, Ts, slots, AGc, Pp, t, m, n, inv_lambda, Jc, hc);
+         __syncthreads();
+         con_build_system(a, Jc, S, m, n);
+         for (int e = tid; e < K; e += NT) h0[e] = hc[e];
+         __syncthreads();
+         if (con_solve(S, hc, K, red, ired))
+         {
+            /* zero pivot: dgesv leaves the right-hand side as it was and the reference carries on with it */
+            __syncthreads();
+            for (int e = tid; e < K; e += NT) hc[e] = h0[e];
+            if (tid == 0) a.con_singular[run]++;
+            __syncthreads();
+         }
+         for (int t = tid + 1; t <= m; t += NT)
+         {
+            const int r0 = a.con_row0[t - 1], r1 = a.con_row0[t];
+            for (int j = 0; j < n; j++)
+            {
+               Ts[j * Pp + t] = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]);
+               double d = 0.0;
+               for (int r = r0; r < r1; r++) d += Jc[(size_t) r * n + j] * hc[r];
+               Gs[j * Pp + t] = d;
+            }
+         }
+         __syncthreads();
+         block_band_solve(a, Gs, Pp, m, n);
+         __syncthreads();
+         for (int t = tid + 1; t <= m; t += NT)
+            for (int j = 0; j < n; j++)
+            {
+               const double q = Ts[j * Pp + t] - Gs[j * Pp + t];
+               Ts[j * Pp + t] = q;
+               violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
+            }
+      }
+      else
+#endif
       {
          const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
          auto update = [&](const int j, const int t, double step)
@@ -672,11 +735,11 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 }
 
 #ifndef OCB_JIT
-template <int NT_MAX, bool FLOAT, int PP, int NN>
+template <int NT_MAX, bool FLOAT, int PP, int NN, bool CONS = false>
 __global__ void __launch_bounds__(NT_MAX, (NT_MAX == 128 && !FLOAT) ? 3 : 1)
 chomp_iterate_kernel(const __grid_constant__ OcbChompArgs a)
 {
-   chomp_iterate_body<FLOAT, PP, NN>(a);
+   chomp_iterate_body<FLOAT, PP, NN, CONS>(a);
 }
 #endif
 
@@ -772,19 +835,27 @@ extern "C" size_t ocb_chomp_smem_bytes(const OcbChompArgs *a)
    return (size_t) smem_layout(*a, a->Ppad, a->n).bytes;
 }
 
-template <int NT_MAX, bool FLOAT, int PP, int NN>
+template <int NT_MAX, bool FLOAT, int PP, int NN, bool CONS = false>
 static cudaError_t launch_variant(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    static OcbSmemOptIn optin; /* one per instantiation, keyed by device inside */
-   cudaError_t e = optin.ensure(chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN>, smem_bytes);
+   cudaError_t e = optin.ensure(chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN, CONS>, smem_bytes);
    if (e != cudaSuccess) return e;
-   chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN><<<args->R, threads, smem_bytes, st>>>(*args);
+   chomp_iterate_kernel<NT_MAX, FLOAT, PP, NN, CONS><<<args->R, threads, smem_bytes, st>>>(*args);
    return cudaGetLastError();
 }
 
 extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    if (threads > 256 || threads % 32) return cudaErrorInvalidValue;
+   if (args->con_K > 0) /* hard constraints: the generic instantiations only */
+   {
+      if (args->floating)
+         return threads <= 128 ? launch_variant<128, true, 0, 0, true>(args, smem_bytes, threads, st)
+                               : launch_variant<256, true, 0, 0, true>(args, smem_bytes, threads, st);
+      return threads <= 128 ? launch_variant<128, false, 0, 0, true>(args, smem_bytes, threads, st)
+                            : launch_variant<256, false, 0, 0, true>(args, smem_bytes, threads, st);
+   }
    if (args->floating)
       return threads <= 128 ? launch_variant<128, true, 0, 0>(args, smem_bytes, threads, st)
                             : launch_variant<256, true, 0, 0>(args, smem_bytes, threads, st);

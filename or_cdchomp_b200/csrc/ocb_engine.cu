@@ -68,6 +68,8 @@ extern "C" void ocb_params_default(ocb_params *p)
    p->obs_factor = 200.0;
    p->obs_factor_self = 10.0;
    p->floating_base = 0;
+   p->n_constraints = 0;
+   p->constraints = nullptr;
 }
 
 /* ------------------------------------------------------------ small algebra */
@@ -973,6 +975,10 @@ struct CompiledRobot
    std::vector<double> inactive_radius;
    std::vector<int> inactive_link;
    int n_slots = 0;
+   /* where every robot link sits: its joint frame (index in `joints`, -1: not moved by an active dof) and
+    * the link frame in that joint frame (or in the world); the joint above each joint (-1: none) */
+   std::vector<int> link_joint, joint_parent;
+   std::vector<Xf> link_rel;
 };
 
 /* Fold fixed / frozen links into joint frames with the moving axis on local z.
@@ -1082,6 +1088,13 @@ int compile_robot(const ocb_robot *rb, double eps_self, bool floating, CompiledR
          D.load = slot_of[par];
       }
    }
+   C.link_joint.assign(nl, -1);
+   C.link_rel = rel;
+   for (int i = 0; i < nl; i++)
+      if (anchor[i] >= 0) C.link_joint[i] = newidx[anchor[i]];
+   C.joint_parent.assign(nj, -1);
+   for (int k = 0; k < nj; k++)
+      if (raw[order[k]].parent >= 0) C.joint_parent[k] = newidx[raw[order[k]].parent];
    /* spheres: active ones grouped by joint (stable), inactive ones frozen in the world */
    struct Tmp { int joint; OcbSphereDev s; };
    std::vector<Tmp> act;
@@ -1335,6 +1348,79 @@ std::string jit_robot_header(const CompiledRobot &C, double eps_self)
    return h;
 }
 
+/* dense inverse of the metric from its banded factor, column by column (stands in for dgetri,
+ * chomp.c:393-403; read by the constraint system only) */
+void metric_inverse(const Metric &M, std::vector<double> &Ainv)
+{
+   const int m = M.m, bw = M.bw;
+   Ainv.assign((size_t) m * m, 0.0);
+   std::vector<double> x(m);
+   for (int c = 0; c < m; c++)
+   {
+      for (int i = 0; i < m; i++) x[i] = (i == c) ? 1.0 : 0.0;
+      for (int i = 0; i < m; i++)
+      {
+         double acc = x[i];
+         for (int k = 1; k <= bw && k <= i; k++) acc -= M.Lband[(size_t) i * bw + (k - 1)] * x[i - k];
+         x[i] = acc;
+      }
+      for (int i = m - 1; i >= 0; i--)
+      {
+         double acc = x[i] * M.dinv[i];
+         for (int k = 1; k <= bw && i + k < m; k++) acc -= M.Lband[(size_t) (i + k) * bw + (k - 1)] * x[i + k];
+         x[i] = acc;
+      }
+      for (int i = 0; i < m; i++) Ainv[(size_t) i * m + c] = x[i];
+   }
+}
+
+Xf xf_invert(const Xf &a)
+{
+   Xf c = xf_transpose_rot(a);
+   for (int r = 0; r < 3; r++) c.t[r] = -(c.R[3 * r] * a.t[0] + c.R[3 * r + 1] * a.t[1] + c.R[3 * r + 2] * a.t[2]);
+   return c;
+}
+
+/* the `create` command's constraints (mod.cpp:2466-2519 enabled masks, 2571-2613 registration) for the
+ * kernel: frames folded onto joint frames, rows stacked waypoint by waypoint */
+int compile_constraints(const ocb_params *params, const ocb_robot *rb, const CompiledRobot &C, int m,
+                        std::vector<OcbConDev> &cons, std::vector<int> &row0, std::vector<int> &row_wp)
+{
+   cons.clear();
+   for (int ci = 0; ci < params->n_constraints; ci++)
+   {
+      const ocb_constraint &s = params->constraints[ci];
+      if (s.link < 0 || s.link >= rb->n_links) return fail(OCB_ERR_ARG, "constraint %d: bad link", ci);
+      if (s.where != OCB_CON_START && s.where != OCB_CON_END && s.where != OCB_CON_ALL)
+         return fail(OCB_ERR_ARG, "constraint %d: where must be OCB_CON_START, OCB_CON_END or OCB_CON_ALL", ci);
+      OcbConDev d;
+      memset(&d, 0, sizeof(d));
+      const Xf A = xf_invert(xf_from_pose(s.T0w));
+      const Xf Cx = xf_mul(xf_mul(C.link_rel[s.link], xf_from_pose(s.pose_link_ee)), xf_invert(xf_from_pose(s.Twe)));
+      memcpy(d.AR, A.R, sizeof(d.AR)); memcpy(d.At, A.t, sizeof(d.At));
+      memcpy(d.CR, Cx.R, sizeof(d.CR)); memcpy(d.Ct, Cx.t, sizeof(d.Ct));
+      d.joint = C.link_joint[s.link];
+      d.anc = 0;
+      for (int j = d.joint; j >= 0; j = C.joint_parent[j]) d.anc |= 1ull << j;
+      d.where = s.where;
+      d.k = 0;
+      for (int i = 0; i < 6; i++)
+         if (s.Bw[i][0] == 0.0 && s.Bw[i][1] == 0.0) d.rows[d.k++] = (i < 3) ? i : 8 - i; /* mod.cpp:1413 */
+      if (d.k > 0) cons.push_back(d); /* a constraint without rows adds nothing to the system */
+   }
+   row0.assign(m + 1, 0);
+   row_wp.clear();
+   for (int i = 0; i < m; i++)
+   {
+      row0[i] = (int) row_wp.size();
+      for (const OcbConDev &d : cons)
+         if (d.where == OCB_CON_ALL || (d.where == OCB_CON_START && i == 0) || (d.where == OCB_CON_END && i == m - 1))
+            for (int r = 0; r < d.k; r++) row_wp.push_back(i);
+   }
+   row0[m] = (int) row_wp.size();
+   return OCB_OK;
+}
+
 void seed_mt(uint32_t *mt, unsigned int seed)
 {
    /* gsl_rng_set on mt19937: seed 0 -> 4357, 2002 initialisation */
@@ -1499,6 +1585,35 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       TRY(batch_upload(b, &a.lim_hi, hi));
    }
    const size_t R = (size_t) n_runs;
+   if (params->n_constraints > 0)
+   {
+      if (!params->constraints) { ocb_batch_destroy(b); return fail(OCB_ERR_ARG, "constraints is null"); }
+      std::vector<OcbConDev> cons;
+      std::vector<int> row0, row_wp;
+      TRY(compile_constraints(params, robot, C, m, cons, row0, row_wp));
+      a.n_con = (int) cons.size();
+      a.con_K = (int) row_wp.size();
+      if (a.con_K > 0)
+      {
+         a.con_stride = (size_t) a.con_K * (n + 2) + (size_t) a.con_K * a.con_K;
+         if (R * a.con_stride * sizeof(double) > ((size_t) 48 << 30))
+         {
+            ocb_batch_destroy(b);
+            return fail(OCB_ERR_ARG, "constraint systems of %d rows for %d runs need %.1f GB of scratch", a.con_K, n_runs,
+                        R * a.con_stride * 8.0 / 1e9);
+         }
+         std::vector<double> Ainv;
+         metric_inverse(M, Ainv);
+         TRY(batch_upload(b, &a.cons, cons));
+         TRY(batch_upload(b, &a.con_row0, row0));
+         TRY(batch_upload(b, &a.con_row_wp, row_wp));
+         TRY(batch_upload(b, &a.Ainv, Ainv));
+         TRY(batch_alloc(b, &a.con_scratch, R * a.con_stride));
+         TRY(batch_alloc(b, &a.con_singular, R));
+         cudaError_t ce = cudaMemsetAsync(a.con_singular, 0, R * sizeof(int), e->stream);
+         if (ce != cudaSuccess) { ocb_batch_destroy(b); return fail(OCB_ERR_CUDA, "batch_create: %s", cudaGetErrorString(ce)); }
+      }
+   }
    TRY(batch_alloc(b, &a.traj, R * P * n));
    TRY(batch_alloc(b, &a.costs, R * 3));
    TRY(batch_alloc(b, &a.status, R));
@@ -1545,6 +1660,12 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
     * one SM's shared memory the iteration is tiled over waypoints (chomp_tiled.cu). */
    a.ws_stride = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
    b->smem = ocb_chomp_smem_bytes(&a);
+   if (b->smem > (size_t) e->smem_optin && a.con_K > 0)
+   {
+      ocb_batch_destroy(b);
+      return fail(OCB_ERR_ARG, "hard constraints need the run in one SM's shared memory (%d spheres, %d waypoints, %d dofs)",
+                  a.nsa, P, n);
+   }
    if (b->smem > (size_t) e->smem_optin)
    {
       a.tiled = 1;
@@ -1566,7 +1687,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       TRY(batch_alloc(b, &a.tile_cost, R * a.n_tiles));
    }
    b->threads = std::min(256, ((P + 31) / 32) * 32);
-   if (e->jit && !a.tiled)
+   if (e->jit && !a.tiled && a.con_K == 0) /* constraints: the library's kernel */
    {
       /* blocks per SM the shared memory allows, not more than ~160 registers per thread can feed */
       int min_blocks = (int) ((size_t) e->smem_per_sm / (b->smem + 1024));

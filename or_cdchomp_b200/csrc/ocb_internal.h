@@ -63,6 +63,20 @@ struct OcbSdfDev
    double edge_hi[3], near[3], near_hi[3];
 };
 
+/* One hard constraint (ocb_constraint) compiled for the kernel: the frame it holds is joint frame
+ * `joint` times C (link offset, tool transform and inv(Twe) folded together), seen through A = inv(T0w). */
+struct OcbConDev
+{
+   double AR[9], At[3];
+   double CR[9], Ct[3];
+   unsigned long long anc; /* bit j: joint j moves the frame */
+   int joint;              /* -1: the frame is fixed in the world (C is then its world pose times inv(Twe)) */
+   int where;              /* OCB_CON_* */
+   int k;                  /* rows */
+   int rows[6];            /* entry of [x y z yaw pitch roll] behind each row */
+   int pad;
+};
+
 struct OcbChompArgs
 {
    /* sizes */
@@ -129,6 +143,15 @@ struct OcbChompArgs
    /* the first fields' descriptors by value: kernel parameters live in the constant bank, so a kernel
     * compiled for <= OCB_INLINE_SDFS fields reads them as instruction operands (no loads, no registers) */
    OcbSdfDev sdf_inline[OCB_INLINE_SDFS];
+   /* hard constraints (chomp.c:553-600): con_K stacked rows, waypoint-major; library kernel only */
+   int n_con, con_K;
+   const OcbConDev *cons;     /* [n_con] */
+   const int *con_row0;       /* [m + 1]: first row of each moving waypoint */
+   const int *con_row_wp;     /* [con_K]: moving waypoint (0-based) of each row */
+   const double *Ainv;        /* [m][m] dense inverse of the metric (only the entries between constrained waypoints are read) */
+   double *con_scratch;       /* [R][con_stride]: J (con_K x n), h, saved h, S (con_K x con_K) */
+   size_t con_stride;
+   int *con_singular;         /* [R] iterations whose constraint system had a zero pivot (the reference prints and goes on) */
 };
 
 #if !defined(__CUDACC_RTC__) && defined(__cplusplus)

@@ -24,6 +24,7 @@
 #include <libcd/chomp.h>
 #include <libcd/kin.h>
 #include <libcd/mat.h>
+#include <libcd/spatial.h>
 #else
 
 struct cd_grid
@@ -51,7 +52,18 @@ int cd_grid_double_bin_sdf(struct cd_grid **gp_dt, struct cd_grid *g_emp);
 int cd_grid_flood_fill(struct cd_grid *g, size_t index_start, int *wrap_dim,
                        int (*replace)(void *, void *), void *rptr);
 
-struct cd_chomp_con;
+/* chomp.h:118-129 */
+struct cd_chomp;
+struct cd_chomp_con
+{
+   struct cd_chomp_con *next;
+   int k;
+   int i;
+   void *cptr;
+   int (*con_eval)(void *cptr, struct cd_chomp *c, int i, double *point, double *con_val, double *con_jacobian);
+   double *h;
+   double *J;
+};
 struct cd_chomp
 {
    int n;
@@ -106,6 +118,8 @@ struct cd_chomp
 
 int cd_chomp_create(struct cd_chomp **cp, int m, int n, int D, double *T, int ldt);
 void cd_chomp_free(struct cd_chomp *c);
+int cd_chomp_add_constraint(struct cd_chomp *c, int k, int i, void *cptr,
+   int (*con_eval)(void *cptr, struct cd_chomp *c, int i, double *point, double *con_val, double *con_jacobian));
 int cd_chomp_init(struct cd_chomp *c);
 int cd_chomp_iterate(struct cd_chomp *c, int do_iteration, double *costp_total,
                      double *costp_obs, double *costp_smooth);
@@ -116,6 +130,12 @@ int cd_kin_pose_compose(const double pose_ab[7], const double pose_bc[7], double
 int cd_kin_pose_compos(const double pose_ab[7], const double pos_bc[3], double pos_ac[3]);
 int cd_kin_pose_compose_vec(const double pose_ab[7], const double vec_bc[3], double vec_ac[3]);
 int cd_kin_pose_invert(const double pose_in[7], double pose_out[7]);
+int cd_kin_quat_to_R(const double quat[4], double R[3][3]);
+int cd_kin_pose_to_xyzypr(const double pose[7], double xyzypr[6]);
+int cd_kin_pose_to_xyzypr_J(const double pose[7], double J[6][7]);
+int cd_spatial_xm_from_pose(double xm[6][6], double pose[7]);
+int cd_spatial_pose_jac(double pose[7], double jac[6][7]);
+int cd_spatial_pose_jac_inverse(double pose[7], double jac_inverse[7][6]);
 
 #endif /* ORACLE_REF_HEADERS */
 #endif

@@ -14,7 +14,6 @@
  * Differences that are deliberate and documented:
  *   - BLAS/LAPACK calls are replaced by the straightforward triple loops /
  *     Gauss-Jordan inverse below (the reference links an unpinned system BLAS).
- *   - hard constraints (chomp.c:553-600) are not restated (out of scope, TSR).
  *
  * Each function cites the reference lines it follows (paths relative to the
  * reference root).
@@ -577,12 +576,152 @@ int cd_kin_pose_invert(const double pose_in[7], double pose_out[7])
    return 0;
 }
 
+/* kin.c:347-370: rotation matrix of a quaternion [x y z w], the 1 - 2(..) form */
+int cd_kin_quat_to_R(const double quat[4], double R[3][3])
+{
+   double x = quat[0], y = quat[1], z = quat[2], w = quat[3];
+   double xx = x * x, xy = x * y, xz = x * z, xw = x * w;
+   double yy = y * y, yz = y * z, yw = y * w, zz = z * z, zw = z * w;
+   R[0][0] = 1 - 2 * (yy + zz); R[0][1] = 2 * (xy - zw);     R[0][2] = 2 * (xz + yw);
+   R[1][0] = 2 * (xy + zw);     R[1][1] = 1 - 2 * (xx + zz); R[1][2] = 2 * (yz - xw);
+   R[2][0] = 2 * (xz - yw);     R[2][1] = 2 * (yz + xw);     R[2][2] = 1 - 2 * (xx + yy);
+   return 0;
+}
+
+/* kin.c:615-647: [x y z yaw pitch roll] of a pose; near the poles (|sin pitch| > 0.99998) the yaw
+ * carries the whole in-plane rotation and the roll is zero */
+int cd_kin_pose_to_xyzypr(const double pose[7], double xyzypr[6])
+{
+   const double quarter_turn = 0.25 * 6.2831853071795864769252867665590057683943387987502116;
+   double qx = pose[3], qy = pose[4], qz = pose[5], qw = pose[6];
+   double half_sinp = qw * qy - qz * qx;
+   xyzypr[0] = pose[0];
+   xyzypr[1] = pose[1];
+   xyzypr[2] = pose[2];
+   if (half_sinp > 0.49999)
+   {
+      xyzypr[3] = -2.0 * atan2(qx, qw);
+      xyzypr[4] = quarter_turn;
+      xyzypr[5] = 0.0;
+   }
+   else if (half_sinp < -0.49999)
+   {
+      xyzypr[3] = 2.0 * atan2(qx, qw);
+      xyzypr[4] = -quarter_turn;
+      xyzypr[5] = 0.0;
+   }
+   else
+   {
+      xyzypr[3] = atan2(2.0 * (qw * qz + qx * qy), 1.0 - 2.0 * (qy * qy + qz * qz));
+      xyzypr[4] = asin(2.0 * half_sinp);
+      xyzypr[5] = atan2(2.0 * (qw * qx + qy * qz), 1.0 - 2.0 * (qx * qx + qy * qy));
+   }
+   return 0;
+}
+
+/* kin.c:680-718: derivative of that vector with respect to the seven pose entries (the general
+ * branch only: the reference does not treat the poles) */
+int cd_kin_pose_to_xyzypr_J(const double pose[7], double J[6][7])
+{
+   double qx = pose[3], qy = pose[4], qz = pose[5], qw = pose[6];
+   double nu, de, as, s;
+   int i, j;
+   for (i = 0; i < 6; i++) for (j = 0; j < 7; j++) J[i][j] = 0.0;
+   J[0][0] = J[1][1] = J[2][2] = 1.0;
+   /* yaw = atan2(nu, de): d = (de dnu - nu dde) / (de^2 + nu^2) */
+   nu = 2.0 * (qw * qz + qx * qy);
+   de = 1.0 - 2.0 * (qy * qy + qz * qz);
+   J[3][3] = de / (de * de + nu * nu) * (2.0 * qy);
+   J[3][4] = de / (de * de + nu * nu) * (2.0 * qx) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qy);
+   J[3][5] = de / (de * de + nu * nu) * (2.0 * qw) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qz);
+   J[3][6] = de / (de * de + nu * nu) * (2.0 * qz);
+   /* pitch = asin(as) */
+   as = 2.0 * (qw * qy - qz * qx);
+   s = 1.0 / sqrt(1.0 - as * as);
+   J[4][3] = s * 2.0 * (-qz);
+   J[4][4] = s * 2.0 * (qw);
+   J[4][5] = s * 2.0 * (-qx);
+   J[4][6] = s * 2.0 * (qy);
+   /* roll = atan2(nu, de) */
+   nu = 2.0 * (qw * qx + qy * qz);
+   de = 1.0 - 2.0 * (qx * qx + qy * qy);
+   J[5][3] = de / (de * de + nu * nu) * (2.0 * qw) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qx);
+   J[5][4] = de / (de * de + nu * nu) * (2.0 * qz) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qy);
+   J[5][5] = de / (de * de + nu * nu) * (2.0 * qy);
+   J[5][6] = de / (de * de + nu * nu) * (2.0 * qx);
+   return 0;
+}
+
+/* spatial.c:71-102: 6 x 6 motion transform [R 0; [t]x R  R] of a pose (angular rows first) */
+int cd_spatial_xm_from_pose(double xm[6][6], double pose[7])
+{
+   double R[3][3], tx[3][3];
+   int i, j, k;
+   for (i = 0; i < 6; i++) for (j = 0; j < 6; j++) xm[i][j] = 0.0;
+   cd_kin_quat_to_R(pose + 3, R);
+   for (i = 0; i < 3; i++)
+      for (j = 0; j < 3; j++) xm[i][j] = xm[3 + i][3 + j] = R[i][j];
+   tx[0][0] = 0.0;      tx[0][1] = -pose[2]; tx[0][2] = pose[1];
+   tx[1][0] = pose[2];  tx[1][1] = 0.0;      tx[1][2] = -pose[0];
+   tx[2][0] = -pose[1]; tx[2][1] = pose[0];  tx[2][2] = 0.0;
+   for (i = 0; i < 3; i++)
+      for (j = 0; j < 3; j++)
+      {
+         double acc = 0.0;
+         for (k = 0; k < 3; k++) acc += tx[i][k] * R[k][j];
+         xm[3 + i][j] = acc;
+      }
+   return 0;
+}
+
+/* spatial.c:295-337: pose rates -> spatial velocity [omega; v of the point at the origin] */
+int cd_spatial_pose_jac(double pose[7], double jac[6][7])
+{
+   double x = pose[0], y = pose[1], z = pose[2];
+   double ax = 2.0 * pose[3], ay = 2.0 * pose[4], az = 2.0 * pose[5], aw = 2.0 * pose[6];
+   int i, j;
+   for (i = 0; i < 6; i++) for (j = 0; j < 7; j++) jac[i][j] = 0.0;
+   jac[3][0] = jac[4][1] = jac[5][2] = 1.0;
+   jac[0][3] = aw;  jac[0][4] = -az; jac[0][5] = ay;  jac[0][6] = -ax;
+   jac[1][3] = az;  jac[1][4] = aw;  jac[1][5] = -ax; jac[1][6] = -ay;
+   jac[2][3] = -ay; jac[2][4] = ax;  jac[2][5] = aw;  jac[2][6] = -az;
+   jac[3][3] = -z * az - y * ay; jac[3][4] = -z * aw + y * ax; jac[3][5] = z * ax + y * aw;  jac[3][6] = z * ay - y * az;
+   jac[4][3] = z * aw + x * ay;  jac[4][4] = -z * az - x * ax; jac[4][5] = z * ay - x * aw;  jac[4][6] = -z * ax + x * az;
+   jac[5][3] = -y * aw + x * az; jac[5][4] = y * az + x * aw;  jac[5][5] = -y * ay - x * ax; jac[5][6] = y * ax - x * ay;
+   return 0;
+}
+
+/* spatial.c:339-375: spatial velocity -> pose rates: p' = v + omega x p, q' = 1/2 omega (x) q */
+int cd_spatial_pose_jac_inverse(double pose[7], double ji[7][6])
+{
+   double x = pose[0], y = pose[1], z = pose[2];
+   double hx = 0.5 * pose[3], hy = 0.5 * pose[4], hz = 0.5 * pose[5], hw = 0.5 * pose[6];
+   int i, j;
+   for (i = 0; i < 7; i++) for (j = 0; j < 6; j++) ji[i][j] = 0.0;
+   ji[0][1] = z;  ji[0][2] = -y;
+   ji[1][0] = -z; ji[1][2] = x;
+   ji[2][0] = y;  ji[2][1] = -x;
+   ji[0][3] = ji[1][4] = ji[2][5] = 1.0;
+   ji[3][0] = hw;  ji[3][1] = hz;  ji[3][2] = -hy;
+   ji[4][0] = -hz; ji[4][1] = hw;  ji[4][2] = hx;
+   ji[5][0] = hy;  ji[5][1] = -hx; ji[5][2] = hw;
+   ji[6][0] = -hx; ji[6][1] = -hy; ji[6][2] = -hz;
+   return 0;
+}
+
 /* ==================================================================== chomp */
 
 /* chomp.c:180-217 */
 void cd_chomp_free(struct cd_chomp *c)
 {
    if (!c) return;
+   free(c->cons_h); free(c->cons_Jcol); free(c->cons_JAJT); free(c->cons_ipiv); free(c->cons_delta);
+   while (c->cons)
+   {
+      struct cd_chomp_con *con = c->cons;
+      c->cons = con->next;
+      free(con);
+   }
    free(c->wds); free(c->initsfinals); free(c->inits); free(c->finals);
    free(c->A); free(c->Ainv); free(c->B);
    free(c->jlimit_lower); free(c->jlimit_upper);
@@ -737,10 +876,11 @@ done:
 }
 
 /* chomp.c:342-428: velocity operator (central differences, one-sided at a free
- * boundary), default metric, explicit inverse of A.  Constraints not restated. */
+ * boundary), default metric, explicit inverse of A, constraint buffers. */
 int cd_chomp_init(struct cd_chomp *c)
 {
    int m = c->m, n = c->n, i, j;
+   struct cd_chomp_con *con;
    zero_fill(c->Kvels, (size_t) m * m);
    zero_fill(c->Evels, (size_t) m * n);
    for (i = 0; i < m; i++)
@@ -780,11 +920,82 @@ int cd_chomp_init(struct cd_chomp *c)
    if (add_default_metric(c)) return -1;
    memcpy(c->Ainv, c->A, (size_t) m * m * sizeof(double));
    if (invert_rm(c->Ainv, m)) return -2;
+   /* chomp.c:405-426: one stacked h and J for the whole constraint list, in list order */
    c->cons_k = 0;
+   for (con = c->cons; con; con = con->next) c->cons_k += con->k;
+   if (c->cons_k)
+   {
+      int K = c->cons_k;
+      c->cons_h = (double *) malloc(K * sizeof(double));
+      c->cons_Jcol = (double *) malloc((size_t) K * n * sizeof(double));
+      c->cons_JAJT = (double *) malloc((size_t) K * K * sizeof(double));
+      c->cons_ipiv = (int *) malloc(K * sizeof(int));
+      c->cons_delta = (double *) malloc(n * sizeof(double));
+      if (!c->cons_h || !c->cons_Jcol || !c->cons_JAJT || !c->cons_ipiv || !c->cons_delta) return -1;
+      K = 0;
+      for (con = c->cons; con; con = con->next)
+      {
+         con->h = c->cons_h + K;
+         con->J = c->cons_Jcol + (size_t) K * n;
+         K += con->k;
+      }
+   }
    return 0;
 }
 
-/* chomp.c:430-683 without the hard-constraint block (553-600).
+/* chomp.c:219-236: new constraints go to the front of the list */
+int cd_chomp_add_constraint(struct cd_chomp *c, int k, int i, void *cptr,
+   int (*con_eval)(void *cptr, struct cd_chomp *c, int i, double *point, double *con_val, double *con_jacobian))
+{
+   struct cd_chomp_con *con = (struct cd_chomp_con *) malloc(sizeof(struct cd_chomp_con));
+   if (!con) return -1;
+   con->k = k;
+   con->i = i;
+   con->cptr = cptr;
+   con->con_eval = con_eval;
+   con->h = 0;
+   con->J = 0;
+   con->next = c->cons;
+   c->cons = con;
+   return 0;
+}
+
+/* stands in for LAPACKE_dgesv with one right-hand side (chomp.c:579-581): LU with partial
+ * pivoting on rows, then the two triangular solves; a (K x K, row-major) is overwritten */
+static int solve_rm(double *a, int K, double *b)
+{
+   int i, j, k;
+   for (k = 0; k < K; k++)
+   {
+      int piv = k;
+      double best = fabs(a[k * K + k]);
+      for (i = k + 1; i < K; i++)
+         if (fabs(a[i * K + k]) > best) { best = fabs(a[i * K + k]); piv = i; }
+      if (best == 0.0) return k + 1;
+      if (piv != k)
+      {
+         double t;
+         for (j = 0; j < K; j++) { t = a[k * K + j]; a[k * K + j] = a[piv * K + j]; a[piv * K + j] = t; }
+         t = b[k]; b[k] = b[piv]; b[piv] = t;
+      }
+      for (i = k + 1; i < K; i++)
+      {
+         double f = a[i * K + k] / a[k * K + k];
+         if (f == 0.0) continue;
+         for (j = k + 1; j < K; j++) a[i * K + j] -= f * a[k * K + j];
+         b[i] -= f * b[k];
+      }
+   }
+   for (k = K - 1; k >= 0; k--)
+   {
+      double acc = b[k];
+      for (j = k + 1; j < K; j++) acc -= a[k * K + j] * b[j];
+      b[k] = acc / a[k * K + k];
+   }
+   return 0;
+}
+
+/* chomp.c:430-683.
  *   vels = Kvels T + Evels (449-451; unused by the sphere cost)
  *   cost_pre, then per moving waypoint cost(); cost_obs = sum/m; G /= m (463-492)
  *   G += A T + B (515-522); AG = Ainv G, or the leapfrog momentum form (525-548)
@@ -833,6 +1044,49 @@ int cd_chomp_iterate(struct cd_chomp *c, int do_iteration, double *costp_total,
       }
       else
          gemm_rm(0, 0, m, n, m, 1.0 / c->lambda, c->Ainv, m, c->G, n, 1.0, c->AG, n);
+
+      /* hard constraints (chomp.c:553-600): with h the constraint values at T, J their Jacobians and
+       * S = J Ainv J^T, solve S x = h - J AG / lambda and move T by -Ainv J^T x, so that the
+       * linearised constraints vanish after the update below */
+      if (c->cons_k)
+      {
+         struct cd_chomp_con *c1, *c2;
+         int K = c->cons_k, r, q;
+         for (c1 = c->cons; c1; c1 = c1->next)
+            c1->con_eval(c1->cptr, c, c1->i, c->T_points[c1->i], c1->h, c1->J);
+         for (c1 = c->cons; c1; c1 = c1->next)
+            for (r = 0; r < c1->k; r++)
+            {
+               double acc = 0.0;
+               for (j = 0; j < n; j++) acc += c1->J[r * n + j] * c->AG_points[c1->i][j];
+               c1->h[r] += (-1.0 / c->lambda) * acc;
+            }
+         for (c1 = c->cons; c1; c1 = c1->next)
+            for (c2 = c->cons; c2; c2 = c2->next)
+            {
+               double ainv = c->Ainv[c1->i * m + c2->i];
+               double *blk = &c->cons_JAJT[(c1->h - c->cons_h) * K + (c2->h - c->cons_h)];
+               for (r = 0; r < c1->k; r++)
+                  for (q = 0; q < c2->k; q++)
+                  {
+                     double acc = 0.0;
+                     for (j = 0; j < n; j++) acc += c1->J[r * n + j] * c2->J[q * n + j];
+                     blk[r * K + q] = ainv * acc;
+                  }
+            }
+         if (solve_rm(c->cons_JAJT, K, c->cons_h)) printf("constraint inversion error!\n");
+         for (c1 = c->cons; c1; c1 = c1->next)
+         {
+            for (j = 0; j < n; j++)
+            {
+               double acc = 0.0;
+               for (r = 0; r < c1->k; r++) acc += c1->J[r * n + j] * c1->h[r];
+               c->cons_delta[j] = acc;
+            }
+            for (i = 0; i < m; i++)
+               for (j = 0; j < n; j++) c->T[i * c->ldt + j] -= c->Ainv[i * m + c1->i] * c->cons_delta[j];
+         }
+      }
 
       for (i = 0; i < m; i++)
          for (j = 0; j < n; j++) c->T[i * c->ldt + j] += (-1.0 / c->lambda) * c->AG[i * n + j];

@@ -132,6 +132,18 @@ struct orc_run
    struct cd_chomp *c;
    int iter;
    int floating; /* floating_base: rows are [x y z qx qy qz qw, adofs] (mod.cpp:991-1021) */
+   int n_cons;
+   struct orc_con *cons; /* struct run_contsr / start_tsr / everyn_tsr (mod.cpp:873-884, 926-940) */
+};
+
+/* one TSR constraint bound to a run: the frame, the two fixed TSR poses, which of
+ * [x y z roll pitch yaw] are held at zero, and how many (k) */
+struct orc_con
+{
+   struct orc_run *r;
+   struct ocb_constraint spec;
+   int enabled[6];
+   int k;
 };
 
 /* ------------------------------------------------- kinematics (OpenRAVE side) */
@@ -265,6 +277,111 @@ static int link_is_active(const struct ocb_robot *rb, int link)
    for (a = link; a > 0; a = rb->parent[a])
       if (rb->dof_index[a] >= 0 && rb->joint_type[a] != OCB_JOINT_FIXED) return 1;
    return 0;
+}
+
+/* 3 x n angular-velocity Jacobian of `link`; stands in for
+ * robot->CalculateAngularVelocityJacobian(linkindex, J) with the active columns picked
+ * (mod.cpp:1456-1459): revolute column = world axis, prismatic column = 0 */
+static void orc_angular_jacobian(const struct ocb_robot *rb, const double *link_poses, int link, double *J)
+{
+   int n = rb->n_dof, a, k;
+   for (k = 0; k < 3 * n; k++) J[k] = 0.0;
+   for (a = link; a > 0; a = rb->parent[a])
+   {
+      double axw[3];
+      int dof = rb->dof_index[a];
+      if (dof < 0 || rb->joint_type[a] != OCB_JOINT_REVOLUTE) continue;
+      cd_kin_pose_compose_vec(&link_poses[7 * a], &rb->axis[3 * a], axw);
+      for (k = 0; k < 3; k++) J[k * n + dof] += rb->dof_coeff[2 * a] * axw[k];
+   }
+}
+
+/* con_tsr / con_everyn_tsr / con_start_tsr (mod.cpp:1330-1497, 1500-1657, 1659-1784; the three
+ * differ only in where the frame and the TSR come from).  Value: the pose of the constrained frame
+ * seen from the TSR, inv(T0w) * frame * inv(Twe), as [x y z yaw pitch roll], enabled entries in
+ * x y z roll pitch yaw order.  Jacobian: the frame's world spatial Jacobian [angular; linear at
+ * the world origin], moved to the TSR frame, turned into pose rates and then into xyzypr rates. */
+static int orc_con_tsr(void *cptr, struct cd_chomp *c, int ti, double *point, double *con_val, double *con_jacobian)
+{
+   struct orc_con *con = (struct orc_con *) cptr;
+   struct orc_run *r = con->r;
+   const struct ocb_robot *rb = r->robot;
+   double pose_ee[7], pose_ee_obj[7], pose_obj[7], pose_table_world[7], pose_table_obj[7], xyzypr[6];
+   int tsri, ki, i, j, l, n = c->n;
+   (void) ti;
+   if (r->floating)
+      orc_fk_base(rb, point, point + 7, r->link_poses);
+   else
+      orc_fk(rb, point, r->link_poses);
+   cd_kin_pose_compose(&r->link_poses[7 * con->spec.link], con->spec.pose_link_ee, pose_ee);
+   cd_kin_pose_invert(con->spec.Twe, pose_ee_obj);
+   cd_kin_pose_compose(pose_ee, pose_ee_obj, pose_obj);
+   cd_kin_pose_invert(con->spec.T0w, pose_table_world);
+   cd_kin_pose_compose(pose_table_world, pose_obj, pose_table_obj);
+   cd_kin_pose_to_xyzypr(pose_table_obj, xyzypr);
+   for (ki = 0, tsri = 0; tsri < 6; tsri++)
+      if (con->enabled[tsri]) con_val[ki++] = xyzypr[tsri < 3 ? tsri : 8 - tsri];
+   if (con_jacobian)
+   {
+      double *spajac = (double *) calloc((size_t) 6 * n, sizeof(double));
+      double *Jpart = (double *) malloc((size_t) 3 * (rb->n_dof ? rb->n_dof : 1) * sizeof(double));
+      double *full = (double *) malloc((size_t) 6 * n * sizeof(double));
+      double xm[6][6], ji[7][6], Jx[6][7], t1[6][6], t2[6][6];
+      const double origin[3] = {0.0, 0.0, 0.0};
+      int off = r->floating ? 7 : 0, na = rb->n_dof;
+      if (r->floating)
+      {
+         double Jsp[6][7];
+         cd_spatial_pose_jac(point, Jsp);
+         for (i = 0; i < 6; i++) for (j = 0; j < 7; j++) spajac[i * n + j] = Jsp[i][j];
+      }
+      orc_angular_jacobian(rb, r->link_poses, con->spec.link, Jpart);
+      for (i = 0; i < 3; i++) for (j = 0; j < na; j++) spajac[i * n + off + j] = Jpart[i * na + j];
+      orc_jacobian(rb, r->link_poses, con->spec.link, origin, Jpart);
+      for (i = 0; i < 3; i++) for (j = 0; j < na; j++) spajac[(3 + i) * n + off + j] = Jpart[i * na + j];
+      cd_spatial_xm_from_pose(xm, pose_table_world);
+      cd_spatial_pose_jac_inverse(pose_table_obj, ji);
+      cd_kin_pose_to_xyzypr_J(pose_table_obj, Jx);
+      for (i = 0; i < 6; i++)
+         for (j = 0; j < 6; j++)
+         {
+            double acc = 0.0;
+            for (l = 0; l < 7; l++) acc += Jx[i][l] * ji[l][j];
+            t1[i][j] = acc;
+         }
+      for (i = 0; i < 6; i++)
+         for (j = 0; j < 6; j++)
+         {
+            double acc = 0.0;
+            for (l = 0; l < 6; l++) acc += t1[i][l] * xm[l][j];
+            t2[i][j] = acc;
+         }
+      for (i = 0; i < 6; i++)
+         for (j = 0; j < n; j++)
+         {
+            double acc = 0.0;
+            for (l = 0; l < 6; l++) acc += t2[i][l] * spajac[l * n + j];
+            full[i * n + j] = acc;
+         }
+      for (ki = 0, tsri = 0; tsri < 6; tsri++)
+         if (con->enabled[tsri])
+         {
+            memcpy(con_jacobian + (size_t) ki * n, full + (size_t) (tsri < 3 ? tsri : 8 - tsri) * n, n * sizeof(double));
+            ki++;
+         }
+      free(spajac);
+      free(Jpart);
+      free(full);
+   }
+   return 0;
+}
+
+/* test hook: value and Jacobian of one constraint at configuration `point` */
+int orc_run_constraint_eval(struct orc_run *r, int index, double *point, double *con_val, double *con_jacobian)
+{
+   if (index < 0 || index >= r->n_cons) return -2;
+   orc_con_tsr(&r->cons[index], r->c, 0, point, con_val, con_jacobian);
+   return r->cons[index].k;
 }
 
 /* ------------------------------------------------ callbacks (mod.cpp:968-1327) */
@@ -499,6 +616,7 @@ void orc_run_destroy(struct orc_run *r)
    free(r->J2);
    free(r->Jadof);
    free(r->link_poses);
+   free(r->cons);
    free(r);
 }
 
@@ -601,6 +719,36 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
       /* mod.cpp:2639-2660: the pose entries are unbounded */
       c->jlimit_lower[j] = (fl && j < 7) ? -HUGE_VAL : rb->limit_lower[j - (fl ? 7 : 0)];
       c->jlimit_upper[j] = (fl && j < 7) ? HUGE_VAL : rb->limit_upper[j - (fl ? 7 : 0)];
+   }
+   /* constraints (mod.cpp:2466-2519 enabled masks, 2582-2613 registration: everyn_tsr and
+    * con_tsr 'all' on every moving point, 'start' on the first, 'end' on the last) */
+   if (pr->n_constraints > 0)
+   {
+      r->cons = (struct orc_con *) calloc(pr->n_constraints, sizeof(struct orc_con));
+      if (!r->cons) { orc_run_destroy(r); return -1; }
+      r->n_cons = pr->n_constraints;
+      for (i = 0; i < pr->n_constraints; i++)
+      {
+         struct orc_con *con = &r->cons[i];
+         con->r = r;
+         con->spec = pr->constraints[i];
+         con->k = 0;
+         for (j = 0; j < 6; j++)
+         {
+            con->enabled[j] = (con->spec.Bw[j][0] == 0.0 && con->spec.Bw[j][1] == 0.0);
+            con->k += con->enabled[j];
+         }
+         if (con->spec.link < 0 || con->spec.link >= rb->n_links) { orc_run_destroy(r); return -2; }
+         switch (con->spec.where)
+         {
+         case OCB_CON_START: cd_chomp_add_constraint(c, con->k, 0, con, orc_con_tsr); break;
+         case OCB_CON_END: cd_chomp_add_constraint(c, con->k, m - 1, con, orc_con_tsr); break;
+         case OCB_CON_ALL:
+            for (j = 0; j < m; j++) cd_chomp_add_constraint(c, con->k, j, con, orc_con_tsr);
+            break;
+         default: orc_run_destroy(r); return -2;
+         }
+      }
    }
    if (cd_chomp_init(c)) { orc_run_destroy(r); return -2; }
    *out = r;

@@ -69,6 +69,8 @@ def load(flavour="port"):
     lib.orc_run_obstacle_gradient.argtypes = [vp, c_double_p, c_double_p]
     lib.orc_run_sphere_positions.restype = C.c_int
     lib.orc_run_sphere_positions.argtypes = [vp, c_double_p, c_int_p]
+    lib.orc_run_constraint_eval.restype = C.c_int
+    lib.orc_run_constraint_eval.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p]
     lib.orc_run_destroy.restype = None
     lib.orc_run_destroy.argtypes = [vp]
     lib.orc_sdf_from_obsarray.restype = C.c_int
@@ -175,6 +177,17 @@ class Run:
         c = np.zeros(self.m)
         self.lib.orc_run_obstacle_gradient(self.h, dptr(g), dptr(c))
         return g, c
+
+    def constraint_eval(self, index, point):
+        """value (k) and Jacobian (k x n) of constraint `index` at configuration `point`
+        (con_tsr, src/orcdchomp_mod.cpp:1330-1497)"""
+        point = as_f64(point).copy()
+        val = np.zeros(6)
+        jac = np.zeros((6, self.n))
+        k = self.lib.orc_run_constraint_eval(self.h, int(index), dptr(point), dptr(val), dptr(jac))
+        if k < 0:
+            raise RuntimeError("orc_run_constraint_eval: %d" % k)
+        return val[:k].copy(), jac.reshape(-1)[:k * self.n].reshape(k, self.n).copy()
 
     def sphere_positions(self):
         na = self.robot.n_spheres_active

@@ -1,0 +1,151 @@
+"""GPU parity tests of the hard end-effector constraints (task space regions): `create ... con_tsr /
+everyn_tsr / start_tsr` (src/orcdchomp_mod.cpp:1330-1784, 1930-1996, 2466-2613) and the projection
+in cd_chomp_iterate (src/libcd/chomp.c:553-600), through the C ABI, against the CPU oracle -- which for
+this part is the reference's own chomp.c / kin.c / spatial.c when oracle/_ref is present."""
+import numpy as np
+import pytest
+
+from or_cdchomp_b200 import capi, models
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_ATOL = 1e-6
+COST_RTOL = 1e-8
+
+
+def upright_scene(oracle, robot, n_runs, seed=7):
+    """Start / goal pairs that differ mostly in the first (vertical) joint, and the TSR that describes
+    'keep the tool at the start height with its start roll and pitch': T0w at the start height, Twe the
+    tool's start orientation, so the constrained entries are zero at the start and stay close to zero
+    along the straight line."""
+    rng = np.random.default_rng(seed)
+    ee = robot.names.index("wam7")
+    base = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    starts = np.repeat(base[None], n_runs, 0)
+    goals = starts.copy()
+    goals[:, 0] += rng.uniform(0.6, 1.3, n_runs)
+    goals[:, 1:] += rng.uniform(-0.05, 0.05, (n_runs, 6))
+    pe = oracle.fk(robot, base)[ee]
+    T0w = models.pose_make((0, 0, pe[2]))
+    Twe = models.pose_make((0, 0, 0), pe[3:7])
+    return ee, starts, goals, T0w, Twe
+
+
+def run_oracle(oracle, flavour, robot, params, sd, starts, goals, n_iter, seeds=None):
+    out = []
+    for r in range(len(starts)):
+        run = oracle.Run(robot, params, [sd], starts[r], goals[r], seed=0 if seeds is None else int(seeds[r]),
+                         flavour=flavour)
+        ret, c, tr, _ = run.iterate(n_iter, want_trace=True)
+        out.append(dict(ret=ret, costs=c, trace=tr, traj=run.traj(), run=run))
+    return out
+
+
+def bounds(*held):
+    """Bw with the named rows (x y z roll pitch yaw) held at zero and the rest free"""
+    names = ["x", "y", "z", "roll", "pitch", "yaw"]
+    Bw = np.tile(np.array([-10.0, 10.0]), (6, 1))
+    for h in held:
+        Bw[names.index(h)] = 0.0
+    return Bw
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from or_cdchomp_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("where,held", [("all", ("z", "roll", "pitch")), ("all", ("roll", "pitch")),
+                                        ("start", ("z", "roll", "pitch")), ("end", ("x", "y", "z", "roll", "pitch", "yaw"))])
+def test_tsr_constraint_matches_oracle(engine, oracle, flavour, wam7, table, where, held):
+    """con_tsr 'all' / 'start' / 'end' with different held rows, 40 iterations"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 4)
+    if where == "end":
+        # hold the whole pose of the last moving waypoint where the straight line puts it
+        P = 40
+        q = starts[0] + (goals[0] - starts[0]) * (P - 2) / (P - 1)
+        starts, goals = starts[:1], goals[:1]
+        T0w = oracle.fk(wam7, q)[ee]
+        Twe = models.pose_make()
+    cons = [capi.make_constraint(where, ee, bounds(*held), T0w=T0w, Twe=Twe)]
+    params = capi.default_params(n_points=40, lambda_=100.0, obs_factor=500.0, constraints=cons)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    assert not b.uses_jit()
+    b.enable_trace(True)
+    costs, status = b.iterate(40)
+    traj, trace = b.get_traj(), b.get_trace(40)
+    ref = run_oracle(oracle, flavour, wam7, params, table["desc"], starts, goals, 40)
+    for r, o in enumerate(ref):
+        assert o["ret"] == 0 and status[r] == 0
+        assert np.max(np.abs(traj[r] - o["traj"])) <= TRAJ_ATOL
+        assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
+        assert np.allclose(trace[r], o["trace"], rtol=1e-7, atol=0)
+        # the constraint holds on the GPU's own result (property, not a comparison)
+        idx = {"all": range(1, 39), "start": [1], "end": [38]}[where]
+        h = np.array([o["run"].constraint_eval(0, traj[r][i])[0] for i in idx])
+        h_ref = np.array([o["run"].constraint_eval(0, o["traj"][i])[0] for i in idx])
+        assert np.max(np.abs(h - h_ref)) < 1e-5
+        if where == "all":  # every point projected in every iteration: the linearisation error is all that is left
+            assert np.max(np.abs(h)) < 1e-4
+    # and it did something: the unconstrained run ends elsewhere
+    p0 = capi.default_params(n_points=40, lambda_=100.0, obs_factor=500.0)
+    b0 = engine.create_batch(wam7, p0, [sid], starts, goals)
+    b0.iterate(40)
+    if where != "end":
+        assert np.max(np.abs(b0.get_traj() - traj)) > 1e-3
+    b0.close()
+    b.close()
+    engine.remove_sdf(sid)
+
+
+def test_two_constraints_tool_offset_momentum(engine, oracle, flavour, wam7, table):
+    """everyn_tsr-style constraint on every point through a tool transform, plus a con_tsr on a different link
+    at the first point; momentum update (the constraint then sees the accumulated AG, chomp.c:562-565)"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 3, seed=11)
+    tool = models.pose_make((0.0, 0.02, 0.12), models.quat_from_axis_angle((0, 1, 0), 0.3))
+    pe = models.pose_compose(oracle.fk(wam7, starts[0])[ee], tool)
+    T0w = models.pose_make((0, 0, pe[2]))
+    Twe = models.pose_make((0, 0, 0), pe[3:7])
+    elbow = wam7.names.index("wam4")
+    q1 = starts[0] + (goals[0] - starts[0]) / 29
+    cons = [capi.make_constraint("all", ee, bounds("z", "pitch"), T0w=T0w, Twe=Twe, pose_link_ee=tool),
+            capi.make_constraint("start", elbow, bounds("x"), T0w=oracle.fk(wam7, q1)[elbow])]
+    starts, goals = starts[:1].repeat(3, 0), goals[:1].repeat(3, 0)
+    goals[1, 3] += 0.02
+    goals[2, 5] -= 0.03
+    params = capi.default_params(n_points=30, lambda_=200.0, obs_factor=300.0, use_momentum=1, constraints=cons)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(30)
+    traj = b.get_traj()
+    ref = run_oracle(oracle, flavour, wam7, params, table["desc"], starts, goals, 30)
+    for r, o in enumerate(ref):
+        assert o["ret"] == 0 and status[r] == 0
+        assert np.max(np.abs(traj[r] - o["traj"])) <= TRAJ_ATOL
+        assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
+    b.close()
+    engine.remove_sdf(sid)
+
+
+def test_constraint_with_wider_metric(engine, oracle, flavour, wam7, table):
+    """derivative = 2: the dense inverse of a penta-diagonal metric couples the constrained waypoints"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 2, seed=5)
+    cons = [capi.make_constraint("all", ee, bounds("roll", "pitch"), T0w=T0w, Twe=Twe)]
+    params = capi.default_params(n_points=36, lambda_=400.0, derivative=2, constraints=cons)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(25)
+    ref = run_oracle(oracle, flavour, wam7, params, table["desc"], starts, goals, 25)
+    for r, o in enumerate(ref):
+        assert o["ret"] == 0 and status[r] == 0
+        assert np.max(np.abs(b.get_traj()[r] - o["traj"])) <= TRAJ_ATOL
+        assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
+    b.close()
+    engine.remove_sdf(sid)
