@@ -150,6 +150,10 @@ def set_constraints(params, constraints):
     return params
 
 
+def count_start_tsr(params):
+    return sum(1 for i in range(params.n_constraints) if params.constraints[i].where == CON_START_TSR)
+
+
 def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 

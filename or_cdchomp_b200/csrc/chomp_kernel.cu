@@ -212,6 +212,10 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
    const double invdt2 = 1.0 / (a.dt * a.dt);
    const double es = a.eps_self, inv_es = 1.0 / es, half_inv_es = 0.5 / es;
    double cost = 0.0;
+   /* start_tsr: the first moving point is the start itself; its velocity is the one-sided difference and
+    * its acceleration that of the next point (mod.cpp:1108-1114, 1126-1128) */
+   const bool first_free = a.free_start && t == 1;
+   const double invdt = 1.0 / a.dt;
 
    if (want_grad)
       for (int k = 0; k < 6 * DIM(a, ng); k++) Wg[k * Pp] = 0.0;
@@ -235,7 +239,8 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
          const bool obs = (best >= 0) && (d_obs < a.eps);
          double vel[3];
 #pragma unroll
-         for (int k = 0; k < 3; k++) vel[k] = (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
+         for (int k = 0; k < 3; k++)
+            vel[k] = first_free ? (ps[k * Pp + 1] - ps[k * Pp]) * invdt : (ps[k * Pp + 1] - ps[k * Pp - 1]) * inv2dt;
          const double vn2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
          double vn, iv2; /* |v| and 1 / |v|^2, unguarded (inf at rest), as mod.cpp:1239 */
          speed_terms(vn2, vn, iv2);
@@ -250,7 +255,9 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
             if (want_grad)
             {
 #pragma unroll
-               for (int k = 0; k < 3; k++) acc[k] = (p[k] * -2.0 + ps[k * Pp - 1] + ps[k * Pp + 1]) * invdt2;
+               for (int k = 0; k < 3; k++)
+                  acc[k] = first_free ? (ps[k * Pp + 1] * -2.0 + p[k] + ps[k * Pp + 2]) * invdt2
+                                      : (p[k] * -2.0 + ps[k * Pp - 1] + ps[k * Pp + 1]) * invdt2;
             }
             obstacle_apply(a, tb.sdfs[best], d_obs, bg, vel, acc, vn, iv2, moving, want_grad, cost_s, f);
          }
@@ -273,7 +280,8 @@ __device__ __forceinline__ double waypoint_cost(const OcbChompArgs &a, const Tab
             if (po)
             {
 #pragma unroll
-               for (int r = 0; r < 3; r++) v2[r] = (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
+               for (int r = 0; r < 3; r++)
+                  v2[r] = first_free ? (po[r * Pp + 1] - po[r * Pp]) * invdt : (po[r * Pp + 1] - po[r * Pp - 1]) * inv2dt;
                const double v2n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
                double v2n, iv22;
                speed_terms(v2n2, v2n, iv22);
@@ -384,7 +392,11 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
    const int NT = blockDim.x;
    const int run = blockIdx.x;
    const int Pp = PP ? PP : a.Ppad;
-   const int P = PP ? PP : a.P, m = PP ? PP - 2 : a.m, n = NN ? NN : a.n;
+   /* start_tsr (free_start): the start point is optimised too.  The kernel then works on P + 1 columns --
+    * column 0 is a stand-in that nothing reads with a non-zero weight, columns 1..P are the run's P
+    * waypoints, of which 1..P-1 move (m = P - 1, mod.cpp:2316) */
+   const int fs = CONS ? a.free_start : 0;
+   const int P = PP ? PP : a.P + fs, m = PP ? PP - 2 : a.m, n = NN ? NN : a.n;
 
    /* ---- shared memory carve-up ---- */
    const SmemLayout lay = smem_layout(a, Pp, n);
@@ -428,8 +440,10 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 #endif
 
    /* ---- stage per-run state and shared constants ---- */
-   double *traj = a.traj + (size_t) run * P * n;
-   for (int e = tid; e < P * n; e += NT) Ts[(e % n) * Pp + (e / n)] = traj[e];
+   double *traj = a.traj + (size_t) run * (P - fs) * n;
+   for (int e = tid; e < (P - fs) * n; e += NT) Ts[(e % n) * Pp + (e / n) + fs] = traj[e];
+   if (fs)
+      for (int j = tid; j < n; j += NT) Ts[j * Pp] = traj[j];
    if (DIM(a, use_momentum))
    {
       const double *ag = a.AG + (size_t) run * m * n;
@@ -455,7 +469,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       double ss = 0.0, sg = 0.0, gg = 0.0;
       for (int j = 0; j < n; j++)
       {
-         const double qs = traj[j], qg = traj[(size_t) (P - 1) * n + j];
+         const double qs = traj[j], qg = traj[(size_t) (P - fs - 1) * n + j];
          ss += qs * qs; sg += qs * qg; gg += qg * qg;
       }
       trC = 0.5 * (a.trc_ss * ss + 2.0 * a.trc_sg * sg + a.trc_gg * gg);
@@ -582,14 +596,17 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
             leapfrog_first = 0;
             AGc = AGs;
          }
-         for (int t = tid + 1; t <= m; t += NT)
+         for (int t = tid + 1; t <= m && K > 0; t += NT)
             if (a.con_row0[t] > a.con_row0[t - 1])
                con_eval_waypoint<FLOAT>(a, Ts, slots, AGc, Pp, t, m, n, inv_lambda, Jc, hc);
          __syncthreads();
-         con_build_system(a, Jc, S, m, n);
-         for (int e = tid; e < K; e += NT) h0[e] = hc[e];
+         if (K > 0)
+         {
+            con_build_system(a, Jc, S, m, n);
+            for (int e = tid; e < K; e += NT) h0[e] = hc[e];
+         }
          __syncthreads();
-         if (con_solve(S, hc, K, red, ired))
+         if (K > 0 && con_solve(S, hc, K, red, ired))
          {
             /* zero pivot: dgesv leaves the right-hand side as it was and the reference carries on with it */
             __syncthreads();
@@ -599,7 +616,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          }
          for (int t = tid + 1; t <= m; t += NT)
          {
-            const int r0 = a.con_row0[t - 1], r1 = a.con_row0[t];
+            const int r0 = K > 0 ? a.con_row0[t - 1] : 0, r1 = K > 0 ? a.con_row0[t] : 0;
             for (int j = 0; j < n; j++)
             {
                Ts[j * Pp + t] = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]);
@@ -713,7 +730,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 #endif
    /* ---- write the run back ---- */
    __syncthreads();
-   for (int e = tid; e < P * n; e += NT) traj[e] = Ts[(e % n) * Pp + (e / n)];
+   for (int e = tid; e < (P - fs) * n; e += NT) traj[e] = Ts[(e % n) * Pp + (e / n) + fs];
    if (DIM(a, use_momentum))
    {
       double *ag = a.AG + (size_t) run * m * n;
@@ -848,7 +865,7 @@ static cudaError_t launch_variant(const OcbChompArgs *args, size_t smem_bytes, i
 extern "C" cudaError_t ocb_launch_chomp(const OcbChompArgs *args, size_t smem_bytes, int threads, cudaStream_t st)
 {
    if (threads > 256 || threads % 32) return cudaErrorInvalidValue;
-   if (args->con_K > 0) /* hard constraints: the generic instantiations only */
+   if (args->con_K > 0 || args->free_start) /* hard constraints: the generic instantiations only */
    {
       if (args->floating)
          return threads <= 128 ? launch_variant<128, true, 0, 0, true>(args, smem_bytes, threads, st)

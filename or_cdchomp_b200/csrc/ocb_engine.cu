@@ -859,7 +859,7 @@ struct Metric
    double ss, sg, gg;
 };
 
-int build_metric(int m, int D, double dt, Metric &M)
+int build_metric(int m, int D, double dt, Metric &M, bool free_start = false)
 {
    M.m = m;
    M.bw = D;
@@ -876,19 +876,22 @@ int build_metric(int m, int D, double dt, Metric &M)
    int prev = m;
    for (int d = 0; d < D; d++)
    {
-      const int cur = prev + 1; /* prev - 1 + init row + final row */
+      /* start_tsr leaves inits[0] unset (mod.cpp:2571-2576): level 0 then has no row for the start
+       * boundary (chomp.c:262-264, 278-283); the higher levels keep theirs (zero vectors, chomp.c:131-141) */
+      const int has_i = (d == 0 && free_start) ? 0 : 1;
+      const int cur = prev - 1 + has_i + 1; /* interior rows + init row + final row */
       std::vector<SRow> K(cur);
       std::vector<double> ci(cur, 0.0), cf(cur, 0.0);
       /* rows of the differencing matrix: (col, value) pairs over the previous level */
       for (int r = 0; r < cur; r++)
       {
          SRow diff;
-         if (r == 0) diff.push_back(std::make_pair(0, 1.0 / dt));
+         if (has_i && r == 0) diff.push_back(std::make_pair(0, 1.0 / dt));
          else if (r == cur - 1) diff.push_back(std::make_pair(prev - 1, -1.0 / dt));
          else
          {
-            diff.push_back(std::make_pair(r - 1, -1.0 / dt));
-            diff.push_back(std::make_pair(r, 1.0 / dt));
+            diff.push_back(std::make_pair(r - has_i, -1.0 / dt));
+            diff.push_back(std::make_pair(r - has_i + 1, 1.0 / dt));
          }
          for (const auto &e : diff)
          {
@@ -904,7 +907,7 @@ int build_metric(int m, int D, double dt, Metric &M)
       }
       if (d == 0)
       {
-         ci[0] += -1.0 / dt;      /* E row 0   = -inits[0]/dt  (chomp.c:281) */
+         if (has_i) ci[0] += -1.0 / dt; /* E row 0   = -inits[0]/dt  (chomp.c:281) */
          cf[cur - 1] += 1.0 / dt; /* E row N-1 = +finals[0]/dt (chomp.c:295) */
       }
       const double w = wds[d] / cur;
@@ -1391,8 +1394,8 @@ int compile_constraints(const ocb_params *params, const ocb_robot *rb, const Com
    {
       const ocb_constraint &s = params->constraints[ci];
       if (s.link < 0 || s.link >= rb->n_links) return fail(OCB_ERR_ARG, "constraint %d: bad link", ci);
-      if (s.where != OCB_CON_START && s.where != OCB_CON_END && s.where != OCB_CON_ALL)
-         return fail(OCB_ERR_ARG, "constraint %d: where must be OCB_CON_START, OCB_CON_END or OCB_CON_ALL", ci);
+      if (s.where != OCB_CON_START && s.where != OCB_CON_END && s.where != OCB_CON_ALL && s.where != OCB_CON_START_TSR)
+         return fail(OCB_ERR_ARG, "constraint %d: where must be one of OCB_CON_*", ci);
       OcbConDev d;
       memset(&d, 0, sizeof(d));
       const Xf A = xf_invert(xf_from_pose(s.T0w));
@@ -1414,7 +1417,8 @@ int compile_constraints(const ocb_params *params, const ocb_robot *rb, const Com
    {
       row0[i] = (int) row_wp.size();
       for (const OcbConDev &d : cons)
-         if (d.where == OCB_CON_ALL || (d.where == OCB_CON_START && i == 0) || (d.where == OCB_CON_END && i == m - 1))
+         if (d.where == OCB_CON_ALL || ((d.where == OCB_CON_START || d.where == OCB_CON_START_TSR) && i == 0) ||
+             (d.where == OCB_CON_END && i == m - 1))
             for (int r = 0; r < d.k; r++) row_wp.push_back(i);
    }
    row0[m] = (int) row_wp.size();
@@ -1503,10 +1507,18 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    const bool floating = params->floating_base != 0;
    int rc = compile_robot(robot, params->epsilon_self, floating, C);
    if (rc) return rc;
-   const int P = params->n_points, m = P - 2, n = robot->n_dof + (floating ? 7 : 0);
+   /* start_tsr: the start point joins the optimised rows (mod.cpp:2316) */
+   int n_start_tsr = 0;
+   if (params->n_constraints > 0 && !params->constraints) return fail(OCB_ERR_ARG, "constraints is null");
+   for (int i = 0; i < params->n_constraints; i++)
+      if (params->constraints[i].where == OCB_CON_START_TSR) n_start_tsr++;
+   if (n_start_tsr > 1) return fail(OCB_ERR_ARG, "at most one start_tsr");
+   if (n_start_tsr && floating) return fail(OCB_ERR_ARG, "floating_base and start_tsr together is not yet implemented!"); /* mod.cpp:2100 */
+   const bool free_start = n_start_tsr > 0;
+   const int P = params->n_points, m = P - 2 + (free_start ? 1 : 0), n = robot->n_dof + (floating ? 7 : 0);
    Metric M;
    const double dt = 1.0 / (P - 1); /* mod.cpp:2567 */
-   rc = build_metric(m, params->derivative, dt, M);
+   rc = build_metric(m, params->derivative, dt, M, free_start);
    if (rc) return fail(OCB_ERR_ARG, "smoothness metric is not positive definite (code %d)", rc);
 
    ocb_batch *b = new (std::nothrow) ocb_batch();
@@ -1528,7 +1540,8 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
    a.ng = C.n_groups;
    a.n_desc = (int) C.desc.size();
    a.NAp = a.nsa + 3;
-   a.Ppad = P;
+   a.Ppad = P + (free_start ? 1 : 0); /* the kernel's extra column, see chomp_iterate_body */
+   a.free_start = free_start ? 1 : 0;
    a.use_momentum = params->use_momentum ? 1 : 0;
    a.use_hmc = use_hmc;
    a.floating = floating ? 1 : 0;
@@ -1660,7 +1673,7 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
     * one SM's shared memory the iteration is tiled over waypoints (chomp_tiled.cu). */
    a.ws_stride = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
    b->smem = ocb_chomp_smem_bytes(&a);
-   if (b->smem > (size_t) e->smem_optin && a.con_K > 0)
+   if (b->smem > (size_t) e->smem_optin && (a.con_K > 0 || a.free_start))
    {
       ocb_batch_destroy(b);
       return fail(OCB_ERR_ARG, "hard constraints need the run in one SM's shared memory (%d spheres, %d waypoints, %d dofs)",
@@ -1686,8 +1699,8 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       TRY(batch_alloc(b, &a.G_obs, R * m * n));
       TRY(batch_alloc(b, &a.tile_cost, R * a.n_tiles));
    }
-   b->threads = std::min(256, ((P + 31) / 32) * 32);
-   if (e->jit && !a.tiled && a.con_K == 0) /* constraints: the library's kernel */
+   b->threads = std::min(256, ((a.Ppad + 31) / 32) * 32);
+   if (e->jit && !a.tiled && a.con_K == 0 && !a.free_start) /* constraints: the library's kernel */
    {
       /* blocks per SM the shared memory allows, not more than ~160 registers per thread can feed */
       int min_blocks = (int) ((size_t) e->smem_per_sm / (b->smem + 1024));

@@ -145,6 +145,7 @@ struct OcbChompArgs
    OcbSdfDev sdf_inline[OCB_INLINE_SDFS];
    /* hard constraints (chomp.c:553-600): con_K stacked rows, waypoint-major; library kernel only */
    int n_con, con_K;
+   int free_start, pad3;      /* start_tsr: P - 1 moving waypoints, the first is the start point (see chomp_iterate_body) */
    const OcbConDev *cons;     /* [n_con] */
    const int *con_row0;       /* [m + 1]: first row of each moving waypoint */
    const int *con_row_wp;     /* [con_K]: moving waypoint (0-based) of each row */

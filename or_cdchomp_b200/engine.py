@@ -192,7 +192,8 @@ class Batch:
         assert q_start.shape == q_goal.shape and q_start.shape[1] == robot.n_dof + (7 if params.floating_base else 0)
         self.R, self.n = q_start.shape
         self.P = params.n_points
-        self.m = self.P - 2
+        # start_tsr: the start point is optimised too (mod.cpp:2316)
+        self.m = self.P - 2 + capi.count_start_tsr(params)
         ids = np.ascontiguousarray(sdf_ids, dtype=np.int32)
         sp = None
         if seeds is not None:

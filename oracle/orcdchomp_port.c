@@ -132,6 +132,7 @@ struct orc_run
    struct cd_chomp *c;
    int iter;
    int floating; /* floating_base: rows are [x y z qx qy qz qw, adofs] (mod.cpp:991-1021) */
+   int start_tsr; /* the start point is optimised too: c->m == n_points-1 (mod.cpp:2316) */
    int n_cons;
    struct orc_con *cons; /* struct run_contsr / start_tsr / everyn_tsr (mod.cpp:873-884, 926-940) */
 };
@@ -399,7 +400,7 @@ static int orc_sphere_cost_pre(void *cptr, struct cd_chomp *c, int m, double **T
    (void) T_points;
    for (ti = 0; ti < r->n_points; ti++)
    {
-      int ti_mov = ti - 1; /* c->m == n_points-2 (no start_tsr) */
+      int ti_mov = (c->m == r->n_points - 2) ? ti - 1 : ti; /* mod.cpp:1040-1043 */
       double Jsp[6][7];
       if (r->floating)
       {
@@ -430,16 +431,28 @@ static int orc_sphere_cost_pre(void *cptr, struct cd_chomp *c, int m, double **T
             orc_jacobian(rb, r->link_poses, link, v, J);
       }
    }
-   /* velocities: (p[t+1] - p[t-1]) * (1/(2 dt))   (mod.cpp:1105-1107) */
+   {
+   /* with start_tsr the interior rows start one further down and row 0 belongs to the start point */
+   size_t shift = (c->m != r->n_points - 2) ? row : 0;
+   /* velocities: (p[t+1] - p[t-1]) * (1/(2 dt))   (mod.cpp:1101-1107) */
    for (ti = 0; ti < r->n_points - 2; ti++)
       for (k = 0; k < (int) row; k++)
       {
          double x = r->sphere_poss_all[(ti + 2) * row + k];
          x -= r->sphere_poss_all[ti * row + k];
          x *= 1.0 / (2.0 * c->dt);
-         r->sphere_vels[ti * row + k] = x;
+         r->sphere_vels[shift + ti * row + k] = x;
       }
-   /* accelerations: (-2 p[t] + p[t-1] + p[t+1]) * (1/dt^2)   (mod.cpp:1121-1125) */
+   /* the start point: one-sided difference (mod.cpp:1108-1114) */
+   if (shift)
+      for (k = 0; k < (int) row; k++)
+      {
+         double x = r->sphere_poss_all[row + k];
+         x -= r->sphere_poss_all[k];
+         x *= 1.0 / (c->dt);
+         r->sphere_vels[k] = x;
+      }
+   /* accelerations: (-2 p[t] + p[t-1] + p[t+1]) * (1/dt^2)   (mod.cpp:1118-1125) */
    for (ti = 0; ti < r->n_points - 2; ti++)
       for (k = 0; k < (int) row; k++)
       {
@@ -448,8 +461,12 @@ static int orc_sphere_cost_pre(void *cptr, struct cd_chomp *c, int m, double **T
          x += r->sphere_poss_all[ti * row + k];
          x += r->sphere_poss_all[(ti + 2) * row + k];
          x *= 1.0 / (c->dt * c->dt);
-         r->sphere_accs[ti * row + k] = x;
+         r->sphere_accs[shift + ti * row + k] = x;
       }
+   /* the start point takes the acceleration of its neighbour (mod.cpp:1126-1128) */
+   if (shift)
+      for (k = 0; k < (int) row; k++) r->sphere_accs[k] = r->sphere_accs[row + k];
+   }
    return 0;
 }
 
@@ -631,8 +648,12 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    struct cd_chomp *c = 0;
    int fl = pr->floating_base ? 1 : 0;
    int n = rb->n_dof + (fl ? 7 : 0), P = pr->n_points, m = P - 2;
-   int i, j, s, na = 0, ni = 0;
+   int i, j, s, na = 0, ni = 0, start_tsr = 0;
    if (pr->lambda < 0.01 || P < 3 || n_sdfs < 1) return -2;
+   for (i = 0; i < pr->n_constraints; i++)
+      if (pr->constraints[i].where == OCB_CON_START_TSR) start_tsr++;
+   if (start_tsr > 1 || (start_tsr && fl)) return -2; /* mod.cpp:2100 */
+   if (start_tsr) m++;                                /* mod.cpp:2316 */
    r = (struct orc_run *) calloc(1, sizeof(struct orc_run));
    if (!r) return -1;
    r->floating = fl;
@@ -663,7 +684,8 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    r->Jadof = (double *) malloc(3 * (rb->n_dof ? rb->n_dof : 1) * sizeof(double));
    r->link_poses = (double *) malloc((size_t) rb->n_links * 7 * sizeof(double));
    r->sphere_poss_all = (double *) malloc((size_t) P * na * 3 * sizeof(double));
-   r->sphere_poss = r->sphere_poss_all + (size_t) na * 3;
+   r->start_tsr = start_tsr;
+   r->sphere_poss = r->sphere_poss_all + (start_tsr ? 0 : (size_t) na * 3); /* mod.cpp:2320-2323 */
    r->sphere_vels = (double *) malloc((size_t) m * na * 3 * sizeof(double));
    r->sphere_accs = (double *) malloc((size_t) m * na * 3 * sizeof(double));
    r->sphere_jacs = (double *) malloc((size_t) m * na * 3 * n * sizeof(double));
@@ -704,10 +726,10 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
    if (fl) /* mod.cpp:2461-2464 */
       for (i = 0; i < P; i++) cd_kin_pose_normalize(&r->traj[i * n]);
 
-   if (cd_chomp_create(&c, m, n, pr->derivative, &r->traj[n], n)) { orc_run_destroy(r); return -1; }
+   if (cd_chomp_create(&c, m, n, pr->derivative, &r->traj[start_tsr ? 0 : n], n)) { orc_run_destroy(r); return -1; } /* mod.cpp:2521 */
    r->c = c;
    c->dt = 1.0 / (P - 1);
-   c->inits[0] = &r->traj[0];
+   c->inits[0] = start_tsr ? 0 : &r->traj[0]; /* mod.cpp:2571-2578 */
    c->finals[0] = &r->traj[(P - 1) * n];
    c->cptr = r;
    c->cost_pre = orc_sphere_cost_pre;
@@ -741,6 +763,7 @@ int orc_run_create(const struct ocb_robot *rb, const struct ocb_params *pr, int 
          if (con->spec.link < 0 || con->spec.link >= rb->n_links) { orc_run_destroy(r); return -2; }
          switch (con->spec.where)
          {
+         case OCB_CON_START_TSR: /* con_start_tsr on the start point itself (mod.cpp:2574) */
          case OCB_CON_START: cd_chomp_add_constraint(c, con->k, 0, con, orc_con_tsr); break;
          case OCB_CON_END: cd_chomp_add_constraint(c, con->k, m - 1, con, orc_con_tsr); break;
          case OCB_CON_ALL:

@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from or_cdchomp_b200.capi import (OcbParams, OcbPrim, OcbRobot, OcbSdf, as_f64, c_double_p,
+from or_cdchomp_b200.capi import (OcbParams, OcbPrim, OcbRobot, OcbSdf, as_f64, c_double_p, count_start_tsr,
                                   c_int_p, dptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -134,7 +134,7 @@ class Run:
         self.robot, self.params, self.sdfs = robot, params, list(sdfs)
         self.n = robot.n_dof + (7 if params.floating_base else 0)
         self.P = params.n_points
-        self.m = self.P - 2
+        self.m = self.P - 2 + count_start_tsr(params)  # start_tsr: mod.cpp:2316
         arr = (OcbSdf * len(self.sdfs))(*[s.struct for s in self.sdfs])
         self._arr = arr
         self.q_start, self.q_goal = as_f64(q_start), as_f64(q_goal)

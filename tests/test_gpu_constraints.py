@@ -149,3 +149,92 @@ def test_constraint_with_wider_metric(engine, oracle, flavour, wam7, table):
         assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_start_tsr_frees_the_start_point(engine, oracle, flavour, wam7, table):
+    """start_tsr (mod.cpp:2316, 2320-2323, 2521, 2571-2576; sphere_cost_pre 1040-1043, 1108-1114, 1126-1128):
+    m = n_points - 1, the start row is optimised under its constraint, no initial boundary row in the metric,
+    one-sided velocity and borrowed acceleration at the start; plain and momentum + HMC updates"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 3)
+    sid = engine.upload_sdf(table["desc"])
+    for kw, seeds in ((dict(), None), (dict(use_momentum=1, use_hmc=1, hmc_resample_lambda=0.1), [3, 4, 5])):
+        cons = [capi.make_constraint("start_tsr", ee, bounds("x", "z", "roll", "pitch", "yaw"), T0w=T0w, Twe=Twe)]
+        pe = oracle.fk(wam7, starts[0])[ee]
+        cons[0].T0w[0] = pe[0]  # the start may slide along y only
+        params = capi.default_params(n_points=40, lambda_=150.0, obs_factor=500.0, constraints=cons, **kw)
+        b = engine.create_batch(wam7, params, [sid], starts, goals, seeds=seeds)
+        assert b.m == 39
+        b.enable_trace(True)
+        b.capture_gradient(1)
+        costs, status = b.iterate(30)
+        traj, trace, grad = b.get_traj(), b.get_trace(30), b.get_gradient()
+        assert grad.shape == (3, 39, 7)
+        ref = run_oracle(oracle, flavour, wam7, params, table["desc"], starts, goals, 30, seeds=seeds)
+        for r, o in enumerate(ref):
+            assert o["ret"] == 0 and status[r] == 0
+            assert np.max(np.abs(traj[r] - o["traj"])) <= TRAJ_ATOL
+            assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
+            assert np.allclose(trace[r], o["trace"], rtol=1e-7, atol=0)
+            assert np.max(np.abs(traj[r][0] - starts[r])) > 1e-3      # the start moved ...
+            h = o["run"].constraint_eval(0, traj[r][0])[0]
+            assert np.max(np.abs(h)) < 5e-3                            # ... inside its region (to first order)
+            assert np.array_equal(traj[r][-1], goals[r])               # the goal never does
+        b.close()
+    engine.remove_sdf(sid)
+
+
+def test_floating_base_constraint(engine, oracle, flavour, wam7, table):
+    """floating_base with a constraint on every point: the pose columns of the constraint Jacobian come from
+    cd_spatial_pose_jac (mod.cpp:1432-1437), unscaled"""
+    rng = np.random.default_rng(21)
+    ee = wam7.names.index("wam7")
+    base0 = np.asarray(wam7.base_pose, dtype=float)
+    arm = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    qs, qg = [], []
+    for r in range(3):
+        move = models.pose_make(rng.uniform(-0.15, 0.15, 3), models.quat_from_axis_angle((0, 0, 1), rng.uniform(0.2, 0.5)))
+        qs.append(np.concatenate([base0, arm]))
+        qg.append(np.concatenate([models.pose_compose(base0, move), arm + rng.uniform(-0.1, 0.1, 7)]))
+    qs, qg = np.array(qs), np.array(qg)
+    pe = oracle.fk(wam7, arm)[ee]
+    cons = [capi.make_constraint("all", ee, bounds("z", "pitch"), T0w=models.pose_make((0, 0, pe[2])),
+                                 Twe=models.pose_make((0, 0, 0), pe[3:7]))]
+    params = capi.default_params(n_points=36, lambda_=200.0, obs_factor=300.0, floating_base=1, constraints=cons)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], qs, qg)
+    costs, status = b.iterate(25)
+    traj = b.get_traj()
+    ref = run_oracle(oracle, flavour, wam7, params, table["desc"], qs, qg, 25)
+    for r, o in enumerate(ref):
+        assert o["ret"] == 0 and status[r] == 0
+        assert np.max(np.abs(traj[r] - o["traj"])) <= TRAJ_ATOL
+        assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
+        assert np.allclose(np.linalg.norm(traj[r][:, 3:7], axis=1), 1.0, atol=1e-14)
+    b.close()
+    engine.remove_sdf(sid)
+
+
+def test_constraint_argument_errors(engine, wam7, table):
+    """what create refuses (mod.cpp:2100; the tiled path and the run-time specialised kernel do not carry constraints)"""
+    ee = wam7.names.index("wam7")
+    sid = engine.upload_sdf(table["desc"])
+    qs, qg = np.array(models.WAM7_DEMO_START), np.array(models.WAM7_DEMO_GOAL)
+    two = [capi.make_constraint("start_tsr", ee, bounds("z")), capi.make_constraint("start_tsr", ee, bounds("x"))]
+    with pytest.raises(RuntimeError, match="at most one start_tsr"):
+        engine.create_batch(wam7, capi.default_params(n_points=20, constraints=two), [sid], qs, qg)
+    with pytest.raises(RuntimeError, match="floating_base and start_tsr"):
+        engine.create_batch(wam7, capi.default_params(n_points=20, floating_base=1, constraints=two[:1]), [sid],
+                            np.concatenate([wam7.base_pose, qs]), np.concatenate([wam7.base_pose, qg]))
+    bad = [capi.make_constraint("all", 99, bounds("z"))]
+    with pytest.raises(RuntimeError, match="bad link"):
+        engine.create_batch(wam7, capi.default_params(n_points=20, constraints=bad), [sid], qs, qg)
+    # a constraint whose bounds hold nothing adds no rows: same result as no constraint
+    free = [capi.make_constraint("all", ee, bounds())]
+    b1 = engine.create_batch(wam7, capi.default_params(n_points=30, lambda_=100.0, constraints=free), [sid], qs, qg)
+    b2 = engine.create_batch(wam7, capi.default_params(n_points=30, lambda_=100.0), [sid], qs, qg)
+    b1.iterate(10)
+    b2.iterate(10)
+    assert np.max(np.abs(b1.get_traj() - b2.get_traj())) < 1e-12
+    b1.close()
+    b2.close()
+    engine.remove_sdf(sid)
