@@ -71,6 +71,14 @@ int ocb_env_enable_kinbody(ocb_env *env, const char *name, int enabled);
 int ocb_env_add_robot(ocb_env *env, const char *name, const ocb_robot *robot,
                       const double *active_dof_values);
 int ocb_env_set_active_dof_values(ocb_env *env, const char *name, const double *values);
+/* what the TSR constraint arguments of `create` look up on the robot (mod.cpp:1957-1977, 1384-1387):
+ * KinBody::GetLink(name), RobotBase::GetManipulators() / GetActiveManipulator() with
+ * GetEndEffector() and GetLocalToolTransform().  names: one per link of the description.  The first
+ * manipulator added is the active one until ocb_env_set_active_manipulator. */
+int ocb_env_set_link_names(ocb_env *env, const char *robot, const char *const *names, int n_names);
+int ocb_env_add_manipulator(ocb_env *env, const char *robot, const char *name, int ee_link,
+                            const double local_tool[7]);
+int ocb_env_set_active_manipulator(ocb_env *env, const char *robot, const char *name);
 
 /* RaveCreateModule(env, "orcdchomp") on GPU `device` */
 int ocb_module_create(ocb_env *env, int device, ocb_module **out);

@@ -89,6 +89,64 @@ std::vector<double> parse_doubles(const std::string &s)
    return v;
 }
 
+/* tsr_create_parse (mod.cpp:3068-3110): "manipindex bodyandlink" then T0w's rotation matrix column by
+ * column and its translation, the same for Twe, then the six [min max] bounds; the two transforms become
+ * poses [x y z qx qy qz qw] */
+struct Tsr
+{
+   double T0w[7], Twe[7], Bw[6][2];
+};
+
+void pose_from_columns(const double *v /* 9 rotation entries by column, 3 translation */, double pose[7])
+{
+   double R[3][3];
+   for (int c = 0; c < 3; c++)
+      for (int r = 0; r < 3; r++) R[r][c] = v[3 * c + r];
+   /* unit quaternion of R, the largest of the four components taken from the diagonal
+    * (cd_kin_quat_from_R, src/libcd/kin.c:426-467) */
+   const double x4 = 1.0 + R[0][0] - R[1][1] - R[2][2], y4 = 1.0 - R[0][0] + R[1][1] - R[2][2];
+   const double z4 = 1.0 - R[0][0] - R[1][1] + R[2][2], w4 = 1.0 + R[0][0] + R[1][1] + R[2][2];
+   double *q = pose + 3;
+   if (x4 > y4 && x4 > z4 && x4 > w4)
+   {
+      q[0] = sqrt(0.25 * x4);
+      const double f = 0.25 / q[0];
+      q[1] = f * (R[1][0] + R[0][1]); q[2] = f * (R[0][2] + R[2][0]); q[3] = f * (R[2][1] - R[1][2]);
+   }
+   else if (y4 > z4 && y4 > w4)
+   {
+      q[1] = sqrt(0.25 * y4);
+      const double f = 0.25 / q[1];
+      q[0] = f * (R[1][0] + R[0][1]); q[2] = f * (R[2][1] + R[1][2]); q[3] = f * (R[0][2] - R[2][0]);
+   }
+   else if (z4 > w4)
+   {
+      q[2] = sqrt(0.25 * z4);
+      const double f = 0.25 / q[2];
+      q[0] = f * (R[0][2] + R[2][0]); q[1] = f * (R[2][1] + R[1][2]); q[3] = f * (R[1][0] - R[0][1]);
+   }
+   else
+   {
+      q[3] = sqrt(0.25 * w4);
+      const double f = 0.25 / q[3];
+      q[0] = f * (R[2][1] - R[1][2]); q[1] = f * (R[0][2] - R[2][0]); q[2] = f * (R[1][0] - R[0][1]);
+   }
+   pose[0] = v[9]; pose[1] = v[10]; pose[2] = v[11];
+}
+
+bool parse_tsr(const std::string &text, Tsr &t)
+{
+   int manipindex = 0, used = 0;
+   char bodyandlink[32];
+   if (sscanf(text.c_str(), "%d %31s%n", &manipindex, bodyandlink, &used) != 2) return false;
+   const std::vector<double> v = parse_doubles(text.substr(used));
+   if (v.size() != 36) return false;
+   pose_from_columns(&v[0], t.T0w);
+   pose_from_columns(&v[12], t.Twe);
+   for (int i = 0; i < 6; i++) { t.Bw[i][0] = v[24 + 2 * i]; t.Bw[i][1] = v[24 + 2 * i + 1]; }
+   return true;
+}
+
 /* cd_kin_pose_compose (kin.c:136-178) on the host: snapshot poses only */
 void pose_compose(const double ab[7], const double bc[7], double ac[7])
 {
@@ -176,6 +234,12 @@ struct Robot
    std::vector<int> parent, joint_type, dof_index, sphere_link;
    std::vector<double> pose_parent, axis, dof_coeff, limit_lower, limit_upper, sphere_pos, sphere_radius, q;
    ocb_robot desc;
+   /* what con_tsr / start_tsr / everyn_tsr look up on the robot (mod.cpp:1957-1977): link names and
+    * manipulators (end-effector link + local tool transform); the first manipulator added is the active one */
+   struct Manip { std::string name; int link; double tool[7]; };
+   std::vector<std::string> link_names;
+   std::vector<Manip> manips;
+   int active_manip = 0;
 
    void assign(const ocb_robot *r, const double *values)
    {
@@ -646,6 +710,7 @@ struct ocb_module
       const double *goals_ptr = nullptr, *starts_ptr = nullptr;
       const unsigned int *seeds_ptr = nullptr;
       const char *unsupported = nullptr;
+      std::vector<ocb_constraint> start_tsrs, everyn_tsrs, con_tsrs; /* a repeated start_tsr / everyn_tsr replaces the earlier one */
       size_t i = 1;
       for (; i < argv.size(); i++)
       {
@@ -692,12 +757,61 @@ struct ocb_module
             basegoal = parse_doubles(argv[++i]);
             if (basegoal.size() != 7) throw module_error("basegoal argument must be length 7!");
          }
-         else if ((a == "start_tsr" || a == "everyn_tsr" || a == "start_cost") && has1)
+         else if (a == "start_cost" && has1)
          {
-            unsupported = argv[i].c_str();
+            unsupported = argv[i].c_str(); /* a host callback per iteration: not on the device path */
             ++i;
          }
-         else if (a == "con_tsr" && i + 2 < argv.size()) { unsupported = "con_tsr"; i += 2; }
+         else if ((a == "start_tsr" || a == "everyn_tsr") && has1)
+         {
+            /* mod.cpp:1988-1997: on the active manipulator's end effector */
+            Tsr t;
+            if (!parse_tsr(argv[++i], t)) throw module_error("Cannot parse " + a + " TSR!");
+            ocb_constraint c;
+            memset(&c, 0, sizeof(c));
+            c.where = (a == "start_tsr") ? OCB_CON_START_TSR : OCB_CON_ALL;
+            c.link = -1; /* the active manipulator, resolved once the robot is known */
+            memcpy(c.T0w, t.T0w, sizeof(c.T0w)); memcpy(c.Twe, t.Twe, sizeof(c.Twe)); memcpy(c.Bw, t.Bw, sizeof(c.Bw));
+            (a == "start_tsr" ? start_tsrs : everyn_tsrs).push_back(c);
+         }
+         else if (a == "con_tsr" && i + 2 < argv.size())
+         {
+            /* mod.cpp:1930-1987: 'start|end|all [manipee NAME | link NAME]' 'TSR' */
+            if (robot_name.empty()) throw module_error("You must pass robot before any con_tsrs!");
+            const std::vector<std::string> sub = shell_split(argv[++i]);
+            if (sub.size() != 1 && sub.size() != 3) throw module_error("con_tsr first argument must be length 1 or 3!");
+            ocb_constraint c;
+            memset(&c, 0, sizeof(c));
+            if (sub[0] == "all") c.where = OCB_CON_ALL;
+            else if (sub[0] == "start") c.where = OCB_CON_START;
+            else if (sub[0] == "end") c.where = OCB_CON_END;
+            else throw module_error("con_tsr first arg must be start, end, or all!");
+            Robot &rb0 = *env->robots[robot_name];
+            c.pose_link_ee[6] = 1.0;
+            if (sub.size() != 3) c.link = -1;
+            else if (sub[1] == "manipee")
+            {
+               size_t k = 0;
+               for (; k < rb0.manips.size(); k++)
+                  if (rb0.manips[k].name == sub[2]) break;
+               if (k == rb0.manips.size()) throw module_error("con_tsr manip not found!");
+               c.link = rb0.manips[k].link;
+               memcpy(c.pose_link_ee, rb0.manips[k].tool, sizeof(c.pose_link_ee));
+            }
+            else if (sub[1] == "link")
+            {
+               size_t k = 0;
+               for (; k < rb0.link_names.size(); k++)
+                  if (rb0.link_names[k] == sub[2]) break;
+               if (k == rb0.link_names.size()) throw module_error("con_tsr link not found!");
+               c.link = (int) k;
+            }
+            else throw module_error("con_tsr first arg must be empty, manipee, or link!");
+            Tsr t;
+            if (!parse_tsr(argv[++i], t)) throw module_error("Cannot parse constraint TSR!");
+            memcpy(c.T0w, t.T0w, sizeof(c.T0w)); memcpy(c.Twe, t.Twe, sizeof(c.Twe)); memcpy(c.Bw, t.Bw, sizeof(c.Bw));
+            con_tsrs.push_back(c);
+         }
          else if (batch_form && a == "n_runs" && has1) n_runs = atoi(argv[++i].c_str());
          else if (batch_form && (a == "adofgoals" || a == "adofstarts" || a == "seeds") && has1)
          {
@@ -722,7 +836,24 @@ struct ocb_module
       if (sdfs.empty()) throw module_error("No signed distance fields have yet been computed!");
       if (pr.lambda < 0.01) throw module_error("lambda must be >=0.01!");
       if (pr.n_points < 3) throw module_error("n_points must be >=3!");
+      if (pr.floating_base && !start_tsrs.empty()) throw module_error("floating_base and start_tsr together is not yet implemented!");
       Robot &rb = *env->robots[robot_name];
+      /* the constraint list in the order the reference registers it (mod.cpp:2571-2613) */
+      std::vector<ocb_constraint> cons;
+      if (!start_tsrs.empty()) cons.push_back(start_tsrs.back());
+      if (!everyn_tsrs.empty()) cons.push_back(everyn_tsrs.back());
+      cons.insert(cons.end(), con_tsrs.begin(), con_tsrs.end());
+      for (ocb_constraint &c : cons)
+         if (c.link < 0)
+         {
+            /* GetActiveManipulator()->GetEndEffectorTransform() (mod.cpp:1384-1385, 1545, 1701) */
+            if (rb.manips.empty()) throw module_error("robot has no active manipulator for the TSR constraint!");
+            const Robot::Manip &mp = rb.manips[rb.active_manip];
+            c.link = mp.link;
+            memcpy(c.pose_link_ee, mp.tool, sizeof(c.pose_link_ee));
+         }
+      pr.n_constraints = (int) cons.size();
+      pr.constraints = cons.empty() ? nullptr : cons.data();
       const int n_adof = rb.desc.n_dof;
       const int n = n_adof + (pr.floating_base ? 7 : 0); /* mod.cpp:2128-2131 */
       if (!goals_ptr && !have_starttraj && (int) adofgoal.size() != n_adof) throw module_error("size of adofgoal does not match active dofs!");
@@ -1093,6 +1224,47 @@ extern "C" int ocb_env_add_robot(ocb_env *env, const char *name, const ocb_robot
    memcpy(kb.pose, robot->base_pose, sizeof(kb.pose));
    env->kinbodies[name] = kb;
    return OCB_OK;
+}
+
+extern "C" int ocb_env_set_link_names(ocb_env *env, const char *robot, const char *const *names, int n_names)
+{
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
+   if (!robot || !names || !env->robots.count(robot)) return OCB_ERR_ARG;
+   Robot &r = *env->robots[robot];
+   if (n_names != r.desc.n_links) return OCB_ERR_ARG;
+   r.link_names.assign(names, names + n_names);
+   return OCB_OK;
+}
+
+extern "C" int ocb_env_add_manipulator(ocb_env *env, const char *robot, const char *name, int ee_link,
+                                       const double local_tool[7])
+{
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
+   if (!robot || !name || !env->robots.count(robot)) return OCB_ERR_ARG;
+   Robot &r = *env->robots[robot];
+   if (ee_link < 0 || ee_link >= r.desc.n_links) return OCB_ERR_ARG;
+   for (const Robot::Manip &m : r.manips)
+      if (m.name == name) return OCB_ERR_ARG;
+   Robot::Manip m;
+   m.name = name;
+   m.link = ee_link;
+   const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+   memcpy(m.tool, local_tool ? local_tool : ident, sizeof(m.tool));
+   r.manips.push_back(m);
+   return OCB_OK;
+}
+
+extern "C" int ocb_env_set_active_manipulator(ocb_env *env, const char *robot, const char *name)
+{
+   if (!env) return OCB_ERR_ARG;
+   std::lock_guard<std::recursive_mutex> guard(env->mutex);
+   if (!robot || !name || !env->robots.count(robot)) return OCB_ERR_ARG;
+   Robot &r = *env->robots[robot];
+   for (size_t k = 0; k < r.manips.size(); k++)
+      if (r.manips[k].name == name) { r.active_manip = (int) k; return OCB_OK; }
+   return OCB_ERR_ARG;
 }
 
 extern "C" int ocb_env_set_active_dof_values(ocb_env *env, const char *name, const double *values)

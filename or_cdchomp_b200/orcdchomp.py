@@ -27,6 +27,9 @@ _MODULE_EXPORTS = {
     "ocb_env_enable_kinbody": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ocb_env_add_robot": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(OcbRobot), c_double_p]),
     "ocb_env_set_active_dof_values": (C.c_int, [C.c_void_p, C.c_char_p, c_double_p]),
+    "ocb_env_set_link_names": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int]),
+    "ocb_env_add_manipulator": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, c_double_p]),
+    "ocb_env_set_active_manipulator": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "ocb_module_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "ocb_module_destroy": (C.c_int, [C.c_void_p]),
     "ocb_module_send_command": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -79,7 +82,26 @@ class Environment:
         self._keep.append(robot_desc)
         if self.lib.ocb_env_add_robot(self.h, name.encode(), C.byref(robot_desc.struct), dptr(q)):
             raise RuntimeError("could not add robot %r" % name)
+        names = [s.encode() for s in getattr(robot_desc, "names", [])]
+        if len(names) == robot_desc.struct.n_links:
+            arr = (C.c_char_p * len(names))(*names)
+            self.lib.ocb_env_set_link_names(self.h, name.encode(), arr, len(names))
         return _Named(name)
+
+    def AddManipulator(self, robot, name, ee_link, local_tool=None):
+        """RobotBase manipulator: end-effector link (name or index) and GetLocalToolTransform();
+        the first one added is the active manipulator"""
+        rname = _name(robot)
+        if isinstance(ee_link, str):
+            desc = [d for d in self._keep if ee_link in getattr(d, "names", [])]
+            ee_link = desc[-1].names.index(ee_link)
+        tool = as_f64(local_tool if local_tool is not None else [0, 0, 0, 0, 0, 0, 1])
+        if self.lib.ocb_env_add_manipulator(self.h, rname.encode(), name.encode(), int(ee_link), dptr(tool)):
+            raise RuntimeError("could not add manipulator %r" % name)
+
+    def SetActiveManipulator(self, robot, name):
+        if self.lib.ocb_env_set_active_manipulator(self.h, _name(robot).encode(), name.encode()):
+            raise RuntimeError("no such manipulator")
 
     def SetTransform(self, body, pose):
         pose = as_f64(pose)
@@ -141,6 +163,41 @@ class Module:
         if self.h:
             self.lib.ocb_module_destroy(self.h)
             self.h = None
+
+
+class TSR:
+    """A task space region in the text form `create` reads (tsr_create_parse, src/orcdchomp_mod.cpp:3068-3110):
+    manipulator index, body-and-link name, T0_w and Tw_e each as rotation matrix column by column followed by the
+    translation, then the bounds Bw (6 x 2, rows x y z roll pitch yaw).  T0_w / Tw_e: 4 x 4 matrices or poses
+    [x y z qx qy qz qw].  A row of Bw that is all zero makes that entry a hard constraint."""
+
+    def __init__(self, T0_w=None, Tw_e=None, Bw=None, manipindex=0, bodyandlink="NULL"):
+        self.T0_w, self.Tw_e = self._matrix(T0_w), self._matrix(Tw_e)
+        self.Bw = np.zeros((6, 2)) if Bw is None else np.asarray(Bw, dtype=float).reshape(6, 2)
+        self.manipindex, self.bodyandlink = int(manipindex), bodyandlink
+
+    @staticmethod
+    def _matrix(T):
+        if T is None:
+            return np.eye(4)
+        T = np.asarray(T, dtype=float)
+        if T.shape == (4, 4):
+            return T
+        x, y, z, w = T[3:7]
+        M = np.eye(4)
+        M[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        M[:3, 3] = T[:3]
+        return M
+
+    def serialize(self, *unused):
+        out = ["%d" % self.manipindex, self.bodyandlink]
+        for M in (self.T0_w, self.Tw_e):
+            out += [repr(float(M[r, c])) for c in range(3) for r in range(3)]
+            out += [repr(float(M[r, 3])) for r in range(3)]
+        out += [repr(float(v)) for v in self.Bw.reshape(-1)]
+        return " ".join(out)
 
 
 def _name(obj):

@@ -111,8 +111,10 @@ def test_addfield_fromobsarray_cache_and_errors(world, oracle, flavour, tmp_path
         mod.create(robot=robot, adofgoal=goal, n_points=2)
     with pytest.raises(RuntimeError, match="size of adofgoal does not match"):
         mod.create(robot=robot, adofgoal=[0, 1])
-    with pytest.raises(RuntimeError, match="not supported by the B200 engine"):
+    with pytest.raises(RuntimeError, match="Cannot parse start_tsr TSR!"):
         mod.create(robot=robot, adofgoal=goal, start_tsr="x")
+    with pytest.raises(RuntimeError, match="not supported by the B200 engine"):
+        mod.create(robot=robot, adofgoal=goal, start_cost="0x1 0x2")
     with pytest.raises(RuntimeError, match="you must pass a created run!"):
         mod.iterate(run="0x1234", n_iter=1)
     with pytest.raises(RuntimeError, match="Could not find kinbody"):
@@ -228,3 +230,64 @@ def test_trajs_fileformstr_dumps(world, tmp_path):
     assert np.array_equal(final, mod.gettraj(run=h2, no_collision_check=True))
     mod.destroy(run=h)
     mod.destroy(run=h2)
+
+
+def test_tsr_arguments_of_create(world, oracle, flavour):
+    """create ... con_tsr 'all manipee arm' TSR / con_tsr 'start link wam4' TSR / everyn_tsr TSR / start_tsr TSR
+    (mod.cpp:1930-1997, tsr_create_parse 3068-3110) against the oracle given the same constraints as numbers"""
+    env, mod, table, robot, robot_desc = world
+    mod.computedistancefield(kinbody=table, cube_extent=0.02)
+    sd = oracle_field_for_table(oracle, flavour)
+    ee = robot_desc.names.index("wam7")
+    tool = models.pose_make((0.0, 0.0, 0.1), models.quat_from_axis_angle((0, 0, 1), 0.4))
+    env.AddManipulator(robot, "arm", "wam7", tool)
+    start = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    goal = start + np.array([1.0, 0.03, -0.02, 0.04, 0.0, -0.03, 0.02])
+    env.SetActiveDOFValues(robot, start)
+    pe = models.pose_compose(oracle.fk(robot_desc, start)[ee], tool)
+    T0w, Twe = models.pose_make((0, 0, pe[2])), models.pose_make((0, 0, 0), pe[3:7])
+    Bw = np.tile(np.array([-10.0, 10.0]), (6, 1))
+    Bw[[2, 3, 4]] = 0.0  # z, roll, pitch
+    tsr = orcdchomp.TSR(T0w, Twe, Bw)
+    assert len(tsr.serialize().split()) == 38
+    con = capi.make_constraint("all", ee, Bw, T0w=T0w, Twe=Twe, pose_link_ee=tool)
+
+    def reference(cons, n_iter=25):
+        params = capi.default_params(n_points=40, lambda_=100.0, obs_factor=500.0, constraints=cons)
+        run = oracle.Run(robot_desc, params, [sd], start, goal, flavour=flavour)
+        ret, c, _, _ = run.iterate(n_iter)
+        assert ret == 0
+        return run.traj()
+
+    want = reference([con])
+    for kw in (dict(con_tsr=("all manipee arm", tsr)), dict(con_tsr=("all", tsr)), dict(everyn_tsr=tsr)):
+        traj = mod.runchomp(robot=robot, n_iter=25, lambda_=100.0, obs_factor=500.0, n_points=40, adofgoal=list(goal),
+                            no_collision_check=True, **kw)
+        assert np.max(np.abs(traj - want)) <= 1e-6
+    # a bare link, first moving point only
+    elbow = robot_desc.names.index("wam4")
+    q1 = start + (goal - start) / 39
+    Bx = np.tile(np.array([-10.0, 10.0]), (6, 1))
+    Bx[0] = 0.0
+    T_el = oracle.fk(robot_desc, q1)[elbow]
+    tsr_el = orcdchomp.TSR(T_el, models.pose_make(), Bx)
+    traj = mod.runchomp(robot=robot, n_iter=25, lambda_=100.0, obs_factor=500.0, n_points=40, adofgoal=list(goal),
+                        no_collision_check=True, con_tsrs=[("start link wam4", tsr_el), ("all manipee arm", tsr)])
+    want2 = reference([capi.make_constraint("start", elbow, Bx, T0w=T_el), con])
+    assert np.max(np.abs(traj - want2)) <= 1e-6
+    # start_tsr: the start row comes back changed
+    traj = mod.runchomp(robot=robot, n_iter=25, lambda_=100.0, obs_factor=500.0, n_points=40, adofgoal=list(goal),
+                        no_collision_check=True, start_tsr=tsr)
+    want3 = reference([capi.make_constraint("start_tsr", ee, Bw, T0w=T0w, Twe=Twe, pose_link_ee=tool)])
+    assert np.max(np.abs(traj - want3)) <= 1e-6 and np.max(np.abs(traj[0] - start)) > 1e-4
+    # the reference's messages
+    with pytest.raises(RuntimeError, match="con_tsr manip not found!"):
+        mod.create(robot=robot, adofgoal=list(goal), con_tsr=("all manipee hand", tsr))
+    with pytest.raises(RuntimeError, match="con_tsr link not found!"):
+        mod.create(robot=robot, adofgoal=list(goal), con_tsr=("all link nothing", tsr))
+    with pytest.raises(RuntimeError, match="con_tsr first arg must be start, end, or all!"):
+        mod.create(robot=robot, adofgoal=list(goal), con_tsr=("middle", tsr))
+    with pytest.raises(RuntimeError, match="Cannot parse constraint TSR!"):
+        mod.create(robot=robot, adofgoal=list(goal), con_tsr=("all", "0 NULL 1 2 3"))
+    with pytest.raises(RuntimeError, match="You must pass robot before any con_tsrs!"):
+        mod.SendCommand("create con_tsr 'all' '%s' robot BarrettWAM adofgoal '0 0 0 0 0 0 0'" % tsr.serialize())
