@@ -147,9 +147,12 @@ int cd_chomp_init(struct cd_chomp *c);
 int cd_chomp_iterate(struct cd_chomp *c, int do_iteration, double *costp_total, double *costp_obs,
                      double *costp_smooth);
 /* robot->limit_* are ignored (c->jlimit_* rule, as in the reference); of params only epsilon,
- * epsilon_self, obs_factor, obs_factor_self and floating_base (then c->n = 7 + robot->n_dof and
- * the quaternion re-normalisation of mod.cpp:2805-2808 happens inside cd_chomp_iterate) are
- * read; sdfs[i].data are host grids, copied. */
+ * epsilon_self, obs_factor, obs_factor_self, floating_base (then c->n = 7 + robot->n_dof and
+ * the quaternion re-normalisation of mod.cpp:2805-2808 happens inside cd_chomp_iterate) and the
+ * hard constraints are read; sdfs[i].data are host grids, copied.  Constraints: what
+ * cd_chomp_add_constraint + con_tsr (chomp.h:131-132, mod.cpp:1330-1497) would register is given as
+ * data -- params->constraints[] with where = OCB_CON_START / END / ALL (copied); OCB_CON_START_TSR is
+ * only offered by the batch interface. */
 int cd_chomp_b200_set_sphere_cost(struct cd_chomp *c, const ocb_robot *robot, const ocb_params *params,
                                   int n_sdfs, const ocb_sdf *sdfs);
 

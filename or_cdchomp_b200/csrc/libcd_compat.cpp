@@ -174,6 +174,7 @@ struct ChompPrivate
    std::vector<double> pose_parent, axis, dof_coeff, sphere_pos, sphere_radius;
    std::vector<ocb_sdf> sdfs;
    std::vector<std::vector<double>> sdf_data;
+   std::vector<ocb_constraint> constraints;
    /* engine side, made by cd_chomp_init */
    ocb_engine *e = nullptr;
    ocb_batch *b = nullptr;
@@ -303,6 +304,17 @@ extern "C" int cd_chomp_b200_set_sphere_cost(struct cd_chomp *c, const ocb_robot
    p->robot.sphere_pos = p->sphere_pos.data();
    p->robot.sphere_radius = p->sphere_radius.data();
    p->params = *params;
+   /* hard constraints travel as data (ocb_constraint), not as con_eval callbacks; start_tsr would change
+    * which rows T holds and is only offered by the batch interface */
+   p->constraints.clear();
+   for (int i = 0; i < params->n_constraints; i++)
+   {
+      if (!params->constraints) return set_err(-2, "constraints is null");
+      if (params->constraints[i].where == OCB_CON_START_TSR) return set_err(-2, "start_tsr is not offered by the cd_chomp facade");
+      p->constraints.push_back(params->constraints[i]);
+   }
+   p->params.n_constraints = (int) p->constraints.size();
+   p->params.constraints = p->constraints.empty() ? nullptr : p->constraints.data();
    p->sdfs.assign(sdfs, sdfs + n_sdfs);
    p->sdf_data.resize(n_sdfs);
    for (int i = 0; i < n_sdfs; i++)
@@ -322,7 +334,7 @@ extern "C" int cd_chomp_init(struct cd_chomp *c)
    ChompPrivate *p = priv(c);
    if (!p->have_cost) return set_err(-2, "no cost attached: call cd_chomp_b200_set_sphere_cost before cd_chomp_init");
    if (c->cost_pre || c->cost || c->cost_extra || c->cons)
-      return set_err(-2, "host callbacks and constraints cannot run on the device");
+      return set_err(-2, "host callbacks (cost, con_eval) cannot run on the device: pass constraints as ocb_constraint in the params of cd_chomp_b200_set_sphere_cost");
    /* the engine's metric is the module's: D-th derivative only, fixed end points, uniform dt */
    for (int d = 0; d < c->D; d++)
       if (c->wds[d] != ((d < c->D - 1) ? 0.0 : 1.0)) return set_err(-2, "wds other than [0..0,1]");

@@ -185,6 +185,65 @@ def modes():
     np.savez_compressed(os.path.join(OUT, "modes.npz"), **out)
 
 
+def constraint_cases(po_mod, robot, flavour):
+    """the TSR scenarios of constraints.npz: (name, params keywords, constraint list, starts, goals, iterations).
+    Shared with the tests so fixture and checks cannot drift apart."""
+    ee = robot.names.index("wam7")
+    base = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    rng = np.random.default_rng(77)
+    starts = np.repeat(base[None], 2, 0)
+    goals = starts.copy()
+    goals[:, 0] += rng.uniform(0.6, 1.3, 2)
+    goals[:, 1:] += rng.uniform(-0.05, 0.05, (2, 6))
+    tool = models.pose_make((0.0, 0.02, 0.12), models.quat_from_axis_angle((0, 1, 0), 0.3))
+    pe = models.pose_compose(po_mod.fk(robot, base, flavour=flavour)[ee], tool)
+    T0w, Twe = models.pose_make((0, 0, pe[2])), models.pose_make((0, 0, 0), pe[3:7])
+
+    def bw(*held):
+        B = np.tile(np.array([-10.0, 10.0]), (6, 1))
+        for h in held:
+            B[["x", "y", "z", "roll", "pitch", "yaw"].index(h)] = 0.0
+        return B
+
+    upright = capi.make_constraint("all", ee, bw("z", "roll", "pitch"), T0w=T0w, Twe=Twe, pose_link_ee=tool)
+    elbow = robot.names.index("wam4")
+    q1 = starts[0] + (goals[0] - starts[0]) / 39
+    pin = capi.make_constraint("start", elbow, bw("x", "y"), T0w=po_mod.fk(robot, q1, flavour=flavour)[elbow])
+    slide = capi.make_constraint("start_tsr", ee, bw("x", "z", "roll", "pitch", "yaw"),
+                                 T0w=models.pose_make((pe[0], 0, pe[2])), Twe=Twe, pose_link_ee=tool)
+    return [("all", dict(n_points=40, lambda_=100.0, obs_factor=500.0), [upright], starts, goals, 30),
+            ("two_mom", dict(n_points=40, lambda_=200.0, obs_factor=300.0, use_momentum=1), [upright, pin],
+             starts[:1], goals[:1], 30),
+            ("start_tsr", dict(n_points=40, lambda_=150.0, obs_factor=500.0), [slide], starts, goals, 30),
+            ("d2", dict(n_points=36, lambda_=400.0, derivative=2), [upright], starts[:1], goals[:1], 20)]
+
+
+def constraints():
+    """hard TSR constraints (mod.cpp:1330-1784; chomp.c:553-600) from the reference build: here the
+    projection, the dense inverse and LAPACKE_dgesv are the reference's own chomp.c + OpenBLAS"""
+    robot = models.wam7_robot()
+    kin_pose, prims, apos, aext = models.table_scene()
+    sizes, lengths, gpose = models.field_geometry(apos, aext, 0.02, 0.2)
+    gp = models.prims_to_grid_frame(prims, gpose)
+    obs, sdf = po.computedistancefield(capi.make_prims(gp), len(gp), sizes, lengths, 0.02, flavour=FL)
+    sd = capi.SdfDesc(sdf, lengths, models.pose_compose(kin_pose, gpose))
+    out = dict(table_sdf=sdf, table_lengths=np.array(lengths), table_pose=models.pose_compose(kin_pose, gpose))
+    for name, kw, cons, starts, goals, n_iter in constraint_cases(po, robot, FL):
+        params = capi.default_params(constraints=cons, **kw)
+        trajs, costs, vals, jacs = [], [], [], []
+        for r in range(len(starts)):
+            run = po.Run(robot, params, [sd], starts[r], goals[r], flavour=FL)
+            q = starts[r] + 0.37 * (goals[r] - starts[r])
+            v, J = run.constraint_eval(0, q)
+            ret, c, _, _ = run.iterate(n_iter)
+            assert ret == 0
+            trajs.append(run.traj()); costs.append(c); vals.append(v); jacs.append(J)
+            run.close()
+        out.update({name + "_traj": np.array(trajs), name + "_costs": np.array(costs), name + "_val": np.array(vals),
+                    name + "_jac": np.array(jacs)})
+    np.savez_compressed(os.path.join(OUT, "constraints.npz"), **out)
+
+
 def mt():
     g = po.MT(0, flavour=FL)
     raw0 = np.array([g.next() for _ in range(1300)], dtype=np.uint64)
@@ -195,5 +254,5 @@ def mt():
 
 if __name__ == "__main__":
     assert po.available("reference"), "build oracle/_ref first (needs /root/reference)"
-    sdf_kat(); sdf_build(); occupancy(); mesh(); chomp(); modes(); mt()
+    sdf_kat(); sdf_build(); occupancy(); mesh(); chomp(); modes(); constraints(); mt()
     print("golden fixtures written to", OUT)

@@ -238,3 +238,45 @@ def test_constraint_argument_errors(engine, wam7, table):
     b1.close()
     b2.close()
     engine.remove_sdf(sid)
+
+
+def test_golden_constraints(engine, oracle, wam7):
+    """against outputs of the reference's own chomp.c / kin.c / spatial.c / LAPACK build
+    (tests/golden/constraints.npz, generated by tests/golden/make_golden.py)"""
+    import importlib.util
+    from conftest import golden_path
+    spec = importlib.util.spec_from_file_location("make_golden", golden_path("make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(golden_path("constraints.npz"))
+    sid = engine.upload_sdf(capi.SdfDesc(gold["table_sdf"], gold["table_lengths"], gold["table_pose"]))
+    for name, kw, cons, starts, goals, n_iter in mg.constraint_cases(oracle, wam7, "port"):
+        params = capi.default_params(constraints=cons, **kw)
+        b = engine.create_batch(wam7, params, [sid], starts, goals)
+        costs, status = b.iterate(n_iter)
+        assert (status == 0).all()
+        assert np.max(np.abs(b.get_traj() - gold[name + "_traj"])) <= TRAJ_ATOL
+        assert np.allclose(costs, gold[name + "_costs"], rtol=COST_RTOL, atol=0)
+        b.close()
+    engine.remove_sdf(sid)
+
+
+def test_cd_chomp_facade_with_constraints(oracle, flavour, wam7, table):
+    """libcd_b200's cd_chomp facade: constraints travel as data in the params of cd_chomp_b200_set_sphere_cost"""
+    from or_cdchomp_b200 import libcd
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 1)
+    cons = [capi.make_constraint("all", ee, bounds("z", "roll", "pitch"), T0w=T0w, Twe=Twe)]
+    params = capi.default_params(n_points=32, lambda_=150.0, obs_factor=400.0, constraints=cons)
+    run = oracle.Run(wam7, params, [table["desc"]], starts[0], goals[0], flavour=flavour)
+    fac = libcd.ChompRun(wam7, params, [table["desc"]], starts[0], goals[0])
+    for it in range(10):
+        ret, c, tr, _ = run.iterate(1, want_trace=True)
+        rc, cf = fac.iterate(1)
+        assert rc == ret == 0
+        assert np.allclose(cf, tr[0], rtol=1e-8, atol=0)
+        assert np.max(np.abs(fac.traj - run.traj())) <= TRAJ_ATOL
+    fac.close()
+    run.close()
+    bad = capi.default_params(n_points=32, constraints=[capi.make_constraint("start_tsr", ee, bounds("z"))])
+    with pytest.raises(RuntimeError, match="start_tsr is not offered"):
+        libcd.ChompRun(wam7, bad, [table["desc"]], starts[0], goals[0])

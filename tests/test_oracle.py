@@ -339,3 +339,66 @@ def test_sphere_at_rest_is_finite(oracle, flavour, wam7, table):
         ret, c, _, gr = run.iterate(3, want_grads=True)
         assert ret == 0 and np.isfinite(gr).all() and np.isfinite(c).all() and np.isfinite(run.traj()).all()
         run.close()
+
+
+def _constraint_cases(oracle, robot, flavour="port"):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", golden_path("make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.constraint_cases(oracle, robot, flavour)
+
+
+def test_port_matches_golden_constraints(oracle):
+    """hard TSR constraints: the self-contained port (its own projection, dense inverse and pivoted
+    elimination; con_tsr restated from mod.cpp:1330-1497) against fixtures made by the reference build,
+    where chomp.c:553-600, kin.c, spatial.c and LAPACKE_dgesv are the reference's own
+    (tests/golden/constraints.npz)."""
+    gold = np.load(golden_path("constraints.npz"))
+    robot = models.wam7_robot()
+    sd = capi.SdfDesc(gold["table_sdf"], gold["table_lengths"], gold["table_pose"])
+    for name, kw, cons, starts, goals, n_iter in _constraint_cases(oracle, robot):
+        params = capi.default_params(constraints=cons, **kw)
+        for r in range(len(starts)):
+            run = oracle.Run(robot, params, [sd], starts[r], goals[r], flavour="port")
+            q = starts[r] + 0.37 * (goals[r] - starts[r])
+            v, J = run.constraint_eval(0, q)
+            assert np.max(np.abs(v - gold[name + "_val"][r])) <= 1e-12
+            assert np.max(np.abs(J - gold[name + "_jac"][r])) <= 1e-12
+            # the analytic Jacobian is the derivative of the value
+            Jn = np.zeros_like(J)
+            for j in range(len(q)):
+                d = np.zeros(len(q))
+                d[j] = 1e-6
+                Jn[:, j] = (run.constraint_eval(0, q + d)[0] - run.constraint_eval(0, q - d)[0]) / 2e-6
+            assert np.max(np.abs(J - Jn)) <= 1e-7
+            ret, c, _, _ = run.iterate(n_iter)
+            assert ret == 0
+            assert np.max(np.abs(run.traj() - gold[name + "_traj"][r])) <= 1e-9
+            assert np.allclose(c, gold[name + "_costs"][r], rtol=1e-9, atol=0)
+            if name == "start_tsr":
+                assert run.m == params.n_points - 1 and np.max(np.abs(run.traj()[0] - starts[r])) > 1e-3
+            run.close()
+
+
+def test_constraint_projection_zeroes_linearised_constraint(oracle, flavour, wam7, table):
+    """chomp.c:553-600 as a property: after one iteration h(T_old) + J (T_new - T_old) = 0 on every constrained
+    row (when no joint limit interferes), whatever the cost gradient does"""
+    ee = wam7.names.index("wam7")
+    start = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    goal = start + np.array([0.9, 0.2, -0.1, 0.15, 0.1, -0.2, 0.1])
+    Bw = np.tile(np.array([-10.0, 10.0]), (6, 1))
+    Bw[[0, 4, 5]] = 0.0
+    T0w = oracle.fk(wam7, start + 0.5 * (goal - start))[ee]
+    cons = [capi.make_constraint("all", ee, Bw, T0w=T0w)]
+    params = capi.default_params(n_points=24, lambda_=300.0, obs_factor=200.0, constraints=cons)
+    run = oracle.Run(wam7, params, [table["desc"]], start, goal, flavour=flavour)
+    T0 = run.traj()
+    hJ = [run.constraint_eval(0, T0[i]) for i in range(1, 23)]
+    ret, _, _, _ = run.iterate(1)
+    assert ret == 0
+    T1 = run.traj()
+    for k, (h, J) in enumerate(hJ):
+        lin = h + J @ (T1[k + 1] - T0[k + 1])
+        assert np.max(np.abs(lin)) <= 1e-9 * max(1.0, np.max(np.abs(h)))
+    run.close()
