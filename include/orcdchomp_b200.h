@@ -298,6 +298,10 @@ int ocb_batch_get_iterations(ocb_batch *b, int *iterations);
  * part of the algorithm that is not continuous in its own rounding, so this is the
  * diagnostic that tells a well-conditioned run from a chaotic one. */
 int ocb_batch_get_limit_rounds(ocb_batch *b, int *rounds);
+/* Hard constraints: how many waypoint systems (tridiagonal metric) or whole systems (wider metrics) of each
+ * run were singular since the batch was created -- linearly dependent constraint rows; the reference prints
+ * "constraint inversion error!" (chomp.c:582-590) and carries on, the engine skips those rows.  skips [n_runs]. */
+int ocb_batch_get_constraint_skips(ocb_batch *b, int *skips);
 /* per-iteration cost log of the last iterate call: [R][n_iter][3] (total, obs,
  * smooth) as RAVELOG_INFO prints them (mod.cpp:2798).  Enable before iterate. */
 int ocb_batch_enable_trace(ocb_batch *b, int enable);

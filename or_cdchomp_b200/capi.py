@@ -335,6 +335,7 @@ EXPORTS = {
     "ocb_batch_set_lambda": (C.c_int, [C.c_void_p, C.c_double]),
     "ocb_batch_get_iterations": (C.c_int, [C.c_void_p, c_int_p]),
     "ocb_batch_get_limit_rounds": (C.c_int, [C.c_void_p, c_int_p]),
+    "ocb_batch_get_constraint_skips": (C.c_int, [C.c_void_p, c_int_p]),
     "ocb_batch_enable_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "ocb_batch_get_trace": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "ocb_batch_get_traj": (C.c_int, [C.c_void_p, c_double_p]),

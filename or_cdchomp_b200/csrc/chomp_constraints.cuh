@@ -12,8 +12,10 @@
  * Differences of FORM: the frame's Jacobian is never stored in world coordinates -- every joint column
  * [axis; origin x axis] goes straight through the k x 6 map of its constraint; the three 6 x 6 products of
  * the reference collapse to  lin = R_A v + (t_A - p) x (R_A w),  ang = E (R_A w)  with E the 3 x 3 product of
- * the reference's yaw-pitch-roll and quaternion-rate tables.  The linear system is solved by the block with
- * the same row-pivoted elimination LAPACK performs.
+ * the reference's yaw-pitch-roll and quaternion-rate tables.  With a tridiagonal metric (derivative = 1) the
+ * dense system J A^-1 J^T is never formed: the correction comes from a block-tridiagonal sweep over the
+ * waypoints (con_project_tridiag).  Wider metrics build the system and solve it by the block with the same
+ * row-pivoted elimination LAPACK performs.
  */
 #ifndef OCB_CHOMP_CONSTRAINTS_CUH
 #define OCB_CHOMP_CONSTRAINTS_CUH
@@ -329,6 +331,251 @@ __device__ inline int con_solve(double *__restrict__ S, double *__restrict__ b, 
       }
    __syncthreads();
    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Tridiagonal metric: the projection without the dense system.
+ *
+ * The correction the reference applies, d = -A^-1 J^T x with (J A^-1 J^T) x = h (chomp.c:567-599), is the
+ * minimiser of 1/2 d^T A d under J_i d_i = -h_i on every constrained waypoint.  With A tridiagonal
+ * (diagonal a_i, off-diagonal b_i, the same for every dof) its optimality conditions
+ *     b_{i-1} d_{i-1} + a_i d_i + b_i d_{i+1} + J_i^T x_i = 0,     J_i d_i = -h_i
+ * are block tridiagonal.  Eliminating waypoint after waypoint from one end leaves, at waypoint i,
+ *     P_i = a_i I - b^2 N_prev,  r_i = -b v_prev                           (what the eliminated side contributes)
+ *     W = P_i^-1 J_i^T,  Q = J_i W,  N_i = P_i^-1 - W Q^-1 W^T,  v_i = N_i r_i - W Q^-1 h_i
+ *     d_i = -b N_i d_next + v_i
+ * P_i and Q are symmetric positive definite (no pivoting).  O(m n^3) instead of O((k m)^3) work and
+ * m (n^2 + n) instead of (k m)^2 doubles; same solution as the reference's up to rounding.
+ *
+ * Two warps eliminate from the two ends towards the middle waypoint, which sees both sides; the two
+ * substitutions then run outwards, again side by side.  Within a warp every stage spreads the entries of
+ * its small matrix over the lanes, one __syncwarp per stage; both inverses by Gauss-Jordan steps between
+ * two buffers.  Every matrix lives in `scr` (shared memory when the run's workspace has room):
+ * N[m][n][n], v[m][n] (d on return), then one work area per warp. */
+struct ConWork
+{
+   double *B0, *B1, *W, *U, *Q0, *Q1, *rv;
+};
+
+__device__ inline ConWork con_work(double *base, int n, int kmax)
+{
+   ConWork w;
+   w.B0 = base; w.B1 = w.B0 + n * n;
+   w.W = w.B1 + n * n; w.U = w.W + n * kmax;
+   w.Q0 = w.U + n * kmax; w.Q1 = w.Q0 + kmax * kmax;
+   w.rv = w.Q1 + kmax * kmax;
+   return w;
+}
+
+/* one elimination step at waypoint i, executed by one warp: N_i and v_i from up to two eliminated
+ * neighbours (coupling b, their N and v; N == nullptr: none).  Returns 1 when the waypoint's constraint
+ * rows were linearly dependent and have been skipped (the reference's dgesv fails on such a system). */
+__device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__restrict__ Jc, const double *__restrict__ hc,
+                                     const ConWork &w, double *__restrict__ N, double *__restrict__ v, int i, int n,
+                                     double b1, const double *N1, const double *v1,
+                                     double b2, const double *N2, const double *v2)
+{
+   const int lane = threadIdx.x & 31;
+   const int kmax = a.con_kmax, nn = n * n;
+   const float inv_n = 1.0f / n; /* (e + 0.5) * inv_n truncates to the row of entry e for the few hundred entries there are */
+   const double ai = __ldg(a.Aband + 3 * i + 1);
+   const int r0 = a.con_row0[i], k = a.con_row0[i + 1] - r0;
+   const double *J = Jc + (size_t) r0 * n, *h = hc + r0;
+   const float inv_k = 1.0f / (k > 0 ? k : 1);
+   const double bb1 = b1 * b1, bb2 = b2 * b2;
+   for (int e = lane; e < nn; e += 32)
+   {
+      const int r = (int) ((e + 0.5f) * inv_n), c = e - r * n;
+      double p = (r == c) ? ai : 0.0;
+      if (N1) p = fma(-bb1, N1[e], p);
+      if (N2) p = fma(-bb2, N2[e], p);
+      w.B0[e] = p;
+   }
+   if (lane < n)
+   {
+      double r = 0.0;
+      if (N1) r = -b1 * v1[lane];
+      if (N2) r = fma(-b2, v2[lane], r);
+      w.rv[lane] = r;
+   }
+   __syncwarp();
+   /* P^-1 */
+   double *src = w.B0, *dst = w.B1;
+   for (int j = 0; j < n; j++)
+   {
+      const double pj = src[j * n + j];
+      const double piv = __drcp_rn(pj > 0.0 ? pj : 1e-300);
+      for (int e = lane; e < nn; e += 32)
+      {
+         const int r = (int) ((e + 0.5f) * inv_n), c = e - r * n;
+         double out;
+         if (r == j) out = (c == j) ? piv : src[e] * piv;
+         else
+         {
+            const double f = src[r * n + j] * piv;
+            out = (c == j) ? -f : fma(-f, src[j * n + c], src[e]);
+         }
+         dst[e] = out;
+      }
+      __syncwarp();
+      double *t = src; src = dst; dst = t;
+   }
+   const double *Pi = src;
+   bool constrained = k > 0;
+   const double *Qi = w.Q0;
+   if (constrained)
+   {
+      for (int e = lane; e < n * k; e += 32)
+      {
+         const int r = (int) ((e + 0.5f) * inv_k), q = e - r * k;
+         double acc = 0.0;
+         for (int c = 0; c < n; c++) acc = fma(Pi[r * n + c], J[q * n + c], acc);
+         w.W[r * kmax + q] = acc;
+      }
+      __syncwarp();
+      for (int e = lane; e < k * k; e += 32)
+      {
+         const int p = (int) ((e + 0.5f) * inv_k), q = e - p * k;
+         double acc = 0.0;
+         for (int c = 0; c < n; c++) acc = fma(J[p * n + c], w.W[c * kmax + q], acc);
+         w.Q0[p * kmax + q] = acc;
+      }
+      __syncwarp();
+      /* Q^-1; rows that depend on the others show up as a vanishing pivot */
+      double scale = 0.0;
+      for (int j = 0; j < k; j++) scale = fmax(scale, w.Q0[j * kmax + j]);
+      double *qs = w.Q0, *qd = w.Q1;
+      for (int j = 0; j < k; j++)
+      {
+         const double pj = qs[j * kmax + j];
+         if (!(pj > 1e-13 * scale)) { constrained = false; break; } /* uniform: every lane reads the same entry */
+         const double piv = __drcp_rn(pj);
+         for (int e = lane; e < k * k; e += 32)
+         {
+            const int r = (int) ((e + 0.5f) * inv_k), c = e - r * k;
+            double out;
+            if (r == j) out = (c == j) ? piv : qs[r * kmax + c] * piv;
+            else
+            {
+               const double f = qs[r * kmax + j] * piv;
+               out = (c == j) ? -f : fma(-f, qs[j * kmax + c], qs[r * kmax + c]);
+            }
+            qd[r * kmax + c] = out;
+         }
+         __syncwarp();
+         double *t = qs; qs = qd; qd = t;
+      }
+      Qi = qs;
+   }
+   const int skipped = (k > 0 && !constrained) ? 1 : 0;
+   if (constrained)
+   {
+      for (int e = lane; e < n * k; e += 32)
+      {
+         const int r = (int) ((e + 0.5f) * inv_k), q = e - r * k;
+         double acc = 0.0;
+         for (int p = 0; p < k; p++) acc = fma(w.W[r * kmax + p], Qi[p * kmax + q], acc);
+         w.U[r * kmax + q] = acc;
+      }
+      __syncwarp();
+   }
+   for (int e = lane; e < nn; e += 32)
+   {
+      const int r = (int) ((e + 0.5f) * inv_n), c = e - r * n;
+      double acc = Pi[e];
+      if (constrained)
+         for (int p = 0; p < k; p++) acc = fma(-w.U[r * kmax + p], w.W[c * kmax + p], acc);
+      N[e] = acc;
+   }
+   __syncwarp();
+   if (lane < n)
+   {
+      double acc = 0.0;
+      for (int c = 0; c < n; c++) acc = fma(N[lane * n + c], w.rv[c], acc);
+      if (constrained)
+         for (int p = 0; p < k; p++) acc = fma(-w.U[lane * kmax + p], h[p], acc);
+      v[lane] = acc;
+   }
+   __syncwarp();
+   return skipped;
+}
+
+/* the whole projection, called by every thread of the block (it holds block barriers); d is left in the
+ * v rows of scr.  Returns (to thread 0) the number of skipped waypoints. */
+__device__ inline int con_project_tridiag(const OcbChompArgs &a, const double *__restrict__ Jc,
+                                          const double *__restrict__ hc, double *__restrict__ scr, int m, int n)
+{
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int nn = n * n, kmax = a.con_kmax;
+   double *Nall = scr, *vall = Nall + (size_t) m * nn;
+   double *work0 = vall + (size_t) m * n;
+   const size_t work_size = 2 * (size_t) nn + 2 * (size_t) n * kmax + 2 * (size_t) kmax * kmax + n;
+   const bool two = (blockDim.x >= 64) && m >= 3;
+   const int mid = two ? m / 2 : m - 1; /* the waypoint both eliminations stop at (one-sided: the last) */
+   int skipped = 0;
+   if (warp == 0)
+   {
+      const ConWork w = con_work(work0, n, kmax);
+      for (int i = 0; i < mid; i++)
+      {
+         const double b = (i > 0) ? __ldg(a.Aband + 3 * i) : 0.0; /* A[i][i-1] */
+         skipped += con_sweep_step(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n, b,
+                                   i > 0 ? Nall + (size_t) (i - 1) * nn : nullptr, vall + (size_t) (i - 1) * n, 0.0, nullptr, nullptr);
+      }
+   }
+   else if (warp == 1 && two)
+   {
+      const ConWork w = con_work(work0 + work_size, n, kmax);
+      for (int i = m - 1; i > mid; i--)
+      {
+         const double b = (i < m - 1) ? __ldg(a.Aband + 3 * i + 2) : 0.0; /* A[i][i+1] */
+         skipped += con_sweep_step(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n, b,
+                                   i < m - 1 ? Nall + (size_t) (i + 1) * nn : nullptr, vall + (size_t) (i + 1) * n, 0.0, nullptr, nullptr);
+      }
+      if (lane == 0) work0[2 * work_size] = (double) skipped; /* handed to thread 0 below */
+   }
+   __syncthreads();
+   if (warp == 0)
+   {
+      /* the middle waypoint: both sides eliminated, nothing left to couple to -> v is d */
+      const ConWork w = con_work(work0, n, kmax);
+      const int i = mid;
+      const double bl = (i > 0) ? __ldg(a.Aband + 3 * i) : 0.0, br = (i < m - 1) ? __ldg(a.Aband + 3 * i + 2) : 0.0;
+      skipped += con_sweep_step(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n,
+                                bl, i > 0 ? Nall + (size_t) (i - 1) * nn : nullptr, vall + (size_t) (i - 1) * n,
+                                br, (two && i < m - 1) ? Nall + (size_t) (i + 1) * nn : nullptr, vall + (size_t) (i + 1) * n);
+      if (two) skipped += (int) work0[2 * work_size];
+   }
+   __syncthreads();
+   /* substitution outwards from the middle: d_i = -b N_i d_next + v_i, in place */
+   if (warp == 0)
+      for (int i = mid - 1; i >= 0; i--)
+      {
+         const double b = __ldg(a.Aband + 3 * i + 2); /* A[i][i+1] */
+         const double *N = Nall + (size_t) i * nn, *dn = vall + (size_t) (i + 1) * n;
+         if (lane < n)
+         {
+            double acc = 0.0;
+            for (int c = 0; c < n; c++) acc = fma(N[lane * n + c], dn[c], acc);
+            vall[(size_t) i * n + lane] = fma(-b, acc, vall[(size_t) i * n + lane]);
+         }
+         __syncwarp();
+      }
+   else if (warp == 1 && two)
+      for (int i = mid + 1; i < m; i++)
+      {
+         const double b = __ldg(a.Aband + 3 * i); /* A[i][i-1] */
+         const double *N = Nall + (size_t) i * nn, *dn = vall + (size_t) (i - 1) * n;
+         if (lane < n)
+         {
+            double acc = 0.0;
+            for (int c = 0; c < n; c++) acc = fma(N[lane * n + c], dn[c], acc);
+            vall[(size_t) i * n + lane] = fma(-b, acc, vall[(size_t) i * n + lane]);
+         }
+         __syncwarp();
+      }
+   __syncthreads();
+   return skipped;
 }
 
 } /* namespace */

@@ -583,7 +583,8 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
           * which zeroes the linearised constraints at the new T.  Thread per dof for the two solves, thread
           * per waypoint for the rows, the whole block for S and its factorisation (global scratch). ---- */
          const int K = a.con_K;
-         double *Jc = a.con_scratch + (size_t) run * a.con_stride, *hc = Jc + (size_t) K * n, *h0 = hc + K, *S = h0 + K;
+         double *gs = a.con_scratch + (size_t) run * a.con_stride; /* global: J, h, saved h, then S or the sweep's matrices */
+         double *Jc = a.con_jh_smem ? ws : gs, *hc = Jc + (size_t) K * n, *h0 = gs + (size_t) K * (n + 1), *S = h0 + K;
          double *slots = ws + 3 * DIM(a, nsa) * Pp;
          block_band_solve(a, Gs, Pp, m, n);
          __syncthreads();
@@ -600,6 +601,23 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
             if (a.con_row0[t] > a.con_row0[t - 1])
                con_eval_waypoint<FLOAT>(a, Ts, slots, AGc, Pp, t, m, n, inv_lambda, Jc, hc);
          __syncthreads();
+         if (K > 0 && a.con_fast)
+         {
+            /* tridiagonal metric: d = -A^-1 J^T x straight from two sweeps over the waypoints */
+            double *scr = a.con_rec_smem ? ws + a.con_rec_off : S;
+            const int skipped = con_project_tridiag(a, Jc, hc, scr, m, n);
+            if (tid == 0 && skipped) a.con_singular[run] += skipped;
+            const double *d = scr + (size_t) m * n * n;
+            for (int t = tid + 1; t <= m; t += NT)
+               for (int j = 0; j < n; j++)
+               {
+                  const double q = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]) + d[(t - 1) * n + j];
+                  Ts[j * Pp + t] = q;
+                  violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
+               }
+         }
+         else
+         {
          if (K > 0)
          {
             con_build_system(a, Jc, S, m, n);
@@ -635,6 +653,7 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
                Ts[j * Pp + t] = q;
                violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
             }
+         }
       }
       else
 #endif

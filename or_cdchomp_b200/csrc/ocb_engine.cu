@@ -1608,7 +1608,21 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       a.con_K = (int) row_wp.size();
       if (a.con_K > 0)
       {
-         a.con_stride = (size_t) a.con_K * (n + 2) + (size_t) a.con_K * a.con_K;
+         a.con_kmax = 0;
+         for (int i = 0; i < m; i++) a.con_kmax = std::max(a.con_kmax, row0[i + 1] - row0[i]);
+         /* tridiagonal metric: no dense system (chomp_constraints.cuh); OCB_CON_DENSE=1 keeps the reference's form */
+         const char *dense_env = getenv("OCB_CON_DENSE");
+         /* a handful of rows (start / end constraints): the dense system is a few small steps, the sweep always m */
+         const int dense_rows = 24;
+         a.con_fast = (params->derivative == 1 && a.con_K > dense_rows && !(dense_env && dense_env[0] == '1')) ? 1 : 0;
+         if (dense_env && dense_env[0] == '0' && params->derivative == 1) a.con_fast = 1; /* OCB_CON_DENSE=0: the sweep whatever the size */
+         const size_t jh = (size_t) a.con_K * (n + 1), rec = ocb_con_tridiag_scratch(m, n, a.con_kmax);
+         const size_t ws_doubles = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
+         a.con_jh_smem = (a.con_fast && jh <= (size_t) 3 * a.nsa * a.Ppad) ? 1 : 0;
+         a.con_rec_off = a.con_jh_smem ? (int) jh : 0;
+         a.con_rec_smem = (a.con_fast && a.con_rec_off + rec <= ws_doubles) ? 1 : 0;
+         a.con_stride = (size_t) a.con_K * (n + 2) +
+                        (a.con_fast ? (a.con_rec_smem ? 0 : rec) : (size_t) a.con_K * a.con_K);
          if (R * a.con_stride * sizeof(double) > ((size_t) 48 << 30))
          {
             ocb_batch_destroy(b);
@@ -1943,6 +1957,20 @@ extern "C" int ocb_batch_get_limit_rounds(ocb_batch *b, int *rounds)
    if (!b || !rounds) return fail(OCB_ERR_ARG, "null argument");
    CU(cudaSetDevice(b->e->device));
    CU(cudaMemcpyAsync(rounds, b->args.limit_rounds, (size_t) b->args.R * sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
+   CU(cudaStreamSynchronize(b->e->stream));
+   return OCB_OK;
+}
+
+extern "C" int ocb_batch_get_constraint_skips(ocb_batch *b, int *skips)
+{
+   if (!b || !skips) return fail(OCB_ERR_ARG, "null argument");
+   CU(cudaSetDevice(b->e->device));
+   if (!b->args.con_singular)
+   {
+      for (int r = 0; r < b->args.R; r++) skips[r] = 0;
+      return OCB_OK;
+   }
+   CU(cudaMemcpyAsync(skips, b->args.con_singular, (size_t) b->args.R * sizeof(int), cudaMemcpyDeviceToHost, b->e->stream));
    CU(cudaStreamSynchronize(b->e->stream));
    return OCB_OK;
 }

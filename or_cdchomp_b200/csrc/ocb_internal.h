@@ -145,7 +145,13 @@ struct OcbChompArgs
    OcbSdfDev sdf_inline[OCB_INLINE_SDFS];
    /* hard constraints (chomp.c:553-600): con_K stacked rows, waypoint-major; library kernel only */
    int n_con, con_K;
-   int free_start, pad3;      /* start_tsr: P - 1 moving waypoints, the first is the start point (see chomp_iterate_body) */
+   int free_start;            /* start_tsr: P - 1 moving waypoints, the first is the start point (see chomp_iterate_body) */
+   int con_kmax;              /* most rows on one waypoint */
+   /* con_fast: tridiagonal metric -> con_project_tridiag instead of the dense system.  Where its operands live:
+    * con_jh_smem: J and h at the start of the run's shared workspace (over the sphere centres, which the
+    * next forward sweep rewrites); con_rec_smem: the sweep's matrices behind them at con_rec_off; else in
+    * con_scratch */
+   int con_fast, con_jh_smem, con_rec_smem, con_rec_off;
    const OcbConDev *cons;     /* [n_con] */
    const int *con_row0;       /* [m + 1]: first row of each moving waypoint */
    const int *con_row_wp;     /* [con_K]: moving waypoint (0-based) of each row */
@@ -154,6 +160,13 @@ struct OcbChompArgs
    size_t con_stride;
    int *con_singular;         /* [R] iterations whose constraint system had a zero pivot (the reference prints and goes on) */
 };
+
+/* doubles of scratch con_project_tridiag (chomp_constraints.cuh) needs */
+static inline size_t ocb_con_tridiag_scratch(int m, int n, int kmax)
+{
+   /* N and v of every waypoint, two work areas (one per warp), one word for the second warp's count */
+   return (size_t) m * n * n + (size_t) m * n + 2 * (2 * (size_t) n * n + 2 * (size_t) n * kmax + 2 * (size_t) kmax * kmax + n) + 1;
+}
 
 #if !defined(__CUDACC_RTC__) && defined(__cplusplus)
 #include <mutex>

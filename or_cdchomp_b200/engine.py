@@ -273,6 +273,13 @@ class Batch:
         check(self.lib, self.lib.ocb_batch_get_limit_rounds(self.h, out.ctypes.data_as(c_int_p)), "ocb_batch_get_limit_rounds")
         return out
 
+    def get_constraint_skips(self):
+        """per run: constraint systems that were singular (dependent rows) and skipped"""
+        out = np.zeros(self.R, dtype=np.int32)
+        check(self.lib, self.lib.ocb_batch_get_constraint_skips(self.h, out.ctypes.data_as(c_int_p)),
+              "ocb_batch_get_constraint_skips")
+        return out
+
     def get_traj(self, out=None):
         if out is None:
             out = np.empty((self.R, self.P, self.n))
