@@ -568,6 +568,52 @@ def measure_hbm_field(torch, eng, stream, device, with_cpu, steps=3):
     return rec
 
 
+def measure_tsr(torch, eng, stream, device, sid, sd, with_cpu, steps=3):
+    """the cfg2 scene with a hard task-space-region constraint on EVERY waypoint (everyn_tsr:
+    tool height, roll and pitch held -- 'carry the cup upright'), 4096 runs x 100 iterations.  Starts share one arm
+    posture, goals differ mostly in the first joint so that every run can satisfy its constraint."""
+    from or_cdchomp_b200 import capi, models
+    from oracle import pyoracle as po
+    robot = models.wam7_robot()
+    ee = robot.names.index("wam7")
+    R = RUNS_PER_GPU
+    rng = np.random.default_rng(20260217)
+    base = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    starts = np.repeat(base[None], R, 0)
+    goals = starts.copy()
+    goals[:, 0] += rng.uniform(0.6, 1.3, R)
+    goals[:, 1:] += rng.uniform(-0.05, 0.05, (R, 6))
+    flavour = po.best_flavour()
+    pe = po.fk(robot, base, flavour=flavour)[ee]  # set-up only: where the tool is at the start
+    Bw = np.tile(np.array([-10.0, 10.0]), (6, 1))
+    Bw[[2, 3, 4]] = 0.0
+    cons = [capi.make_constraint("all", ee, Bw, T0w=models.pose_make((0, 0, pe[2])), Twe=models.pose_make((0, 0, 0), pe[3:7]))]
+    params = capi.default_params(n_points=N_POINTS, lambda_=LAMBDA, obs_factor=OBS_FACTOR, constraints=cons)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    bb = BatchBench(torch, eng, stream, device, robot, params, [sid], starts, goals)
+    kern_ms, done, failed = bb.timed(N_ITER, steps, 2, flush)
+    skips = int(bb.batch.get_constraint_skips().sum())
+    out_traj = torch.empty((R, N_POINTS, 7), dtype=torch.float64, pin_memory=True).numpy()
+    e2e_s = bb.e2e(N_ITER, 2, out_traj, pinned(torch, starts), pinned(torch, goals))
+    bb.close()
+    del flush
+    rec = {"metric": METRIC, "value": done / (kern_ms * 1e-3), "unit": UNIT,
+           "workload": "cfg2 scene, 4096 WAM7 runs x 100 iterations, every waypoint under a 3-row TSR constraint "
+                       "(294 constraint rows per run; block-tridiagonal projection, library kernel)",
+           "runs": R, "kernel_ms_per_step": kern_ms, "runs_failed_joint_limits": failed, "constraint_rows": 3 * (N_POINTS - 2),
+           "singular_waypoint_systems": skips,
+           "e2e": {"value": done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * R * 7 * 8,
+                   "d2h_bytes_per_step": R * N_POINTS * 7 * 8 + R * 28,
+                   "what": "create+iterate+gettraj+destroy through the C ABI, pinned host buffers, wall clock"}}
+    if with_cpu:
+        k = 8
+        v, dt = cpu_baseline(flavour, robot, params, [sd], starts[:k], goals[:k], N_ITER, threads=1)
+        rec["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if flavour == "reference" else "port",
+                               "sample": "first %d runs x %d iterations, one thread (%.1f s); the reference solves a dense "
+                                         "294 x 294 system per iteration (LAPACKE_dgesv, chomp.c:579)" % (k, N_ITER, dt)}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -578,8 +624,8 @@ def main():
     ap.add_argument("--runs", type=int, default=RUNS_PER_GPU, help="runs per GPU (weak) or in total (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", "--no-sdf", dest="no_extras", action="store_true",
-                    help="headline only: skip the cfg3 / cfg4 / cfg5 / HBM-field sub-records")
-    ap.add_argument("--only", default="", help="comma list of sub-records to run (cfg3,cfg4,cfg5,hbm); default all")
+                    help="headline only: skip the cfg3 / cfg4 / cfg5 / HBM-field / TSR sub-records")
+    ap.add_argument("--only", default="", help="comma list of sub-records to run (cfg3,cfg4,cfg5,hbm,tsr); default all")
     ap.add_argument("--no-jit", action="store_true", help="use the library's own kernel instead of the run-time specialised one")
     ap.add_argument("--shrink", type=float, default=0.05,
                     help="end points drawn in the joint limits shrunk by this fraction (BASELINE: 0.05; experiments only)")
@@ -714,7 +760,7 @@ def main():
                   "runs_failed_joint_limits": s["failed"]}
 
     extras = {}
-    want = [w for w in args.only.split(",") if w] or ["cfg3", "cfg4", "cfg5", "hbm"]
+    want = [w for w in args.only.split(",") if w] or ["cfg3", "cfg4", "cfg5", "hbm", "tsr"]
     with_cpu = not args.no_cpu_baseline
     if rank == 0 and world == 1 and not args.no_extras:   # single-GPU measurements: not repeated under torchrun
         if "cfg3" in want:
@@ -726,6 +772,9 @@ def main():
             extras["cfg5_dense"] = measure_cfg5(torch, eng, stream, device, with_cpu)
         if "hbm" in want:
             extras["cfg2_hbm_field"] = measure_hbm_field(torch, eng, stream, device, with_cpu)
+            eng.trim()
+        if "tsr" in want:
+            extras["cfg2_tsr_constraint"] = measure_tsr(torch, eng, stream, device, sid, sd, with_cpu)
             eng.trim()
 
     if rank == 0:

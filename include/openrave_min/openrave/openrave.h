@@ -81,7 +81,19 @@ public:
 class RobotBase : public KinBody
 {
 public:
+   class Manipulator
+   {
+   public:
+      virtual ~Manipulator() {}
+      virtual const std::string &GetName() const = 0;
+      virtual LinkPtr GetEndEffector() const = 0;
+      virtual Transform GetLocalToolTransform() const = 0;
+   };
+   typedef std::shared_ptr<Manipulator> ManipulatorPtr;
+
    virtual const std::vector<int> &GetActiveDOFIndices() const = 0;
+   virtual const std::vector<ManipulatorPtr> &GetManipulators() const = 0;
+   virtual ManipulatorPtr GetActiveManipulator() const = 0;
 };
 } /* namespace OpenRAVE */
 

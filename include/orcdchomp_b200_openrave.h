@@ -7,6 +7,8 @@
  *                           CalculateJacobian calls of sphere_cost_pre (src/orcdchomp_mod.cpp:
  *                           1022-1049) and restates the bookkeeping of mod::create
  *                           (src/orcdchomp_mod.cpp:2104-2134 dofs, 2180-2210 spheres, 2639-2660 limits).
+ *   ocb_or::tsr_constraint  one con_tsr / start_tsr / everyn_tsr argument (manipulator end effector with its
+ *                           local tool transform, or a bare link) as the engine's ocb_constraint.
  *
  * Header only; include <openrave/openrave.h> (or include/openrave_min/, a declaration-only stand-in
  * used to build and test this file where OpenRAVE is absent) before it.
@@ -183,6 +185,36 @@ inline void extract_robot(const OpenRAVE::RobotBase &robot, const std::vector<Sp
    r.sphere_link = A.sphere_link.data();
    r.sphere_pos = A.sphere_pos.data();
    r.sphere_radius = A.sphere_radius.data();
+}
+
+/* One TSR argument of `create` as the engine's ocb_constraint.  The constrained frame is what the reference's
+ * callbacks read on every evaluation: contsr->manip->GetEndEffectorTransform() = end-effector link transform *
+ * GetLocalToolTransform() (src/orcdchomp_mod.cpp:1384-1385; the active manipulator for start_tsr / everyn_tsr,
+ * 1545, 1701), or contsr->link->GetTransform() (1387).  Pass the manipulator, or a link with manip == nullptr.
+ * where: OCB_CON_START / OCB_CON_END / OCB_CON_ALL for con_tsr 'start' / 'end' / 'all' (1947-1956),
+ * OCB_CON_ALL for everyn_tsr, OCB_CON_START_TSR for start_tsr.  T0w, Twe, Bw: struct tsr as parsed by
+ * tsr_create_parse (3068-3110). */
+inline ocb_constraint tsr_constraint(const RobotArrays &A, int where, const OpenRAVE::RobotBase::Manipulator *manip,
+                                     const OpenRAVE::KinBody::Link *link, const double T0w[7], const double Twe[7],
+                                     const double Bw[6][2])
+{
+   ocb_constraint c;
+   const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+   c.where = where;
+   int or_link = -1;
+   for (int k = 0; k < 7; k++) c.pose_link_ee[k] = ident[k];
+   if (manip)
+   {
+      or_link = manip->GetEndEffector()->GetIndex();
+      pose_from_transform(manip->GetLocalToolTransform(), c.pose_link_ee);
+   }
+   else if (link)
+      or_link = link->GetIndex();
+   if (or_link < 0 || or_link >= (int) A.link_map.size()) throw std::runtime_error("con_tsr link not found!"); /* mod.cpp:1974 */
+   c.link = A.link_map[or_link];
+   for (int k = 0; k < 7; k++) { c.T0w[k] = T0w[k]; c.Twe[k] = Twe[k]; }
+   for (int i = 0; i < 6; i++) { c.Bw[i][0] = Bw[i][0]; c.Bw[i][1] = Bw[i][1]; }
+   return c;
 }
 
 } /* namespace ocb_or */

@@ -89,8 +89,21 @@ struct FakeJoint : KinBody::Joint
    dReal GetValue(int) const override { return value; }
 };
 
+struct FakeManip : RobotBase::Manipulator
+{
+   std::string name;
+   KinBody::LinkPtr ee;
+   Pose tool;
+   const std::string &GetName() const override { return name; }
+   KinBody::LinkPtr GetEndEffector() const override { return ee; }
+   Transform GetLocalToolTransform() const override { return to_transform(tool); }
+};
+
 struct FakeRobot : RobotBase
 {
+   std::vector<RobotBase::ManipulatorPtr> manips;
+   const std::vector<RobotBase::ManipulatorPtr> &GetManipulators() const override { return manips; }
+   RobotBase::ManipulatorPtr GetActiveManipulator() const override { return manips.empty() ? nullptr : manips[0]; }
    std::string name = "probe";
    std::vector<KinBody::LinkPtr> links;
    std::vector<KinBody::JointPtr> joints, passive;
@@ -173,6 +186,21 @@ int main(int argc, char **argv)
    for (int s = 0; s < r.n_spheres; s++)
       printf("sphere %d %.17g %.17g %.17g %.17g\n", r.sphere_link[s], r.sphere_pos[3 * s], r.sphere_pos[3 * s + 1], r.sphere_pos[3 * s + 2], r.sphere_radius[s]);
    printf("map"); for (int i = 0; i < nl; i++) printf(" %d", A.link_map[i]); printf("\n");
+   /* a manipulator on OpenRAVE link 5 with a tool offset: the constraint frame the adapter hands to the engine */
+   {
+      std::shared_ptr<FakeManip> mp(new FakeManip());
+      mp->name = "arm";
+      mp->ee = L[5];
+      mp->tool = random_pose(0.1);
+      rb.manips.push_back(mp);
+      const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+      double Bw[6][2] = {{0, 0}, {-1, 1}, {0, 0}, {0, 0}, {-1, 1}, {-1, 1}};
+      const ocb_constraint c1 = ocb_or::tsr_constraint(A, OCB_CON_ALL, rb.GetActiveManipulator().get(), nullptr, ident, ident, Bw);
+      const ocb_constraint c2 = ocb_or::tsr_constraint(A, OCB_CON_START, nullptr, L[3].get(), ident, ident, Bw);
+      printf("con %d %d", c1.where, c1.link); for (int k = 0; k < 7; k++) printf(" %.17g", c1.pose_link_ee[k]); printf("\n");
+      printf("con %d %d", c2.where, c2.link); for (int k = 0; k < 7; k++) printf(" %.17g", c2.pose_link_ee[k]); printf("\n");
+      printf("tool"); for (int k = 0; k < 7; k++) printf(" %.17g", mp->tool.v[k]); printf("\n");
+   }
    /* reference link poses by OpenRAVE's rule, for three active-dof vectors */
    for (int trial = 0; trial < 3; trial++)
    {

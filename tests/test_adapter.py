@@ -72,6 +72,13 @@ def test_chain_extractor_matches_openrave_rule(oracle, tmp_path, seed):
         else:
             i += 1
     assert trials == 3
+    # ocb_or::tsr_constraint: the manipulator's end effector (OpenRAVE link 5) with its tool transform, a bare link (3)
+    cons = [ln.split()[1:] for ln in lines if ln.startswith("con ")]
+    tool = [float(x) for x in next(ln for ln in lines if ln.startswith("tool")).split()[1:]]
+    assert [int(cons[0][0]), int(cons[0][1])] == [capi.CON_ALL, link_map[5]]
+    assert np.allclose([float(x) for x in cons[0][2:]], tool, atol=0)
+    assert [int(cons[1][0]), int(cons[1][1])] == [capi.CON_START, link_map[3]]
+    assert [float(x) for x in cons[1][2:]] == [0, 0, 0, 0, 0, 0, 1]
 
 
 def test_sphere_table_xml_reader():

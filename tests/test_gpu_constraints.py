@@ -280,3 +280,25 @@ def test_cd_chomp_facade_with_constraints(oracle, flavour, wam7, table):
     bad = capi.default_params(n_points=32, constraints=[capi.make_constraint("start_tsr", ee, bounds("z"))])
     with pytest.raises(RuntimeError, match="start_tsr is not offered"):
         libcd.ChompRun(wam7, bad, [table["desc"]], starts[0], goals[0])
+
+
+def test_dependent_rows_are_skipped_and_counted(engine, oracle, wam7, table):
+    """the same constraint twice: every waypoint's rows are linearly dependent.  The reference's dgesv then fails
+    ("constraint inversion error!", chomp.c:582-590) and it moves on with an unsolved right-hand side; the engine
+    (tridiagonal metric) leaves those waypoints unconstrained, counts them, and stays finite"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 2)
+    c = capi.make_constraint("all", ee, bounds("z", "pitch"), T0w=T0w, Twe=Twe)
+    params = capi.default_params(n_points=30, lambda_=100.0, obs_factor=500.0, constraints=[c, c])
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(5)
+    assert (status == 0).all() and np.isfinite(b.get_traj()).all() and np.isfinite(costs).all()
+    assert (b.get_constraint_skips() == 5 * 28).all()
+    b.close()
+    # the same constraint once: nothing skipped
+    params = capi.default_params(n_points=30, lambda_=100.0, obs_factor=500.0, constraints=[c])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    b.iterate(5)
+    assert (b.get_constraint_skips() == 0).all()
+    b.close()
+    engine.remove_sdf(sid)
