@@ -302,3 +302,24 @@ def test_dependent_rows_are_skipped_and_counted(engine, oracle, wam7, table):
     assert (b.get_constraint_skips() == 0).all()
     b.close()
     engine.remove_sdf(sid)
+
+
+@pytest.mark.parametrize("n_points", [4, 5, 32, 33, 66])
+def test_short_trajectories_both_projection_forms(engine, oracle, flavour, wam7, table, n_points, monkeypatch):
+    """block sizes of one and two warps, one to three moving waypoints: the two-sided sweep degenerates to a
+    one-sided one / to the middle step alone; both forms (OCB_CON_DENSE=0 sweep, =1 dense system) against the oracle"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 2, seed=n_points)
+    cons = [capi.make_constraint("all", ee, bounds("z", "roll", "pitch"), T0w=T0w, Twe=Twe)]
+    params = capi.default_params(n_points=n_points, lambda_=100.0, obs_factor=500.0, constraints=cons)
+    ref = run_oracle(oracle, flavour, wam7, params, table["desc"], starts, goals, 10)
+    sid = engine.upload_sdf(table["desc"])
+    for form in ("0", "1"):
+        monkeypatch.setenv("OCB_CON_DENSE", form)
+        b = engine.create_batch(wam7, params, [sid], starts, goals)
+        costs, status = b.iterate(10)
+        for r, o in enumerate(ref):
+            assert o["ret"] == 0 and status[r] == 0
+            assert np.max(np.abs(b.get_traj()[r] - o["traj"])) <= TRAJ_ATOL, form
+            assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0), form
+        b.close()
+    engine.remove_sdf(sid)
