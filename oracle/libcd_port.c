@@ -624,31 +624,36 @@ int cd_kin_pose_to_xyzypr(const double pose[7], double xyzypr[6])
 int cd_kin_pose_to_xyzypr_J(const double pose[7], double J[6][7])
 {
    double qx = pose[3], qy = pose[4], qz = pose[5], qw = pose[6];
-   double nu, de, as, s;
+   double nu, de, den, dn, nn, as, s;
    int i, j;
    for (i = 0; i < 6; i++) for (j = 0; j < 7; j++) J[i][j] = 0.0;
    J[0][0] = J[1][1] = J[2][2] = 1.0;
-   /* yaw = atan2(nu, de): d = (de dnu - nu dde) / (de^2 + nu^2) */
-   nu = 2.0 * (qw * qz + qx * qy);
+   /* an angle atan2(nu, de) has the gradient dn grad(nu) - nn grad(de), dn = de / (de^2 + nu^2), nn = nu / (de^2 + nu^2);
+    * the factors are applied in the reference's order, so the entries round as its own do */
+   nu = 2.0 * (qw * qz + qx * qy);          /* yaw */
    de = 1.0 - 2.0 * (qy * qy + qz * qz);
-   J[3][3] = de / (de * de + nu * nu) * (2.0 * qy);
-   J[3][4] = de / (de * de + nu * nu) * (2.0 * qx) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qy);
-   J[3][5] = de / (de * de + nu * nu) * (2.0 * qw) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qz);
-   J[3][6] = de / (de * de + nu * nu) * (2.0 * qz);
-   /* pitch = asin(as) */
-   as = 2.0 * (qw * qy - qz * qx);
+   den = de * de + nu * nu;
+   dn = de / den;
+   nn = nu / den;
+   J[3][3] = dn * (2.0 * qy);
+   J[3][4] = dn * (2.0 * qx) - nn * (-4.0 * qy);
+   J[3][5] = dn * (2.0 * qw) - nn * (-4.0 * qz);
+   J[3][6] = dn * (2.0 * qz);
+   as = 2.0 * (qw * qy - qz * qx);          /* pitch = asin(as) */
    s = 1.0 / sqrt(1.0 - as * as);
    J[4][3] = s * 2.0 * (-qz);
    J[4][4] = s * 2.0 * (qw);
    J[4][5] = s * 2.0 * (-qx);
    J[4][6] = s * 2.0 * (qy);
-   /* roll = atan2(nu, de) */
-   nu = 2.0 * (qw * qx + qy * qz);
+   nu = 2.0 * (qw * qx + qy * qz);          /* roll */
    de = 1.0 - 2.0 * (qx * qx + qy * qy);
-   J[5][3] = de / (de * de + nu * nu) * (2.0 * qw) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qx);
-   J[5][4] = de / (de * de + nu * nu) * (2.0 * qz) - nu / (de * de + nu * nu) * (-2.0 * 2.0 * qy);
-   J[5][5] = de / (de * de + nu * nu) * (2.0 * qy);
-   J[5][6] = de / (de * de + nu * nu) * (2.0 * qx);
+   den = de * de + nu * nu;
+   dn = de / den;
+   nn = nu / den;
+   J[5][3] = dn * (2.0 * qw) - nn * (-4.0 * qx);
+   J[5][4] = dn * (2.0 * qz) - nn * (-4.0 * qy);
+   J[5][5] = dn * (2.0 * qy);
+   J[5][6] = dn * (2.0 * qx);
    return 0;
 }
 
