@@ -96,6 +96,12 @@ const char *ocb_module_last_error(void);
  * of spheres found (only the first cap are stored).  Returns 0, or -2 with the reason in err. */
 int ocb_kdata_parse_spheres(const char *xml, int cap, char *link_names, double *pos, double *radius,
                             int *n_out, char *err, size_t err_cap);
+/* A TSR in the text form of the create command, read as tsr_create_parse reads it
+ * (src/orcdchomp_mod.cpp:3068-3110): "manipindex bodyandlink", T0_w as nine rotation entries by column and
+ * three translation entries, the same for Tw_e, then Bw (6 x 2, rows x y z roll pitch yaw).  The two
+ * transforms are returned as poses [x y z qx qy qz qw] (cd_kin_pose_from_dR).  0, or OCB_ERR_ARG when the
+ * text does not hold exactly those 38 fields. */
+int ocb_tsr_parse(const char *text, double T0w[7], double Twe[7], double Bw[12]);
 /* numeric access to a run handle returned by create / createbatch ("%p" text) */
 int ocb_module_run_batch(ocb_module *m, const char *handle, ocb_batch **batch);
 

@@ -1226,6 +1226,16 @@ extern "C" int ocb_env_add_robot(ocb_env *env, const char *name, const ocb_robot
    return OCB_OK;
 }
 
+extern "C" int ocb_tsr_parse(const char *text, double T0w[7], double Twe[7], double Bw[12])
+{
+   Tsr t;
+   if (!text || !T0w || !Twe || !Bw || !parse_tsr(text, t)) return OCB_ERR_ARG;
+   memcpy(T0w, t.T0w, sizeof(t.T0w));
+   memcpy(Twe, t.Twe, sizeof(t.Twe));
+   memcpy(Bw, t.Bw, sizeof(t.Bw));
+   return OCB_OK;
+}
+
 extern "C" int ocb_env_set_link_names(ocb_env *env, const char *robot, const char *const *names, int n_names)
 {
    if (!env) return OCB_ERR_ARG;

@@ -35,6 +35,7 @@ _MODULE_EXPORTS = {
     "ocb_module_send_command": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ocb_module_last_error": (C.c_char_p, []),
     "ocb_module_run_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ocb_tsr_parse": (C.c_int, [C.c_char_p, c_double_p, c_double_p, c_double_p]),
     "ocb_kdata_parse_spheres": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, c_double_p, c_double_p, capi.c_int_p,
                                           C.c_char_p, C.c_size_t]),
 }
@@ -198,6 +199,14 @@ class TSR:
             out += [repr(float(M[r, 3])) for r in range(3)]
         out += [repr(float(v)) for v in self.Bw.reshape(-1)]
         return " ".join(out)
+
+
+def parse_tsr(text):
+    """(T0w pose, Twe pose, Bw 6x2) of a TSR text, as the create command reads it (ocb_tsr_parse)"""
+    T0w, Twe, Bw = np.zeros(7), np.zeros(7), np.zeros(12)
+    if _lib().ocb_tsr_parse(text.encode(), dptr(T0w), dptr(Twe), dptr(Bw)):
+        raise ValueError("Cannot parse TSR!")
+    return T0w, Twe, Bw.reshape(6, 2)
 
 
 def _name(obj):

@@ -78,3 +78,35 @@ def test_module_header_symbols_exported():
     lib = orcdchomp._lib()
     for n in names:
         assert getattr(lib, n) is not None
+
+
+def test_tsr_text_round_trip():
+    """orcdchomp.TSR.serialize() -> the library's reader of the create command's TSR arguments
+    (tsr_create_parse, src/orcdchomp_mod.cpp:3068-3110): rotation by columns, translation, bounds; poses come
+    back as [x y z qx qy qz qw] with the quaternion of cd_kin_quat_from_R (largest component positive)"""
+    import numpy as np
+    from or_cdchomp_b200 import models, orcdchomp
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        q0 = models.quat_from_axis_angle(rng.normal(size=3), rng.uniform(-3.1, 3.1))
+        q1 = models.quat_from_axis_angle(rng.normal(size=3), rng.uniform(-3.1, 3.1))
+        T0w, Twe = models.pose_make(rng.uniform(-1, 1, 3), q0), models.pose_make(rng.uniform(-1, 1, 3), q1)
+        Bw = rng.uniform(-1, 1, (6, 2))
+        Bw[rng.integers(0, 6)] = 0.0
+        text = orcdchomp.TSR(T0w, Twe, Bw, manipindex=trial % 3, bodyandlink="NULL").serialize()
+        assert len(text.split()) == 38
+        a, b, bw = orcdchomp.parse_tsr(text)
+        for got, want in ((a, T0w), (b, Twe)):
+            assert np.allclose(got[:3], want[:3], atol=0)
+            assert min(np.abs(got[3:] - want[3:]).max(), np.abs(got[3:] + want[3:]).max()) < 1e-15 * 8
+            assert got[3 + int(np.argmax(np.abs(got[3:])))] > 0
+        assert np.array_equal(bw, Bw)
+    # 4 x 4 matrices are accepted as well
+    M = np.eye(4)
+    M[:3, 3] = [0.1, 0.2, 0.3]
+    a, b, bw = orcdchomp.parse_tsr(orcdchomp.TSR(M, None, np.zeros((6, 2))).serialize())
+    assert np.allclose(a, [0.1, 0.2, 0.3, 0, 0, 0, 1]) and np.allclose(b, [0, 0, 0, 0, 0, 0, 1])
+    import pytest
+    for bad in ("", "0 NULL 1 2 3", "x NULL " + " ".join(["0"] * 36), "0 NULL " + " ".join(["0"] * 37)):
+        with pytest.raises(ValueError):
+            orcdchomp.parse_tsr(bad)
