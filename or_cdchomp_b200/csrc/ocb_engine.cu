@@ -1559,6 +1559,12 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
          }
       a.band_toeplitz = same ? 1 : 0;
       for (int k = 0; k < W; k++) a.band_row[k] = same ? M.Aband[(size_t) mid * W + k] : 0.0;
+      /* c tridiag(-1, 2, -1): the solve is two weighted running sums (chomp_device.cuh: band_solve_121_scan);
+       * OCB_SOLVE_LDL=1 in the environment keeps the factorised form (development knob) */
+      const char *ldl = getenv("OCB_SOLVE_LDL");
+      const double c = same && bw == 1 ? -a.band_row[0] : 0.0;
+      a.band_121 = (same && bw == 1 && c > 0.0 && a.band_row[2] == -c && a.band_row[1] == 2.0 * c && !(ldl && ldl[0] == '1')) ? 1 : 0;
+      a.band_121_scale = a.band_121 ? 1.0 / ((double) (m + 1) * c) : 0.0;
    }
    a.lambda = params->lambda;
    a.dt = dt;

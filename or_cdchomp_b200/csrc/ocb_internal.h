@@ -114,8 +114,9 @@ struct OcbChompArgs
    double trc_ss, trc_sg, trc_gg;
    /* band_toeplitz: every row of A holds the same band (true for derivative = 1: A = (m+1) tridiag(-1, 2, -1));
     * band_row is that band, read as instruction operands instead of m x (2 bw + 1) table loads */
-   int band_toeplitz, pad2;
+   int band_toeplitz, band_121; /* band_121: A = c tridiag(-1, 2, -1) exactly -> closed-form inverse (band_solve_121_scan) */
    double band_row[2 * OCB_MAX_BW + 1];
+   double band_121_scale;       /* 1 / ((m + 1) c) */
    /* parameters */
    double lambda, dt, eps, eps_self, obs_factor, obs_factor_self, hmc_lambda;
    const double *lim_lo;

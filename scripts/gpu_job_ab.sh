@@ -1,8 +1,9 @@
 #!/bin/bash
+# A/B of a development knob on the headline: bench headline with and without, then the CHOMP suites
 mkdir -p gpurun_out
-for flags in "" "-DJR_NO_TRIG_CACHE"; do
-OCB_JIT_FLAGS="$flags" timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r2_bench_e.json 2> gpurun_out/r2_bench_e.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2_bench_e.json')); print('flags [$flags] value', d['value'], 'kern_ms', d['kernel_ms_per_step'], 'failed', d['runs_failed_joint_limits'])"
+for v in 0 1; do
+  OCB_SOLVE_LDL=$v timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ab_$v.json 2>/dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/ab_$v.json')); print('OCB_SOLVE_LDL=$v value', d['value'], 'kern_ms', d['kernel_ms_per_step'], 'failed', d['runs_failed_joint_limits'])"
 done
-timeout 1200 python -m pytest tests/test_gpu_chomp.py -m gpu -q --timeout=600 -p no:cacheprovider -x 2>&1 | tail -3
+timeout 1500 python -m pytest tests/test_gpu_chomp.py tests/test_gpu_fullsize.py tests/test_gpu_constraints.py -m gpu -q --timeout=900 -p no:cacheprovider 2>&1 | tail -5
