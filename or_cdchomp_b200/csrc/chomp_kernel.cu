@@ -476,6 +476,12 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
    }
    __syncthreads();
 
+   /* Default metric with both end points fixed (band_121 & 2): A = c tridiag(-1, 2, -1) and B = -c (q_start e_1 +
+    * q_goal e_m), so A^-1 (A T + B) = T - L with L the straight line from q_start to q_goal -- exactly, no
+    * stencil and no rounding of a product with A that the solve then undoes.  The update becomes
+    * T -= (A^-1 G_obs / m + T - L) / lambda.  The full gradient G (grad_mode 1) is only formed when asked for. */
+   const bool line_form = !CONS && (a.band_121 & 2) && a.grad_mode != 1 && band_scan_lanes(a, n) >= 2;
+   const double inv_mp1 = 1.0 / (m + 1);
    double cost_obs = 0.0, cost_smooth = 0.0;
    double csum_done = 0.0, ssum_done = 0.0; /* this thread's cost partials of the last completed iteration */
    int red_parity = 0;
@@ -543,7 +549,14 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
 #else
          csum += waypoint_cost<FLOAT, PP>(a, tb, Ts, ws, Gs, t, !final_pass PHASE_PASS);
 #endif
-         if (!final_pass)
+         if (!final_pass && line_form)
+         {
+            /* the smoothness part of the update is T - L in closed form (see line_form): G stays the raw
+             * obstacle gradient, its 1/m goes into the solve's scale */
+            if (a.grad_mode == 2)
+               for (int j = 0; j < n; j++) a.grad_out[((size_t) run * m + (t - 1)) * n + j] = Gs[j * Pp + t] * inv_m;
+         }
+         else if (!final_pass)
          {
             const double bi = __ldg(a.bcoef_i + t - 1), bf = __ldg(a.bcoef_f + t - 1);
             for (int j = 0; j < n; j++)
@@ -661,6 +674,8 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
          auto update = [&](const int j, const int t, double step)
          {
+            if (line_form) /* + A^-1 (A T + B) = T - L, L the straight line between the fixed end points */
+               step += Ts[j * Pp + t] - fma(Ts[j * Pp + P - 1] - Ts[j * Pp], (double) t * inv_mp1, Ts[j * Pp]);
             if (DIM(a, use_momentum))
             {
                step = fma(coef, step, AGs[j * Pp + t]);
@@ -671,7 +686,10 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
             violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
          };
          const int lpd = band_scan_lanes(a, n);
-         if (lpd >= 2)
+         if (line_form)
+            band_solve_121_scan(a, Gs, Pp, m, n, lpd, [&](const int j, const int i, const double ag) { update(j, i + 1, ag); },
+                                a.band_121_scale * inv_m);
+         else if (lpd >= 2)
             band_solve_scan(a, Gs, Pp, m, n, lpd, [&](const int j, const int i, const double ag) { update(j, i + 1, ag); }, Ls, dinv);
          else
          {

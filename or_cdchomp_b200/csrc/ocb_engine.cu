@@ -1565,6 +1565,15 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       const double c = same && bw == 1 ? -a.band_row[0] : 0.0;
       a.band_121 = (same && bw == 1 && c > 0.0 && a.band_row[2] == -c && a.band_row[1] == 2.0 * c && !(ldl && ldl[0] == '1')) ? 1 : 0;
       a.band_121_scale = a.band_121 ? 1.0 / ((double) (m + 1) * c) : 0.0;
+      if (a.band_121)
+      {
+         /* and B = -c (q_start e_1 + q_goal e_m): the smoothness part of the update in closed form (bit 1; chomp_iterate_body) */
+         bool ends = M.bi[0] == -c && M.bf[m - 1] == -c;
+         for (int i = 0; i < m && ends; i++)
+            if ((i > 0 && M.bi[i] != 0.0) || (i < m - 1 && M.bf[i] != 0.0)) ends = false;
+         const char *lf = getenv("OCB_LINE_FORM");
+         if (ends && !(lf && lf[0] == '0')) a.band_121 |= 2;
+      }
    }
    a.lambda = params->lambda;
    a.dt = dt;
