@@ -32,7 +32,7 @@ for r in rows:
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, "r2_launch_shares.txt"), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400, python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n"
-            "# (set-up SDF build; headline: 3 warm-up + 2 timed + 3 end-to-end steps of chomp_iterate_jit; sub-records cfg3 / cfg4 / cfg5 / HBM field)\n"
+            "# (set-up SDF build; headline: 3 warm-up + 2 timed + 3 end-to-end steps of chomp_iterate_jit; sub-records cfg3 / cfg4 / cfg5 / HBM field / TSR-constrained batch -- the latter runs the library kernel chomp_iterate_kernel<128,0,0,0,1>)\n"
             "# per-launch times are cold-cache and serialised: shares, not absolutes\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("%-64s launches %4d  total %10.3f ms  avg %8.3f ms  share %5.1f%%\n" % (k[-64:], v[0], v[1] / 1e6, v[1] / 1e6 / v[0], 100 * v[1] / tot))
