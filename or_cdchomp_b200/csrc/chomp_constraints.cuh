@@ -369,23 +369,31 @@ __device__ inline ConWork con_work(double *base, int n, int kmax)
 
 /* one elimination step at waypoint i, executed by one warp: N_i and v_i from up to two eliminated
  * neighbours (coupling b, their N and v; N == nullptr: none).  Returns 1 when the waypoint's constraint
- * rows were linearly dependent and have been skipped (the reference's dgesv fails on such a system). */
-__device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__restrict__ Jc, const double *__restrict__ hc,
-                                     const ConWork &w, double *__restrict__ N, double *__restrict__ v, int i, int n,
-                                     double b1, const double *N1, const double *v1,
-                                     double b2, const double *N2, const double *v2)
+ * rows were linearly dependent and have been skipped (the reference's dgesv fails on such a system).
+ * NN / KK: the number of dofs / of rows on every waypoint when known at compile time (0: read at run
+ * time) -- with literal bounds the small dot products unroll and their loads overlap. */
+template <int NN, int KK>
+__device__ __forceinline__ int con_sweep_step(const OcbChompArgs &a, const double *__restrict__ Jc,
+                                              const double *__restrict__ hc, const ConWork &w, double *__restrict__ N,
+                                              double *__restrict__ v, int i, int n_rt, double b1, const double *N1,
+                                              const double *v1, double b2, const double *N2, const double *v2)
 {
    const int lane = threadIdx.x & 31;
-   const int kmax = a.con_kmax, nn = n * n;
-   const float inv_n = 1.0f / n; /* (e + 0.5) * inv_n truncates to the row of entry e for the few hundred entries there are */
+   const int n = NN ? NN : n_rt;
+   const int kmax = KK ? KK : a.con_kmax, nn = n * n;
    const double ai = __ldg(a.Aband + 3 * i + 1);
-   const int r0 = a.con_row0[i], k = a.con_row0[i + 1] - r0;
+   const int r0 = a.con_row0[i];
+   const int k = KK ? KK : a.con_row0[i + 1] - r0;
    const double *J = Jc + (size_t) r0 * n, *h = hc + r0;
-   const float inv_k = 1.0f / (k > 0 ? k : 1);
+   /* entry e of a row-major matrix with `cols` columns -> (row, column); exact for the few hundred entries there are */
+   auto split = [](int e, int cols, float inv, int &r, int &c) { r = (int) ((e + 0.5f) * inv); c = e - r * cols; };
+   const float inv_n = 1.0f / n, inv_k = 1.0f / (k > 0 ? k : 1);
    const double bb1 = b1 * b1, bb2 = b2 * b2;
+#pragma unroll
    for (int e = lane; e < nn; e += 32)
    {
-      const int r = (int) ((e + 0.5f) * inv_n), c = e - r * n;
+      int r, c;
+      split(e, n, inv_n, r, c);
       double p = (r == c) ? ai : 0.0;
       if (N1) p = fma(-bb1, N1[e], p);
       if (N2) p = fma(-bb2, N2[e], p);
@@ -399,22 +407,22 @@ __device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__rest
       w.rv[lane] = r;
    }
    __syncwarp();
-   /* P^-1 */
+   /* P^-1: Gauss-Jordan steps between two buffers */
    double *src = w.B0, *dst = w.B1;
+#pragma unroll
    for (int j = 0; j < n; j++)
    {
       const double pj = src[j * n + j];
       const double piv = __drcp_rn(pj > 0.0 ? pj : 1e-300);
+#pragma unroll
       for (int e = lane; e < nn; e += 32)
       {
-         const int r = (int) ((e + 0.5f) * inv_n), c = e - r * n;
+         int r, c;
+         split(e, n, inv_n, r, c);
+         const double f = src[r * n + j] * piv, sjc = src[j * n + c], se = src[e];
          double out;
-         if (r == j) out = (c == j) ? piv : src[e] * piv;
-         else
-         {
-            const double f = src[r * n + j] * piv;
-            out = (c == j) ? -f : fma(-f, src[j * n + c], src[e]);
-         }
+         if (r == j) out = (c == j) ? piv : se * piv;
+         else out = (c == j) ? -f : fma(-f, sjc, se);
          dst[e] = out;
       }
       __syncwarp();
@@ -425,26 +433,33 @@ __device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__rest
    const double *Qi = w.Q0;
    if (constrained)
    {
+#pragma unroll
       for (int e = lane; e < n * k; e += 32)
       {
-         const int r = (int) ((e + 0.5f) * inv_k), q = e - r * k;
+         int r, q;
+         split(e, k, inv_k, r, q);
          double acc = 0.0;
+#pragma unroll
          for (int c = 0; c < n; c++) acc = fma(Pi[r * n + c], J[q * n + c], acc);
          w.W[r * kmax + q] = acc;
       }
       __syncwarp();
       for (int e = lane; e < k * k; e += 32)
       {
-         const int p = (int) ((e + 0.5f) * inv_k), q = e - p * k;
+         int p, q;
+         split(e, k, inv_k, p, q);
          double acc = 0.0;
+#pragma unroll
          for (int c = 0; c < n; c++) acc = fma(J[p * n + c], w.W[c * kmax + q], acc);
          w.Q0[p * kmax + q] = acc;
       }
       __syncwarp();
       /* Q^-1; rows that depend on the others show up as a vanishing pivot */
       double scale = 0.0;
+#pragma unroll
       for (int j = 0; j < k; j++) scale = fmax(scale, w.Q0[j * kmax + j]);
       double *qs = w.Q0, *qd = w.Q1;
+#pragma unroll
       for (int j = 0; j < k; j++)
       {
          const double pj = qs[j * kmax + j];
@@ -452,14 +467,12 @@ __device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__rest
          const double piv = __drcp_rn(pj);
          for (int e = lane; e < k * k; e += 32)
          {
-            const int r = (int) ((e + 0.5f) * inv_k), c = e - r * k;
+            int r, c;
+            split(e, k, inv_k, r, c);
+            const double f = qs[r * kmax + j] * piv, sjc = qs[j * kmax + c], se = qs[r * kmax + c];
             double out;
-            if (r == j) out = (c == j) ? piv : qs[r * kmax + c] * piv;
-            else
-            {
-               const double f = qs[r * kmax + j] * piv;
-               out = (c == j) ? -f : fma(-f, qs[j * kmax + c], qs[r * kmax + c]);
-            }
+            if (r == j) out = (c == j) ? piv : se * piv;
+            else out = (c == j) ? -f : fma(-f, sjc, se);
             qd[r * kmax + c] = out;
          }
          __syncwarp();
@@ -470,30 +483,42 @@ __device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__rest
    const int skipped = (k > 0 && !constrained) ? 1 : 0;
    if (constrained)
    {
+#pragma unroll
       for (int e = lane; e < n * k; e += 32)
       {
-         const int r = (int) ((e + 0.5f) * inv_k), q = e - r * k;
+         int r, q;
+         split(e, k, inv_k, r, q);
          double acc = 0.0;
+#pragma unroll
          for (int p = 0; p < k; p++) acc = fma(w.W[r * kmax + p], Qi[p * kmax + q], acc);
          w.U[r * kmax + q] = acc;
       }
       __syncwarp();
    }
+#pragma unroll
    for (int e = lane; e < nn; e += 32)
    {
-      const int r = (int) ((e + 0.5f) * inv_n), c = e - r * n;
+      int r, c;
+      split(e, n, inv_n, r, c);
       double acc = Pi[e];
       if (constrained)
+      {
+#pragma unroll
          for (int p = 0; p < k; p++) acc = fma(-w.U[r * kmax + p], w.W[c * kmax + p], acc);
+      }
       N[e] = acc;
    }
    __syncwarp();
    if (lane < n)
    {
       double acc = 0.0;
+#pragma unroll
       for (int c = 0; c < n; c++) acc = fma(N[lane * n + c], w.rv[c], acc);
       if (constrained)
+      {
+#pragma unroll
          for (int p = 0; p < k; p++) acc = fma(-w.U[lane * kmax + p], h[p], acc);
+      }
       v[lane] = acc;
    }
    __syncwarp();
@@ -502,8 +527,9 @@ __device__ inline int con_sweep_step(const OcbChompArgs &a, const double *__rest
 
 /* the whole projection, called by every thread of the block (it holds block barriers); d is left in the
  * v rows of scr.  Returns (to thread 0) the number of skipped waypoints. */
-__device__ inline int con_project_tridiag(const OcbChompArgs &a, const double *__restrict__ Jc,
-                                          const double *__restrict__ hc, double *__restrict__ scr, int m, int n)
+template <int NN, int KK>
+__device__ __noinline__ int con_project_tridiag(const OcbChompArgs &a, const double *__restrict__ Jc,
+                                                const double *__restrict__ hc, double *__restrict__ scr, int m, int n)
 {
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int nn = n * n, kmax = a.con_kmax;
@@ -519,7 +545,7 @@ __device__ inline int con_project_tridiag(const OcbChompArgs &a, const double *_
       for (int i = 0; i < mid; i++)
       {
          const double b = (i > 0) ? __ldg(a.Aband + 3 * i) : 0.0; /* A[i][i-1] */
-         skipped += con_sweep_step(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n, b,
+         skipped += con_sweep_step<NN, KK>(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n, b,
                                    i > 0 ? Nall + (size_t) (i - 1) * nn : nullptr, vall + (size_t) (i - 1) * n, 0.0, nullptr, nullptr);
       }
    }
@@ -529,7 +555,7 @@ __device__ inline int con_project_tridiag(const OcbChompArgs &a, const double *_
       for (int i = m - 1; i > mid; i--)
       {
          const double b = (i < m - 1) ? __ldg(a.Aband + 3 * i + 2) : 0.0; /* A[i][i+1] */
-         skipped += con_sweep_step(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n, b,
+         skipped += con_sweep_step<NN, KK>(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n, b,
                                    i < m - 1 ? Nall + (size_t) (i + 1) * nn : nullptr, vall + (size_t) (i + 1) * n, 0.0, nullptr, nullptr);
       }
       if (lane == 0) work0[2 * work_size] = (double) skipped; /* handed to thread 0 below */
@@ -541,7 +567,7 @@ __device__ inline int con_project_tridiag(const OcbChompArgs &a, const double *_
       const ConWork w = con_work(work0, n, kmax);
       const int i = mid;
       const double bl = (i > 0) ? __ldg(a.Aband + 3 * i) : 0.0, br = (i < m - 1) ? __ldg(a.Aband + 3 * i + 2) : 0.0;
-      skipped += con_sweep_step(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n,
+      skipped += con_sweep_step<NN, KK>(a, Jc, hc, w, Nall + (size_t) i * nn, vall + (size_t) i * n, i, n,
                                 bl, i > 0 ? Nall + (size_t) (i - 1) * nn : nullptr, vall + (size_t) (i - 1) * n,
                                 br, (two && i < m - 1) ? Nall + (size_t) (i + 1) * nn : nullptr, vall + (size_t) (i + 1) * n);
       if (two) skipped += (int) work0[2 * work_size];

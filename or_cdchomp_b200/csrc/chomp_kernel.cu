@@ -618,7 +618,12 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
          {
             /* tridiagonal metric: d = -A^-1 J^T x straight from two sweeps over the waypoints */
             double *scr = a.con_rec_smem ? ws + a.con_rec_off : S;
-            const int skipped = con_project_tridiag(a, Jc, hc, scr, m, n);
+            /* the common shapes with their sizes as literals (7 dofs; the same 3 or 6 rows on every waypoint) */
+            const int ku = a.con_kuniform;
+            const int skipped = (n == 7 && ku == 3) ? con_project_tridiag<7, 3>(a, Jc, hc, scr, m, n)
+                              : (n == 7 && ku == 6) ? con_project_tridiag<7, 6>(a, Jc, hc, scr, m, n)
+                              : (n == 7)            ? con_project_tridiag<7, 0>(a, Jc, hc, scr, m, n)
+                                                    : con_project_tridiag<0, 0>(a, Jc, hc, scr, m, n);
             if (tid == 0 && skipped) a.con_singular[run] += skipped;
             const double *d = scr + (size_t) m * n * n;
             for (int t = tid + 1; t <= m; t += NT)

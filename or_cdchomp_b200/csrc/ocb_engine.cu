@@ -1625,6 +1625,9 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
       {
          a.con_kmax = 0;
          for (int i = 0; i < m; i++) a.con_kmax = std::max(a.con_kmax, row0[i + 1] - row0[i]);
+         a.con_kuniform = a.con_kmax;
+         for (int i = 0; i < m; i++)
+            if (row0[i + 1] - row0[i] != a.con_kmax) a.con_kuniform = 0;
          /* tridiagonal metric: no dense system (chomp_constraints.cuh); OCB_CON_DENSE=1 keeps the reference's form */
          const char *dense_env = getenv("OCB_CON_DENSE");
          /* a handful of rows (start / end constraints): the dense system is a few small steps, the sweep always m */

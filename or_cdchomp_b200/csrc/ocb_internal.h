@@ -148,6 +148,7 @@ struct OcbChompArgs
    int n_con, con_K;
    int free_start;            /* start_tsr: P - 1 moving waypoints, the first is the start point (see chomp_iterate_body) */
    int con_kmax;              /* most rows on one waypoint */
+   int con_kuniform, pad4;    /* the number of rows when every moving waypoint carries the same (> 0), else 0 */
    /* con_fast: tridiagonal metric -> con_project_tridiag instead of the dense system.  Where its operands live:
     * con_jh_smem: J and h at the start of the run's shared workspace (over the sphere centres, which the
     * next forward sweep rewrites); con_rec_smem: the sweep's matrices behind them at con_rec_off; else in
