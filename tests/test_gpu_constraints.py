@@ -323,3 +323,22 @@ def test_short_trajectories_both_projection_forms(engine, oracle, flavour, wam7,
             assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0), form
         b.close()
     engine.remove_sdf(sid)
+
+
+def test_long_trajectory_sweep_in_global_scratch(engine, oracle, flavour, wam7, table):
+    """n_points = 256 (cfg4's shape, 8 warps per run), momentum, every waypoint constrained: 762 rows; the sweep's
+    matrices no longer fit the run's shared workspace and live in global scratch"""
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 2, seed=256)
+    cons = [capi.make_constraint("all", ee, bounds("z", "roll", "pitch"), T0w=T0w, Twe=Twe)]
+    params = capi.default_params(n_points=256, lambda_=100.0, obs_factor=500.0, use_momentum=1, constraints=cons)
+    sid = engine.upload_sdf(table["desc"])
+    b = engine.create_batch(wam7, params, [sid], starts, goals)
+    costs, status = b.iterate(8)
+    ref = run_oracle(oracle, flavour, wam7, params, table["desc"], starts, goals, 8)
+    for r, o in enumerate(ref):
+        assert o["ret"] == 0 and status[r] == 0
+        assert np.max(np.abs(b.get_traj()[r] - o["traj"])) <= TRAJ_ATOL
+        assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0)
+    assert (b.get_constraint_skips() == 0).all()
+    b.close()
+    engine.remove_sdf(sid)
