@@ -269,12 +269,19 @@ chomp_tile_cost_kernel(const __grid_constant__ OcbChompArgs a, const int want_gr
    /* own spheres are dealt to the workers four at a time, back and forth over the workers, so
     * that every worker sees every part of the robot (in-range pairs cluster on neighbouring
     * links) and long and short partner sweeps alike */
-   for (int round = 0; round * NW < n_quads; round++)
+   /* full rounds hand every worker a quad; what is left after them (fewer than 4 NW spheres, the ones with the
+    * shortest partner sweeps but the same obstacle work) is split evenly, 1..4 spheres per worker, so that no
+    * worker carries a whole extra quad while the others wait at the barrier */
+   const int full_rounds = n_quads / NW;
+   const int rem_base = full_rounds * NW * 4, rem = nsa - rem_base;
+   const int share = (rem + NW - 1) / NW;
+   for (int round = 0; round < full_rounds + (rem > 0 ? 1 : 0); round++)
    {
-      const int quad = round * NW + ((round & 1) ? NW - 1 - worker : worker);
-      if (quad >= n_quads) continue;
-      const int s0 = quad << 2, se = nsa;
-      /* four own spheres share every partner load of the range sweep */
+      const int widx = (round & 1) ? NW - 1 - worker : worker;
+      const int s0 = (round < full_rounds) ? ((round * NW + widx) << 2) : rem_base + widx * share;
+      const int se = min((round < full_rounds) ? s0 + 4 : s0 + share, nsa);
+      if (s0 >= se) continue;
+      /* (up to) four own spheres share every partner load of the range sweep */
       int sk[4], lk[4];
       double p[4][3], rk[4], f[4][3], cs[4];
 #pragma unroll
