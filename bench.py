@@ -602,6 +602,11 @@ def measure_tsr(torch, eng, stream, device, sid, sd, with_cpu, steps=3):
                        "(294 constraint rows per run; block-tridiagonal projection, library kernel)",
            "runs": R, "kernel_ms_per_step": kern_ms, "runs_failed_joint_limits": failed, "constraint_rows": 3 * (N_POINTS - 2),
            "singular_waypoint_systems": skips,
+           "roofline": roofline_record(algorithmic_bytes_per_run_iter(N_POINTS, 7, robot.n_spheres_active, 1, False), done, kern_ms,
+                                       traffic=load_json("profiles", "traffic.json").get("chomp_tsr_bytes_per_launch"),
+                                       kernel="chomp_iterate_kernel<128,0,0,0,1> (library kernel with the constraint projection)",
+                                       note="same compulsory bytes as the unconstrained iteration (the constraint's operands never leave "
+                                            "the SM); the projection sweep is latency-bound: profiles/r2_tsr_ncu.csv"),
            "e2e": {"value": done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * R * 7 * 8,
                    "d2h_bytes_per_step": R * N_POINTS * 7 * 8 + R * 28,
                    "what": "create+iterate+gettraj+destroy through the C ABI, pinned host buffers, wall clock"}}
