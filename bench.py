@@ -394,10 +394,11 @@ def measure_sdf_build(torch, eng, stream, device, with_cpu=True, n=400):
     out_obs = torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
     out_sdf = torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
     eng.computedistancefield(gp, sizes, lengths, ce, out=(out_obs, out_sdf))
-    t0 = time.perf_counter()
-    for _ in range(2):
+    e2e_s = 1e30
+    for _ in range(3):  # best of three: the 1 GB device-to-host copy shares the host's PCIe / memory with other tenants
+        t0 = time.perf_counter()
         eng.computedistancefield(gp, sizes, lengths, ce, out=(out_obs, out_sdf))
-    e2e_s = (time.perf_counter() - t0) / 2
+        e2e_s = min(e2e_s, time.perf_counter() - t0)
     traffic = (load_json("profiles", "traffic.json").get("sdf_build_bytes_400cubed_r2") or {}).get("total") if n == 400 else None
     rec = {"metric": "sdf_build_mvoxels_per_s", "value": ncell / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "workload": "BASELINE configs[2]: computedistancefield, 64 boxes + 32 spheres, cube_extent %g -> %s voxels"
