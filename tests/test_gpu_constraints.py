@@ -342,3 +342,32 @@ def test_long_trajectory_sweep_in_global_scratch(engine, oracle, flavour, wam7, 
     assert (b.get_constraint_skips() == 0).all()
     b.close()
     engine.remove_sdf(sid)
+
+
+def test_constraints_through_the_multi_engine_interface(oracle, wam7, table):
+    """ocb_multi_*: a constrained batch dealt over several engines in one process gives, in global run order,
+    exactly what one engine gives (devices 0 and 1 when the box has them, else two engines on device 0)"""
+    import torch
+    from or_cdchomp_b200.engine import Engine, MultiEngine
+    ee, starts, goals, T0w, Twe = upright_scene(oracle, wam7, 9, seed=3)
+    cons = [capi.make_constraint("all", ee, bounds("z", "roll", "pitch"), T0w=T0w, Twe=Twe),
+            capi.make_constraint("start_tsr", ee, bounds("x", "z", "roll", "pitch", "yaw"),
+                                 T0w=models.pose_make((oracle.fk(wam7, starts[0])[ee][0], 0, T0w[2])), Twe=Twe)]
+    params = capi.default_params(n_points=40, lambda_=150.0, obs_factor=500.0, constraints=cons)
+    e = Engine(0)
+    sid = e.upload_sdf(table["desc"])
+    b = e.create_batch(wam7, params, [sid], starts, goals)
+    c1, s1 = b.iterate(15)
+    t1 = b.get_traj()
+    b.close()
+    e.close()
+    assert (s1 == 0).all() and np.max(np.abs(t1[:, 0] - starts)) > 1e-4
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    m = MultiEngine(devs)
+    msid = m.upload_sdf(table["desc"])
+    mb = m.create_batch(wam7, params, [msid], starts, goals)
+    c2, s2 = mb.iterate(15)
+    assert np.array_equal(s1, s2) and np.array_equal(c1, c2) and np.array_equal(mb.get_traj(), t1)
+    mb.close()
+    m.remove_sdf(msid)
+    m.close()
