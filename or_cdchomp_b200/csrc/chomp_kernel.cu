@@ -22,8 +22,14 @@
  *     per-joint-frame wrench (F, M) and J^T f is evaluated as axis . (M - o x F)
  *     for every ancestor joint;
  *   - A^-1 G is a banded LDL^T solve (factor computed once on the host), not a
- *     product with an explicit dense inverse;
- *   - A T + B is the banded stencil;  B and trC are evaluated from the end points;
+ *     product with an explicit dense inverse; for the default metric c tridiag(-1, 2, -1)
+ *     it IS the product with the explicit inverse, whose entries are known in closed
+ *     form, evaluated as two weighted running sums (band_solve_121_scan);
+ *   - A T + B is the banded stencil;  B and trC are evaluated from the end points; with
+ *     the default metric and fixed end points A^-1 (A T + B) = T - (straight line between
+ *     the end points) and no stencil is evaluated in the update (line_form);
+ *   - hard constraints (chomp.c:553-600) are a block-tridiagonal sweep over the waypoints
+ *     instead of a dense system when the metric is tridiagonal (chomp_constraints.cuh);
  *   - each SDF sample reads its 4 cells once and yields value and gradient.
  */
 #include "chomp_device.cuh"
