@@ -166,6 +166,14 @@ int ocb_engine_enable_jit(ocb_engine *e, int on);
  * csrc/chomp_jit_robot.cuh turns into straight-line code.  Returns the length of the text (0: this
  * robot takes the table-driven kernel), copies at most cap-1 bytes into buf (may be NULL). */
 long ocb_debug_jit_robot_header(const ocb_robot *robot, const ocb_params *params, char *buf, size_t cap);
+/* The smoothness metric of a run as the engine builds it (host only, no device needed; for inspection and
+ * tests): band of A [m][2 derivative + 1], its dense inverse [m][m], the coefficient vectors of B
+ * (B = bi (x) q_start + bf (x) q_goal) [m] each, closed_form bit 0: A = c tridiag(-1, 2, -1) (the solve is the
+ * product with the closed-form inverse), bit 1: B = -c (q_start e_1 + q_goal e_m) (the smoothness part of the
+ * update is T minus the straight line), c.  m = n_points - 2, or n_points - 1 with free_start (start_tsr).
+ * Any output may be NULL. */
+int ocb_debug_metric(int n_points, int derivative, int free_start, double *Aband, double *Ainv, double *bi,
+                     double *bf, int *closed_form, double *c);
 
 /* --- SDF residency (replaces mod::sdfs[], mod.cpp:584-586 / 716-718 / 836) --- */
 /* copies the grid to HBM; *id indexes it in later calls */

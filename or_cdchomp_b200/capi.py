@@ -348,6 +348,8 @@ EXPORTS = {
     "ocb_batch_copy_run_traj_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ocb_engine_launch_count": (C.c_long, [C.c_void_p]),
     "ocb_debug_jit_robot_header": (C.c_long, [C.POINTER(OcbRobot), C.POINTER(OcbParams), C.c_char_p, C.c_size_t]),
+    "ocb_debug_metric": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p,
+                                   c_double_p]),
     # several GPUs in one process (csrc/ocb_multi.cpp)
     "ocb_multi_last_error": (C.c_char_p, []),
     "ocb_multi_create": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_void_p)]),

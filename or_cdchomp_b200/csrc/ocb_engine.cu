@@ -1787,6 +1787,52 @@ extern "C" long ocb_debug_jit_robot_header(const ocb_robot *robot, const ocb_par
    return (long) h.size();
 }
 
+/* the smoothness metric of a run as the engine builds it (host only; for inspection and tests): band of A
+ * [m][2D+1], dense inverse [m][m] from the banded factor, B's two coefficient vectors [m] each, and whether
+ * the closed forms of the default metric apply (bit 0: A = c tridiag(-1, 2, -1); bit 1: B = -c (q_s e_1 + q_g e_m)).
+ * free_start: the start_tsr layout (m = n_points - 1, no initial boundary row).  Any output may be NULL. */
+extern "C" int ocb_debug_metric(int n_points, int derivative, int free_start, double *Aband, double *Ainv, double *bi,
+                                double *bf, int *closed_form, double *c_out)
+{
+   if (n_points < 3 || derivative < 1 || derivative > OCB_MAX_BW) return fail(OCB_ERR_ARG, "bad metric shape");
+   const int m = n_points - 2 + (free_start ? 1 : 0);
+   Metric M;
+   const int rc = build_metric(m, derivative, 1.0 / (n_points - 1), M, free_start != 0);
+   if (rc) return fail(OCB_ERR_ARG, "smoothness metric is not positive definite (code %d)", rc);
+   if (Aband) memcpy(Aband, M.Aband.data(), M.Aband.size() * sizeof(double));
+   if (Ainv)
+   {
+      std::vector<double> inv;
+      metric_inverse(M, inv);
+      memcpy(Ainv, inv.data(), inv.size() * sizeof(double));
+   }
+   if (bi) memcpy(bi, M.bi.data(), m * sizeof(double));
+   if (bf) memcpy(bf, M.bf.data(), m * sizeof(double));
+   if (closed_form || c_out)
+   {
+      const int bw = derivative, W = 2 * bw + 1, mid = m / 2;
+      bool same = m > 2 * bw + 1;
+      for (int i = 0; i < m && same; i++)
+         for (int k = -bw; k <= bw; k++)
+         {
+            if (i + k < 0 || i + k >= m) continue;
+            if (M.Aband[(size_t) i * W + k + bw] != M.Aband[(size_t) mid * W + k + bw]) { same = false; break; }
+         }
+      const double c = (same && bw == 1) ? -M.Aband[(size_t) mid * W] : 0.0;
+      int flags = (same && bw == 1 && c > 0.0 && M.Aband[(size_t) mid * W + 2] == -c && M.Aband[(size_t) mid * W + 1] == 2.0 * c) ? 1 : 0;
+      if (flags)
+      {
+         bool ends = M.bi[0] == -c && M.bf[m - 1] == -c;
+         for (int i = 0; i < m && ends; i++)
+            if ((i > 0 && M.bi[i] != 0.0) || (i < m - 1 && M.bf[i] != 0.0)) ends = false;
+         if (ends) flags |= 2;
+      }
+      if (closed_form) *closed_form = flags;
+      if (c_out) *c_out = c;
+   }
+   return OCB_OK;
+}
+
 extern "C" int ocb_batch_uses_jit(const ocb_batch *b) { return (b && b->jit_kernel) ? 1 : 0; }
 extern "C" int ocb_batch_tile_width(const ocb_batch *b) { return (b && b->args.tiled) ? b->args.tile_w : 0; }
 

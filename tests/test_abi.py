@@ -201,3 +201,70 @@ def test_kernel_sources_compile_under_nvrtc():
     jit_cpp = open(os.path.join(csrc, "ocb_jit.cpp")).read()
     passed = set(_re.findall(r'\{"([A-Za-z_]+)", ', jit_cpp)) | set(_re.findall(r"-DOCB_JIT_([A-Za-z_]+)=", jit_cpp))
     assert used - {"f", "FLAGS"} <= passed, used - passed
+
+
+def test_metric_and_its_closed_forms():
+    """host side of the smoothness metric (build_metric / metric_inverse, no device): against the reference's
+    definition A = sum_d w_d / N_d K_d^T K_d, B = ... K_d^T E_d (chomp.c:239-340) built densely here, and the
+    closed forms the kernels use for the default metric -- (A^-1)_ij = min(i,j)(m+1-max(i,j))/((m+1)c) and
+    A^-1 (A T + B) = T - straight line"""
+    import ctypes as C
+    import numpy as np
+    from or_cdchomp_b200 import capi
+    lib = capi.load_library()
+
+    def metric(P, D, free):
+        m = P - 2 + free
+        W = 2 * D + 1
+        band, inv, bi, bf = np.zeros((m, W)), np.zeros((m, m)), np.zeros(m), np.zeros(m)
+        flags, c = C.c_int(), C.c_double()
+        assert lib.ocb_debug_metric(P, D, free, capi.dptr(band), capi.dptr(inv), capi.dptr(bi), capi.dptr(bf),
+                                    C.byref(flags), C.byref(c)) == 0
+        A = np.zeros((m, m))
+        for i in range(m):
+            for k in range(-D, D + 1):
+                if 0 <= i + k < m:
+                    A[i, i + k] = band[i, k + D]
+        return A, inv, bi, bf, flags.value, c.value
+
+    def dense_reference(P, D, free):
+        """chomp.c:239-340 with wds = [0..0,1]: K_d by repeated differencing with boundary rows; inits[0] absent when free"""
+        m, dt = P - 2 + free, 1.0 / (P - 1)
+        K, Ei, Ef = np.eye(m), np.zeros(m), np.zeros(m)   # level -1: identity on the moving points
+        for d in range(D):
+            has_i = 0 if (d == 0 and free) else 1
+            prev = K.shape[0]
+            cur = prev - 1 + has_i + 1
+            Dm = np.zeros((cur, prev))
+            ci, cf = np.zeros(cur), np.zeros(cur)
+            if has_i:
+                Dm[0, 0] = 1.0 / dt
+            for i in range(prev - 1):
+                Dm[has_i + i, i], Dm[has_i + i, i + 1] = -1.0 / dt, 1.0 / dt
+            Dm[cur - 1, prev - 1] = -1.0 / dt
+            K, Ei, Ef = Dm @ K, Dm @ Ei, Dm @ Ef
+            if d == 0:
+                if has_i:
+                    Ei[0] += -1.0 / dt
+                Ef[cur - 1] += 1.0 / dt
+        w = 1.0 / K.shape[0]
+        return w * K.T @ K, w * K.T @ Ei, w * K.T @ Ef
+
+    for P, D, free in ((100, 1, 0), (40, 1, 1), (50, 2, 0), (30, 3, 0), (5, 1, 0), (256, 1, 0)):
+        A, inv, bi, bf, flags, c = metric(P, D, free)
+        Ar, bir, bfr = dense_reference(P, D, free)
+        m = A.shape[0]
+        assert np.allclose(A, Ar, rtol=1e-13, atol=1e-9) and np.allclose(bi, bir, rtol=1e-13, atol=1e-9)
+        assert np.allclose(bf, bfr, rtol=1e-13, atol=1e-9)
+        assert np.allclose(inv @ A, np.eye(m), atol=1e-9)
+        assert flags == (3 if (D == 1 and not free and m > 3) else 0), (P, D, free, flags)
+        if flags == 3:
+            i = np.arange(1, m + 1)
+            closed = np.minimum.outer(i, i) * (m + 1 - np.maximum.outer(i, i)) / ((m + 1) * c)
+            assert np.allclose(inv, closed, rtol=1e-11, atol=0)
+            rng = np.random.default_rng(P)
+            qs, qg, T = rng.normal(size=3), rng.normal(size=3), rng.normal(size=(m, 3))
+            B = np.outer(bi, qs) + np.outer(bf, qg)
+            line = qs[None] + (qg - qs)[None] * (i[:, None] / (m + 1))
+            assert np.allclose(inv @ (A @ T + B), T - line, atol=1e-9)
+    assert lib.ocb_debug_metric(2, 1, 0, None, None, None, None, None, None) != 0
