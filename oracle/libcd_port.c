@@ -14,6 +14,11 @@
  * Differences that are deliberate and documented:
  *   - BLAS/LAPACK calls are replaced by the straightforward triple loops /
  *     Gauss-Jordan inverse below (the reference links an unpinned system BLAS).
+ *   - a constraint with k = 0 rows (a TSR none of whose bounds is [0, 0]) adds nothing here.  In the
+ *     reference cblas_dgemv(CblasTrans, k = 0, ...) at chomp.c:594-596 returns before scaling its
+ *     output ("quick return if possible"), so cons_delta keeps the previous constraint's
+ *     correction -- or, for the first constraint of the list, uninitialised memory -- and chomp.c:597-598
+ *     applies it once more at that constraint's waypoint.  Not reproduced (and not by the engine).
  *
  * Each function cites the reference lines it follows (paths relative to the
  * reference root).

@@ -371,3 +371,37 @@ def test_constraints_through_the_multi_engine_interface(oracle, wam7, table):
     mb.close()
     m.remove_sdf(msid)
     m.close()
+
+
+def test_tree_robot_prismatic_mimic_branch(engine, oracle, flavour, table):
+    """a constraint on each branch of a tree with a prismatic joint and a mimic joint: the frames come through a
+    reloaded branch frame, the columns include a prismatic one (zero angular part) and a dof that two joints share"""
+    robot = models.prismatic_test_robot()
+    sd = capi.SdfDesc(table["sdf"], table["lengths"], models.pose_make((-0.5, -0.6, 0.1)))
+    start = np.array([0.1, 0.3, 0.2, -0.4])
+    goals = start[None] + np.array([[0.12, 0.25, 0.1, 0.15], [-0.1, -0.2, 0.15, 0.2], [0.1, 0.2, -0.12, -0.25]])
+    starts = np.repeat(start[None], 3, 0)
+    tip, tool = robot.names.index("armA2"), robot.names.index("tool")
+    fk0 = oracle.fk(robot, start)
+    offset = models.pose_make((0.0, 0.05, 0.0), models.quat_from_axis_angle((1, 0, 0), 0.2))
+    cons = [capi.make_constraint("all", tip, bounds("z"), T0w=fk0[tip]),
+            capi.make_constraint("start", tool, bounds("x"), T0w=models.pose_compose(fk0[tool], offset), pose_link_ee=offset)]
+    params = capi.default_params(n_points=33, lambda_=200.0, obs_factor=300.0, epsilon=0.15, constraints=cons)
+    sid = engine.upload_sdf(sd)
+    for env in ("0", "1"):
+        import os
+        os.environ["OCB_CON_DENSE"] = env
+        try:
+            b = engine.create_batch(robot, params, [sid], starts, goals)
+        finally:
+            del os.environ["OCB_CON_DENSE"]
+        costs, status = b.iterate(25)
+        ref = run_oracle(oracle, flavour, robot, params, sd, starts, goals, 25)
+        for r, o in enumerate(ref):
+            assert (o["ret"] == 0) == (status[r] == 0)
+            if o["ret"] == 0:
+                assert np.max(np.abs(b.get_traj()[r] - o["traj"])) <= TRAJ_ATOL, env
+                assert np.allclose(costs[r], o["costs"], rtol=COST_RTOL, atol=0), env
+        assert any(o["ret"] == 0 for o in ref)
+        b.close()
+    engine.remove_sdf(sid)
