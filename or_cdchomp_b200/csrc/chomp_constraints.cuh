@@ -160,8 +160,8 @@ __device__ inline bool con_applies(const OcbConDev &c, int i, int m)
 /* Values h and Jacobian rows J (row length n) of every constraint on moving waypoint t (column t of the
  * [item][waypoint] arrays), written at the waypoint's rows of the run's stacked system; then
  * h += -1/lambda * J AG_t  (chomp.c:562-565).  The joint frames of waypoint t are those the forward
- * sweep of this iteration left in the workspace. */
-template <bool FLOAT>
+ * sweep of this iteration left in the workspace (or, SAVE_FRAMES, rebuilt here). */
+template <bool FLOAT, bool SAVE_FRAMES>
 __device__ inline void con_eval_waypoint(const OcbChompArgs &a, const double *__restrict__ Ts,
                                          double *__restrict__ slots, const double *__restrict__ AGc,
                                          int Pp, int t, int m, int n, double inv_lambda,
@@ -186,7 +186,9 @@ __device__ inline void con_eval_waypoint(const OcbChompArgs &a, const double *__
          for (int j = 0; j <= c.joint; j++)
          {
             const OcbJointDev &J = a.joints[j];
-            fk_step<false, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
+            /* SAVE_FRAMES: no forward sweep has left the branch frames of this waypoint in `slots` (tiled path):
+             * this walk saves them itself, the second one reloads them */
+            fk_step<SAVE_FRAMES, FLOAT>(J, Ts[J.dof * Pp + t], slots, Pp, t, R, tr, ax, org, Ts + t, Pp);
             if (j == c.joint) con_frame(c, R, tr, f);
          }
       double *Jr = Jc + (size_t) row * n;
@@ -602,6 +604,99 @@ __device__ __noinline__ int con_project_tridiag(const OcbChompArgs &a, const dou
       }
    __syncthreads();
    return skipped;
+}
+
+/* The constrained update of one run by its whole block (chomp.c:525-605 with constraints): on entry Gs holds the
+ * complete gradient G (barrier done).  AG = A^-1 G (or the momentum form, leapfrog_first is cleared); constraint
+ * values h and Jacobians J at the current T; the correction -A^-1 J^T x with (J A^-1 J^T) x = h - J AG / lambda;
+ * T -= AG / lambda + A^-1 J^T x, which zeroes the linearised constraints at the new T.  Tridiagonal metric:
+ * con_project_tridiag; else the dense system in global scratch, solved by the block.  ws: the run's shared
+ * workspace when J / h / the sweep's matrices may live there (con_jh_smem / con_rec_smem), else unused;
+ * slots: the saved branch frames of the forward sweep ([12 slot][Pp]; SAVE_FRAMES: scratch for them).
+ * Returns this thread's joint-limit violation flag. */
+template <bool FLOAT, bool SAVE_FRAMES>
+__device__ __forceinline__ int con_update(const OcbChompArgs &a, const int run, double *__restrict__ Ts,
+                                          double *__restrict__ Gs, double *__restrict__ AGs, double *ws, double *slots,
+                                          double *red, int *ired, const int Pp, const int m, const int n,
+                                          const double inv_lambda, int &leapfrog_first)
+{
+   const int tid = threadIdx.x, NT = blockDim.x;
+   const int K = a.con_K;
+   int violated = 0;
+   double *gs = a.con_scratch + (size_t) run * a.con_stride; /* global: J, h, saved h, then S or the sweep's matrices */
+   double *Jc = a.con_jh_smem ? ws : gs, *hc = Jc + (size_t) K * n, *h0 = gs + (size_t) K * (n + 1), *S = h0 + K;
+   block_band_solve(a, Gs, Pp, m, n);
+   __syncthreads();
+   const double *AGc = Gs;
+   if (a.use_momentum)
+   {
+      const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
+      for (int t = tid + 1; t <= m; t += NT)
+         for (int j = 0; j < n; j++) AGs[j * Pp + t] = fma(coef, Gs[j * Pp + t], AGs[j * Pp + t]);
+      leapfrog_first = 0;
+      AGc = AGs;
+   }
+   for (int t = tid + 1; t <= m && K > 0; t += NT)
+      if (a.con_row0[t] > a.con_row0[t - 1])
+         con_eval_waypoint<FLOAT, SAVE_FRAMES>(a, Ts, slots, AGc, Pp, t, m, n, inv_lambda, Jc, hc);
+   __syncthreads();
+   if (K > 0 && a.con_fast)
+   {
+      /* tridiagonal metric: d = -A^-1 J^T x straight from two sweeps over the waypoints */
+      double *scr = a.con_rec_smem ? ws + a.con_rec_off : S;
+      /* the common shapes with their sizes as literals (7 dofs; the same 3 or 6 rows on every waypoint) */
+      const int ku = a.con_kuniform;
+      const int skipped = (n == 7 && ku == 3) ? con_project_tridiag<7, 3>(a, Jc, hc, scr, m, n)
+                        : (n == 7 && ku == 6) ? con_project_tridiag<7, 6>(a, Jc, hc, scr, m, n)
+                        : (n == 7)            ? con_project_tridiag<7, 0>(a, Jc, hc, scr, m, n)
+                                              : con_project_tridiag<0, 0>(a, Jc, hc, scr, m, n);
+      if (tid == 0 && skipped) a.con_singular[run] += skipped;
+      const double *d = scr + (size_t) m * n * n;
+      for (int t = tid + 1; t <= m; t += NT)
+         for (int j = 0; j < n; j++)
+         {
+            const double q = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]) + d[(t - 1) * n + j];
+            Ts[j * Pp + t] = q;
+            violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
+         }
+      return violated;
+   }
+   if (K > 0)
+   {
+      con_build_system(a, Jc, S, m, n);
+      for (int e = tid; e < K; e += NT) h0[e] = hc[e];
+   }
+   __syncthreads();
+   if (K > 0 && con_solve(S, hc, K, red, ired))
+   {
+      /* zero pivot: dgesv leaves the right-hand side as it was and the reference carries on with it */
+      __syncthreads();
+      for (int e = tid; e < K; e += NT) hc[e] = h0[e];
+      if (tid == 0) a.con_singular[run]++;
+      __syncthreads();
+   }
+   for (int t = tid + 1; t <= m; t += NT)
+   {
+      const int r0 = K > 0 ? a.con_row0[t - 1] : 0, r1 = K > 0 ? a.con_row0[t] : 0;
+      for (int j = 0; j < n; j++)
+      {
+         Ts[j * Pp + t] = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]);
+         double d = 0.0;
+         for (int r = r0; r < r1; r++) d += Jc[(size_t) r * n + j] * hc[r];
+         Gs[j * Pp + t] = d;
+      }
+   }
+   __syncthreads();
+   block_band_solve(a, Gs, Pp, m, n);
+   __syncthreads();
+   for (int t = tid + 1; t <= m; t += NT)
+      for (int j = 0; j < n; j++)
+      {
+         const double q = Ts[j * Pp + t] - Gs[j * Pp + t];
+         Ts[j * Pp + t] = q;
+         violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
+      }
+   return violated;
 }
 
 } /* namespace */

@@ -596,89 +596,9 @@ __device__ __forceinline__ void chomp_iterate_body(const OcbChompArgs &a)
       int violated = 0;
 #ifndef OCB_JIT
       if (CONS)
-      {
-         /* ---- the same with hard constraints (chomp.c:553-600): AG first, then the constraint values h and
-          * Jacobians J at the current T; S = J A^-1 J^T; S x = h - J AG / lambda; T -= AG / lambda + A^-1 J^T x,
-          * which zeroes the linearised constraints at the new T.  Thread per dof for the two solves, thread
-          * per waypoint for the rows, the whole block for S and its factorisation (global scratch). ---- */
-         const int K = a.con_K;
-         double *gs = a.con_scratch + (size_t) run * a.con_stride; /* global: J, h, saved h, then S or the sweep's matrices */
-         double *Jc = a.con_jh_smem ? ws : gs, *hc = Jc + (size_t) K * n, *h0 = gs + (size_t) K * (n + 1), *S = h0 + K;
-         double *slots = ws + 3 * DIM(a, nsa) * Pp;
-         block_band_solve(a, Gs, Pp, m, n);
-         __syncthreads();
-         const double *AGc = Gs;
-         if (DIM(a, use_momentum))
-         {
-            const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
-            for (int t = tid + 1; t <= m; t += NT)
-               for (int j = 0; j < n; j++) AGs[j * Pp + t] = fma(coef, Gs[j * Pp + t], AGs[j * Pp + t]);
-            leapfrog_first = 0;
-            AGc = AGs;
-         }
-         for (int t = tid + 1; t <= m && K > 0; t += NT)
-            if (a.con_row0[t] > a.con_row0[t - 1])
-               con_eval_waypoint<FLOAT>(a, Ts, slots, AGc, Pp, t, m, n, inv_lambda, Jc, hc);
-         __syncthreads();
-         if (K > 0 && a.con_fast)
-         {
-            /* tridiagonal metric: d = -A^-1 J^T x straight from two sweeps over the waypoints */
-            double *scr = a.con_rec_smem ? ws + a.con_rec_off : S;
-            /* the common shapes with their sizes as literals (7 dofs; the same 3 or 6 rows on every waypoint) */
-            const int ku = a.con_kuniform;
-            const int skipped = (n == 7 && ku == 3) ? con_project_tridiag<7, 3>(a, Jc, hc, scr, m, n)
-                              : (n == 7 && ku == 6) ? con_project_tridiag<7, 6>(a, Jc, hc, scr, m, n)
-                              : (n == 7)            ? con_project_tridiag<7, 0>(a, Jc, hc, scr, m, n)
-                                                    : con_project_tridiag<0, 0>(a, Jc, hc, scr, m, n);
-            if (tid == 0 && skipped) a.con_singular[run] += skipped;
-            const double *d = scr + (size_t) m * n * n;
-            for (int t = tid + 1; t <= m; t += NT)
-               for (int j = 0; j < n; j++)
-               {
-                  const double q = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]) + d[(t - 1) * n + j];
-                  Ts[j * Pp + t] = q;
-                  violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
-               }
-         }
-         else
-         {
-         if (K > 0)
-         {
-            con_build_system(a, Jc, S, m, n);
-            for (int e = tid; e < K; e += NT) h0[e] = hc[e];
-         }
-         __syncthreads();
-         if (K > 0 && con_solve(S, hc, K, red, ired))
-         {
-            /* zero pivot: dgesv leaves the right-hand side as it was and the reference carries on with it */
-            __syncthreads();
-            for (int e = tid; e < K; e += NT) hc[e] = h0[e];
-            if (tid == 0) a.con_singular[run]++;
-            __syncthreads();
-         }
-         for (int t = tid + 1; t <= m; t += NT)
-         {
-            const int r0 = K > 0 ? a.con_row0[t - 1] : 0, r1 = K > 0 ? a.con_row0[t] : 0;
-            for (int j = 0; j < n; j++)
-            {
-               Ts[j * Pp + t] = fma(-inv_lambda, AGc[j * Pp + t], Ts[j * Pp + t]);
-               double d = 0.0;
-               for (int r = r0; r < r1; r++) d += Jc[(size_t) r * n + j] * hc[r];
-               Gs[j * Pp + t] = d;
-            }
-         }
-         __syncthreads();
-         block_band_solve(a, Gs, Pp, m, n);
-         __syncthreads();
-         for (int t = tid + 1; t <= m; t += NT)
-            for (int j = 0; j < n; j++)
-            {
-               const double q = Ts[j * Pp + t] - Gs[j * Pp + t];
-               Ts[j * Pp + t] = q;
-               violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
-            }
-         }
-      }
+         /* ---- the same with hard constraints (chomp.c:553-600): chomp_constraints.cuh ---- */
+         violated = con_update<FLOAT, false>(a, run, Ts, Gs, AGs, ws, ws + 3 * DIM(a, nsa) * Pp, red, ired, Pp, m, n,
+                                             inv_lambda, leapfrog_first);
       else
 #endif
       {

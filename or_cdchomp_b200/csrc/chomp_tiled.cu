@@ -27,6 +27,7 @@
  * worker touches accumulators owned by another one.
  */
 #include "chomp_device.cuh"
+#include "chomp_constraints.cuh"
 
 namespace
 {
@@ -563,11 +564,21 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
       }
    }
    __syncthreads();
+   int violated = 0;
+   if (a.con_K > 0)
+   {
+      /* ---- the same with hard constraints (chomp.c:553-600; chomp_constraints.cuh): the branch frames of the
+       * constrained waypoints are rebuilt into global scratch, the constraint system lives there too ---- */
+      double *slots = a.con_scratch + (size_t) run * a.con_stride + a.con_slots_off;
+      violated = a.floating ? con_update<true, true>(a, run, Ts, Gs, AGs, nullptr, slots, red, ired, Pp, m, n, inv_lambda, leapfrog_first)
+                            : con_update<false, true>(a, run, Ts, Gs, AGs, nullptr, slots, red, ired, Pp, m, n, inv_lambda, leapfrog_first);
+   }
+   else
+   {
    block_band_solve(a, Gs, Pp, m, n);
    __syncthreads();
 
    /* ---- momentum / plain update (chomp.c:525-548, 604-605) ---- */
-   int violated = 0;
    {
       const double coef = (leapfrog_first ? 0.5 : 1.0) * inv_lambda;
       for (int t = tid + 1; t <= m; t += NT)
@@ -583,6 +594,7 @@ chomp_run_update_kernel(const __grid_constant__ OcbChompArgs a, const int iter, 
             Ts[j * Pp + t] = q;
             violated |= (q < __ldg(a.lim_lo + j)) | (q > __ldg(a.lim_hi + j));
          }
+   }
    }
    const int any_violation = __syncthreads_or(violated);
    int rounds = 0;

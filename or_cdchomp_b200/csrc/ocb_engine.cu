@@ -1636,11 +1636,18 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
          if (dense_env && dense_env[0] == '0' && params->derivative == 1) a.con_fast = 1; /* OCB_CON_DENSE=0: the sweep whatever the size */
          const size_t jh = (size_t) a.con_K * (n + 1), rec = ocb_con_tridiag_scratch(m, n, a.con_kmax);
          const size_t ws_doubles = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
-         a.con_jh_smem = (a.con_fast && jh <= (size_t) 3 * a.nsa * a.Ppad) ? 1 : 0;
+         /* a sphere model too large for the persistent kernel takes the tiled path (decided below by the same
+          * test): its update kernel has no forward sweep's workspace, so everything lives in global scratch,
+          * including the branch frames the constraint evaluation rebuilds for itself */
+         a.ws_stride = ws_doubles;
+         const bool will_tile = ocb_chomp_smem_bytes(&a) > (size_t) e->smem_optin;
+         a.con_jh_smem = (!will_tile && a.con_fast && jh <= (size_t) 3 * a.nsa * a.Ppad) ? 1 : 0;
          a.con_rec_off = a.con_jh_smem ? (int) jh : 0;
-         a.con_rec_smem = (a.con_fast && a.con_rec_off + rec <= ws_doubles) ? 1 : 0;
+         a.con_rec_smem = (!will_tile && a.con_fast && a.con_rec_off + rec <= ws_doubles) ? 1 : 0;
          a.con_stride = (size_t) a.con_K * (n + 2) +
                         (a.con_fast ? (a.con_rec_smem ? 0 : rec) : (size_t) a.con_K * a.con_K);
+         a.con_slots_off = a.con_stride;
+         if (will_tile) a.con_stride += (size_t) 12 * a.n_slots * a.Ppad;
          if (R * a.con_stride * sizeof(double) > ((size_t) 48 << 30))
          {
             ocb_batch_destroy(b);
@@ -1705,10 +1712,10 @@ extern "C" int ocb_batch_create(ocb_engine *e, const ocb_robot *robot, const ocb
     * one SM's shared memory the iteration is tiled over waypoints (chomp_tiled.cu). */
    a.ws_stride = (size_t) (3 * a.nsa + 12 * a.n_slots + 6 * a.ng) * a.Ppad;
    b->smem = ocb_chomp_smem_bytes(&a);
-   if (b->smem > (size_t) e->smem_optin && (a.con_K > 0 || a.free_start))
+   if (b->smem > (size_t) e->smem_optin && a.free_start)
    {
       ocb_batch_destroy(b);
-      return fail(OCB_ERR_ARG, "hard constraints need the run in one SM's shared memory (%d spheres, %d waypoints, %d dofs)",
+      return fail(OCB_ERR_ARG, "start_tsr needs the run in one SM's shared memory (%d spheres, %d waypoints, %d dofs)",
                   a.nsa, P, n);
    }
    if (b->smem > (size_t) e->smem_optin)

@@ -160,6 +160,7 @@ struct OcbChompArgs
    const double *Ainv;        /* [m][m] dense inverse of the metric (only the entries between constrained waypoints are read) */
    double *con_scratch;       /* [R][con_stride]: J (con_K x n), h, saved h, S (con_K x con_K) */
    size_t con_stride;
+   size_t con_slots_off;      /* tiled path: where, in a run's scratch, the constraint evaluation keeps its branch frames */
    int *con_singular;         /* [R] iterations whose constraint system had a zero pivot (the reference prints and goes on) */
 };
 

@@ -405,3 +405,40 @@ def test_tree_robot_prismatic_mimic_branch(engine, oracle, flavour, table):
         assert any(o["ret"] == 0 for o in ref)
         b.close()
     engine.remove_sdf(sid)
+
+
+def test_constraints_on_the_tiled_path(engine, oracle, flavour, table):
+    """a 200-sphere arm does not fit the persistent kernel: the constrained update runs in the tiled path's
+    update kernel, with the branch frames, the rows and the sweep's matrices in global scratch; both projection
+    forms, plain and momentum, against the oracle"""
+    robot = models.dense_sphere_arm(200, seed=5)
+    ee = robot.names.index("wam7")
+    base = np.array([0.4, 0.9, 0.1, 1.4, 0.2, -0.5, 0.3])
+    starts = np.repeat(base[None], 2, 0)
+    goals = starts + np.array([[0.5, 0.03, -0.02, 0.04, 0.0, -0.03, 0.02], [0.7, -0.04, 0.03, -0.02, 0.03, 0.02, -0.04]])
+    pe = oracle.fk(robot, base)[ee]
+    cons = [capi.make_constraint("all", ee, bounds("z", "roll", "pitch"), T0w=models.pose_make((0, 0, pe[2])),
+                                 Twe=models.pose_make((0, 0, 0), pe[3:7]))]
+    sid = engine.upload_sdf(table["desc"])
+    import os
+    for kw in (dict(), dict(use_momentum=1)):
+        params = capi.default_params(n_points=48, lambda_=300.0, obs_factor=100.0, epsilon=0.2, constraints=cons, **kw)
+        ref = run_oracle(oracle, flavour, robot, params, table["desc"], starts, goals, 5)
+        for form in ("0", "1"):
+            os.environ["OCB_CON_DENSE"] = form
+            try:
+                b = engine.create_batch(robot, params, [sid], starts, goals)
+            finally:
+                del os.environ["OCB_CON_DENSE"]
+            assert b.tile_width() > 0 and not b.uses_jit()
+            costs, status = b.iterate(5)
+            for r, o in enumerate(ref):
+                assert o["ret"] == 0 and status[r] == 0
+                assert np.max(np.abs(b.get_traj()[r] - o["traj"])) <= TRAJ_ATOL, (kw, form)
+                assert np.allclose(costs[r], o["costs"], rtol=1e-7, atol=0), (kw, form)
+            b.close()
+    # start_tsr stays with the persistent kernel
+    bad = capi.default_params(n_points=48, constraints=[capi.make_constraint("start_tsr", ee, bounds("z"))])
+    with pytest.raises(RuntimeError, match="start_tsr needs the run in one SM"):
+        engine.create_batch(robot, bad, [sid], starts, goals)
+    engine.remove_sdf(sid)
