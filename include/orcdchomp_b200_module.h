@@ -39,10 +39,12 @@
  *     carries an affine_transform group, x y z qw qx qy qz, as mod.cpp:2912-2956);
  *   - trajs_fileformstr writes the waypoints before every iteration in the same XML layout
  *     (joint_values group only, full precision, mod.cpp:2769-2795), one launch per iteration;
- *   - con_tsr, start_tsr, everyn_tsr and
- *     start_cost are recognised and rejected with an error
- *     (out of scope for the hot path); ee_force,
- *     ee_force_at and ee_torque_weights are accepted and ignored, as in the
+ *   - con_tsr 'start|end|all [manipee M | link L]' TSR, everyn_tsr TSR and start_tsr TSR are read with the
+ *     reference's grammar, TSR text format and error texts (mod.cpp:1930-1997, 3068-3110) and run on the
+ *     device (ocb_params.constraints); the stand-in environment learns link names and manipulators through
+ *     ocb_env_set_link_names / ocb_env_add_manipulator / ocb_env_set_active_manipulator;
+ *   - start_cost (a host callback evaluated every iteration, mod.cpp:1787-1792) is recognised and rejected
+ *     with an error; ee_force, ee_force_at and ee_torque_weights are accepted and ignored, as in the
  *     reference (mod.cpp:1323).
  */
 #ifndef ORCDCHOMP_B200_MODULE_H
