@@ -788,6 +788,7 @@ def main():
         abytes = algorithmic_bytes_per_run_iter(P, n, robot.n_spheres_active, 1, False)
         tr = load_json("profiles", "traffic.json")
         roofline = roofline_record(abytes, h["local_done"], h["kern_ms"], traffic=tr.get("chomp_iterate_kernel_bytes_per_launch"),
+                                   kernel="chomp_iterate_jit" if h["kernel_kind"].startswith("run-time") else "chomp_iterate_kernel",
                                    note="fp64-issue/latency bound, not HBM bound: see roofline_fp64 for the second ceiling")
         ops = load_json("profiles", "r2_fp64_ops.json")
         fp64 = None
